@@ -1,0 +1,183 @@
+"""Python mirror of the C ABI (tests, bench, Python callers).  All compute happens in libgsi.so on
+the GPU; numpy / torch are used only for buffers.  The unit of work follows the reference:
+``Context.precompute`` == compute_eigens() over a batch of users
+(precompute_local_threads.cpp:100-213) and returns what the out_eigen_ records hold."""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+
+class GsiError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("gsi error %d: %s" % (code, msg))
+        self.code = code
+
+
+@dataclass
+class Records:
+    """Batch of out_eigen_ records (README.md:14-19).  Record of user u:
+    sig_min[offsets[u]:offsets[u+1]], lam[lam_off[u]:+k[u]], vec[vec_off[u]:+n*k].reshape(n,k)."""
+
+    offsets: np.ndarray
+    items: np.ndarray
+    sig_min: np.ndarray
+    k: np.ndarray
+    lam_off: np.ndarray
+    vec_off: np.ndarray
+    lam: np.ndarray
+    vec: np.ndarray
+
+    def n(self, u: int) -> int:
+        return int(self.offsets[u + 1] - self.offsets[u])
+
+    def lam_of(self, u: int) -> np.ndarray:
+        return self.lam[self.lam_off[u]: self.lam_off[u] + self.k[u]]
+
+    def vec_of(self, u: int) -> np.ndarray:
+        n, k = self.n(u), int(self.k[u])
+        return self.vec[self.vec_off[u]: self.vec_off[u] + n * k].reshape(n, k)
+
+    def sig_of(self, u: int) -> np.ndarray:
+        return self.sig_min[self.offsets[u]: self.offsets[u + 1]]
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return ctypes.c_void_p(a.ctypes.data)
+    return ctypes.c_void_p(int(a.data_ptr()))     # torch tensor
+
+
+def upper_bounds(offsets: np.ndarray):
+    """(lam_cap, vec_cap) that always suffice: sum max(n,2), sum n*max(n,2)."""
+    n = np.diff(np.asarray(offsets, dtype=np.int64))
+    m = np.maximum(n, 2)
+    return int(m.sum()), int((n * m).sum())
+
+
+class Context:
+    """One per GPU (gsi_create).  ``stream``: a raw cudaStream_t handle (e.g.
+    ``torch.cuda.current_stream().cuda_stream``) or None for a private stream."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self._lib.gsi_create(ctypes.byref(h), device, ctypes.c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise GsiError(rc, (self._lib.gsi_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gsi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise GsiError(rc, (self._lib.gsi_last_error(self._h) or b"").decode())
+
+    @property
+    def version(self) -> str:
+        return self._lib.gsi_version().decode()
+
+    def set_workspace_limit(self, nbytes: int):
+        self._check(self._lib.gsi_set_workspace_limit(self._h, nbytes))
+
+    def sync(self):
+        self._check(self._lib.gsi_sync(self._h))
+
+    # ---- weights (precompute_local.cpp:113-158) ----
+    def set_weights(self, w):
+        """Dense (N+1)x(N+1) float64 table: numpy array (copied to the device) or CUDA torch tensor
+        (borrowed)."""
+        if isinstance(w, np.ndarray):
+            w = np.ascontiguousarray(w, dtype=np.float64)
+            assert w.ndim == 2 and w.shape[0] == w.shape[1]
+            self._check(self._lib.gsi_set_weights_host(self._h, _ptr(w), w.shape[0]))
+        else:
+            assert w.is_cuda and w.is_contiguous() and w.dim() == 2 and w.shape[0] == w.shape[1]
+            assert str(w.dtype) == "torch.float64"
+            self._keep = [w]
+            self._check(self._lib.gsi_set_weights_device(self._h, _ptr(w), w.shape[0]))
+
+    def set_weights_edges(self, m1, m2, w) -> int:
+        m1 = np.ascontiguousarray(m1, dtype=np.int32)
+        m2 = np.ascontiguousarray(m2, dtype=np.int32)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        rows = ctypes.c_int(0)
+        self._check(self._lib.gsi_set_weights_edges(self._h, _ptr(m1), _ptr(m2), _ptr(w), len(w), ctypes.byref(rows)))
+        return rows.value
+
+    # ---- precompute ----
+    def precompute(self, offsets, items) -> Records:
+        """Host arrays in, host arrays out (gsi_precompute_host)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        items = np.ascontiguousarray(items, dtype=np.int32)
+        nu = len(offsets) - 1
+        lam_cap, vec_cap = upper_bounds(offsets)
+        sig = np.zeros(int(offsets[-1]), dtype=np.float64)
+        k = np.zeros(nu, dtype=np.int32)
+        lam_off = np.zeros(nu, dtype=np.int64)
+        vec_off = np.zeros(nu, dtype=np.int64)
+        lam = np.zeros(lam_cap, dtype=np.float64)
+        vec = np.zeros(vec_cap, dtype=np.float64)
+        tot = np.zeros(2, dtype=np.int64)
+        self._check(self._lib.gsi_precompute_host(self._h, nu, _ptr(offsets), _ptr(items), _ptr(sig), _ptr(k),
+                                                  _ptr(lam_off), _ptr(vec_off), _ptr(lam), lam_cap, _ptr(vec), vec_cap,
+                                                  _ptr(tot)))
+        return Records(offsets, items, sig, k, lam_off, vec_off, lam[: tot[0]], vec[: tot[1]])
+
+    def precompute_device(self, offsets_host, d_items, d_sig, d_k, d_lam_off, d_vec_off, d_lam, d_vec):
+        """Everything resident on the device (torch CUDA tensors); returns (lam_used, vec_used)."""
+        offsets_host = np.ascontiguousarray(offsets_host, dtype=np.int64)
+        tot = np.zeros(2, dtype=np.int64)
+        self._check(self._lib.gsi_precompute_device(
+            self._h, len(offsets_host) - 1, _ptr(offsets_host), _ptr(d_items), _ptr(d_sig), _ptr(d_k),
+            _ptr(d_lam_off), _ptr(d_vec_off), _ptr(d_lam), d_lam.numel(), _ptr(d_vec), d_vec.numel(), _ptr(tot)))
+        return int(tot[0]), int(tot[1])
+
+    def precompute_stream(self, offsets, items, sink):
+        """gsi_precompute_stream: ``sink(chunk: RecordChunk) -> int`` is called once per chunk."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        items = np.ascontiguousarray(items, dtype=np.int32)
+
+        def _cb(_opaque, chunk_p):
+            return int(sink(chunk_p.contents) or 0)
+
+        cb = _lib.RECORD_SINK(_cb)
+        self._check(self._lib.gsi_precompute_stream(self._h, len(offsets) - 1, _ptr(offsets), _ptr(items), cb, None))
+
+    # ---- measurement ----
+    def timing_enable(self, on: bool = True):
+        self._check(self._lib.gsi_timing_enable(self._h, int(on)))
+
+    def timing_reset(self):
+        self._check(self._lib.gsi_timing_reset(self._h))
+
+    def timing(self) -> dict:
+        n = len(_lib.T_NAMES)
+        ms = np.zeros(n, dtype=np.float64)
+        launches = np.zeros(n, dtype=np.int64)
+        samples = np.zeros(n, dtype=np.int64)
+        self._check(self._lib.gsi_timing_get(self._h, _ptr(ms), _ptr(launches), _ptr(samples)))
+        return {name: dict(ms=float(ms[i]), launches=int(launches[i]), samples=int(samples[i]))
+                for i, name in enumerate(_lib.T_NAMES)}
+
+    def measure_fp64_tflops(self, dmma: bool = False) -> float:
+        v = ctypes.c_double(0)
+        self._check(self._lib.gsi_measure_fp64_tflops(self._h, int(dmma), ctypes.byref(v)))
+        return v.value

@@ -1,0 +1,692 @@
+// libgsi.so -- C ABI (include/gsi.h) over the sm_100a kernels.  Host side: context, planner
+// (bucketing users by n, chunking by workspace), launch sequencing, staging.  No CPU fallback:
+// every entry point needs a CUDA device.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+
+#include "gsi_internal.cuh"
+#include "kern_bj.cuh"
+#include "kern_eig_cta.cuh"
+#include "kern_out.cuh"
+
+static thread_local std::string g_tls_err;
+
+int gsi_fail(gsi_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    g_tls_err = buf;
+    return code;
+}
+
+// ---- timing spans --------------------------------------------------------------------------
+static cudaEvent_t take_event(gsi_ctx* ctx) {
+    if (!ctx->ev_pool.empty()) { cudaEvent_t e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+GsiSpan::GsiSpan(gsi_ctx* c, int cls_, int64_t n_launches, int64_t n_timed) : ctx(c), cls(cls_), launches(n_launches) {
+    ctx->t_launch[cls] += n_launches;
+    if (ctx->timing) {
+        ctx->t_samples[cls] += (n_timed < 0 ? n_launches : n_timed);
+        a = take_event(ctx); b = take_event(ctx); cudaEventRecord(a, ctx->stream);
+    }
+}
+void GsiSpan::end() {
+    if (a) { cudaEventRecord(b, ctx->stream); ctx->spans.push_back({cls, a, b}); a = nullptr; }
+}
+void gsi_count_launch(gsi_ctx* ctx, int cls, int64_t n) { ctx->t_launch[cls] += n; }
+
+static void drain_spans(gsi_ctx* ctx) {
+    for (auto& s : ctx->spans) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(s.b) == cudaSuccess && cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess)
+            ctx->t_ms[s.cls] += ms;
+        ctx->ev_pool.push_back(s.a);
+        ctx->ev_pool.push_back(s.b);
+    }
+    ctx->spans.clear();
+}
+
+// ---- growable device / pinned buffers ---------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    int ensure(gsi_ctx* ctx, size_t bytes) {
+        if (bytes <= cap) return GSI_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e != cudaSuccess) { cudaGetLastError(); return gsi_fail(ctx, GSI_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+        cap = want;
+        return GSI_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return (T*)p; }
+};
+struct PinBuf {
+    void* p = nullptr; size_t cap = 0;
+    int ensure(gsi_ctx* ctx, size_t bytes) {
+        if (bytes <= cap) return GSI_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) { cudaGetLastError(); return gsi_fail(ctx, GSI_ERR_NOMEM, "cudaMallocHost(%zu): %s", want, cudaGetErrorString(e)); }
+        cap = want;
+        return GSI_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return (T*)p; }
+};
+
+struct Workspace {
+    DevBuf meta, vec_pad, lam_pad, G, rows, cols, perm, hpart, q, totals, items, sig, outk, outlam, outvec, stage_vec, stage_lam, probe;
+    PinBuf h_meta, h_stage_vec, h_stage_lam, h_small, h_k, h_lamoff, h_vecoff, h_sig;
+};
+
+struct gsi_ctx_full : gsi_ctx { Workspace ws; };
+static Workspace& WS(gsi_ctx* c) { return static_cast<gsi_ctx_full*>(c)->ws; }
+
+// ---- context ----------------------------------------------------------------------------------
+template <int EPT> static cudaError_t set_smem_attr() {
+    return cudaFuncSetAttribute(eig_cta_kernel<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)eig_cta_smem_bytes(32 * EPT));
+}
+
+extern "C" int gsi_create(gsi_ctx** out, int device, void* stream) {
+    if (!out) return gsi_fail(nullptr, GSI_ERR_INVALID, "gsi_create: out is null");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return gsi_fail(nullptr, GSI_ERR_CUDA, "gsi_create: no CUDA device (%s); libgsi has no CPU fallback",
+                        cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return gsi_fail(nullptr, GSI_ERR_INVALID, "gsi_create: device %d of %d", device, ndev);
+    gsi_ctx_full* ctx = new gsi_ctx_full();
+    ctx->device = device;
+    GSI_CUDA(ctx, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GSI_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        int rc = gsi_fail(nullptr, GSI_ERR_CUDA, "gsi_create: device %d is sm_%d%d; libgsi is built for sm_100a only", device, prop.major, prop.minor);
+        delete ctx;
+        return rc;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (stream) ctx->stream = (cudaStream_t)stream;
+    else { GSI_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    GSI_CUDA(ctx, set_smem_attr<1>());
+    GSI_CUDA(ctx, set_smem_attr<2>());
+    GSI_CUDA(ctx, set_smem_attr<3>());
+    GSI_CUDA(ctx, set_smem_attr<4>());
+    GSI_CUDA(ctx, set_smem_attr<5>());
+    *out = ctx;
+    return GSI_OK;
+}
+
+extern "C" int gsi_destroy(gsi_ctx* c) {
+    if (!c) return GSI_OK;
+    gsi_ctx_full* ctx = static_cast<gsi_ctx_full*>(c);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    drain_spans(ctx);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    Workspace& w = ctx->ws;
+    DevBuf* d[] = {&w.meta, &w.vec_pad, &w.lam_pad, &w.G, &w.rows, &w.cols, &w.perm, &w.hpart, &w.q, &w.totals, &w.items,
+                   &w.sig, &w.outk, &w.outlam, &w.outvec, &w.stage_vec, &w.stage_lam, &w.probe};
+    for (auto b : d) b->release();
+    PinBuf* p[] = {&w.h_meta, &w.h_stage_vec, &w.h_stage_lam, &w.h_small, &w.h_k, &w.h_lamoff, &w.h_vecoff, &w.h_sig};
+    for (auto b : p) b->release();
+    if (ctx->own_w && ctx->d_w) cudaFree(ctx->d_w);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return GSI_OK;
+}
+
+extern "C" const char* gsi_last_error(const gsi_ctx* ctx) { return ctx ? ctx->err.c_str() : g_tls_err.c_str(); }
+extern "C" const char* gsi_version(void) { return "gsi 0.1 sm_100a fp64"; }
+extern "C" int gsi_set_workspace_limit(gsi_ctx* ctx, int64_t bytes) {
+    if (!ctx || bytes < ((int64_t)64 << 20)) return gsi_fail(ctx, GSI_ERR_INVALID, "workspace limit must be >= 64 MiB");
+    ctx->ws_limit = bytes;
+    return GSI_OK;
+}
+extern "C" int gsi_sync(gsi_ctx* ctx) {
+    if (!ctx) return GSI_ERR_INVALID;
+    GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GSI_OK;
+}
+
+// ---- weights ----------------------------------------------------------------------------------
+static int drop_weights(gsi_ctx* ctx) {
+    if (ctx->own_w && ctx->d_w) cudaFree(ctx->d_w);
+    ctx->d_w = nullptr; ctx->w_rows = 0; ctx->own_w = false;
+    return GSI_OK;
+}
+extern "C" int gsi_set_weights_host(gsi_ctx* ctx, const double* w, int rows) {
+    if (!ctx || !w || rows < 1) return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_set_weights_host: bad arguments");
+    GSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    drop_weights(ctx);
+    GSI_CUDA(ctx, cudaMalloc((void**)&ctx->d_w, (size_t)rows * rows * sizeof(double)));
+    ctx->own_w = true; ctx->w_rows = rows;
+    GSI_CUDA(ctx, cudaMemcpyAsync(ctx->d_w, w, (size_t)rows * rows * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GSI_OK;
+}
+extern "C" int gsi_set_weights_device(gsi_ctx* ctx, const double* d_w, int rows) {
+    if (!ctx || !d_w || rows < 1) return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_set_weights_device: bad arguments");
+    drop_weights(ctx);
+    ctx->d_w = const_cast<double*>(d_w); ctx->w_rows = rows; ctx->own_w = false;
+    return GSI_OK;
+}
+extern "C" int gsi_set_weights_edges(gsi_ctx* ctx, const int32_t* m1, const int32_t* m2, const double* w, int64_t ne, int* rows_out) {
+    if (!ctx || (ne > 0 && (!m1 || !m2 || !w))) return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_set_weights_edges: bad arguments");
+    GSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    int mx = 0;
+    for (int64_t e = 0; e < ne; ++e) {
+        if (m1[e] < 0 || m2[e] < 0) return gsi_fail(ctx, GSI_ERR_INVALID, "negative movie id in edge %lld", (long long)e);
+        mx = std::max(mx, std::max(m1[e], m2[e]));
+    }
+    const int rows = mx + 1;
+    drop_weights(ctx);
+    GSI_CUDA(ctx, cudaMalloc((void**)&ctx->d_w, (size_t)rows * rows * sizeof(double)));
+    ctx->own_w = true; ctx->w_rows = rows;
+    GSI_CUDA(ctx, cudaMemsetAsync(ctx->d_w, 0, (size_t)rows * rows * sizeof(double), ctx->stream));
+    if (ne > 0) {
+        int32_t *da, *db; double* dw;
+        GSI_CUDA(ctx, cudaMalloc((void**)&da, ne * 4));
+        GSI_CUDA(ctx, cudaMalloc((void**)&db, ne * 4));
+        GSI_CUDA(ctx, cudaMalloc((void**)&dw, ne * 8));
+        GSI_CUDA(ctx, cudaMemcpyAsync(da, m1, ne * 4, cudaMemcpyHostToDevice, ctx->stream));
+        GSI_CUDA(ctx, cudaMemcpyAsync(db, m2, ne * 4, cudaMemcpyHostToDevice, ctx->stream));
+        GSI_CUDA(ctx, cudaMemcpyAsync(dw, w, ne * 8, cudaMemcpyHostToDevice, ctx->stream));
+        scatter_edges_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(da, db, dw, ne, ctx->d_w, rows);
+        GSI_CUDA(ctx, cudaGetLastError());
+        GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(da); cudaFree(db); cudaFree(dw);
+    }
+    if (rows_out) *rows_out = rows;
+    return GSI_OK;
+}
+extern "C" int gsi_get_weights(gsi_ctx* ctx, double** d_w, int* rows) {
+    if (!ctx || !ctx->d_w) return gsi_fail(ctx, GSI_ERR_STATE, "no weight table set");
+    if (d_w) *d_w = ctx->d_w;
+    if (rows) *rows = ctx->w_rows;
+    return GSI_OK;
+}
+
+// ---- planner ----------------------------------------------------------------------------------
+struct Job { int64_t user; int n; int64_t item_off; };
+struct Chunk { bool large; int begin, end; };   // [begin, end) into the sorted job list
+
+static inline int64_t pad_slots(int n) { return (int64_t)n * std::max(n, 2); }
+static inline int ld_of(int n) { return (n + 7) & ~7; }
+static inline int nb_of(int n) { int nb = (n + GSI_BJ_B - 1) / GSI_BJ_B; return nb + (nb & 1); }
+
+static int plan(gsi_ctx* ctx, int64_t nu, const int64_t* off, std::vector<Job>& small, std::vector<Job>& large,
+                std::vector<Chunk>& chunks) {
+    small.clear(); large.clear(); chunks.clear();
+    for (int64_t u = 0; u < nu; ++u) {
+        const int64_t n = off[u + 1] - off[u];
+        if (n < 1) return gsi_fail(ctx, GSI_ERR_INVALID, "user %lld has %lld rated movies (need >= 1)", (long long)u, (long long)n);
+        if (n > 46000) return gsi_fail(ctx, GSI_ERR_INVALID, "user %lld: n = %lld too large", (long long)u, (long long)n);
+        (n <= GSI_S_MAX_N ? small : large).push_back({u, (int)n, off[u]});
+    }
+    auto desc = [](const Job& a, const Job& b) { return a.n != b.n ? a.n > b.n : a.user < b.user; };
+    std::sort(small.begin(), small.end(), desc);
+    std::sort(large.begin(), large.end(), desc);
+    // large first (longest jobs first), then small
+    const int64_t budget = ctx->ws_limit / (int64_t)sizeof(double);
+    int b = 0;
+    while (b < (int)large.size()) {
+        const int nmax = large[b].n;
+        const int nb = nb_of(nmax), ncols = nb * GSI_BJ_B;
+        int64_t used = 0;
+        int e = b;
+        while (e < (int)large.size() && e - b < 60000) {
+            const int n = large[e].n;
+            if (e > b && (double)n < 0.7 * nmax) break;
+            const int64_t need = (int64_t)ld_of(n) * ncols + pad_slots(n) + (int64_t)(nb / 2) * 1024 * (1 + (ld_of(nmax) + GSI_BJ_ROWS - 1) / GSI_BJ_ROWS);
+            if (e > b && used + need > budget) break;
+            used += need; ++e;
+        }
+        chunks.push_back({true, b, e});
+        b = e;
+    }
+    b = 0;
+    while (b < (int)small.size()) {
+        int64_t used = 0;
+        int e = b;
+        while (e < (int)small.size() && e - b < (1 << 20)) {
+            const int64_t need = pad_slots(small[e].n) + small[e].n;
+            if (e > b && used + need > budget) break;
+            used += need; ++e;
+        }
+        chunks.push_back({false, b, e});
+        b = e;
+    }
+    return GSI_OK;
+}
+
+// meta upload helper: lay arrays out in one pinned block, copy once
+struct MetaBuilder {
+    std::vector<char> host;
+    template <class T> size_t add(const std::vector<T>& v) {
+        size_t o = (host.size() + 15) & ~(size_t)15;
+        host.resize(o + v.size() * sizeof(T));
+        if (!v.empty()) memcpy(host.data() + o, v.data(), v.size() * sizeof(T));
+        return o;
+    }
+    size_t reserve(size_t bytes) {
+        size_t o = (host.size() + 15) & ~(size_t)15;
+        host.resize(o + bytes, 0);
+        return o;
+    }
+};
+
+struct RunOut {               // where a chunk's records go
+    double* d_lam; int64_t lam_cap;
+    double* d_vec; int64_t vec_cap;
+    int64_t* d_totals;        // [3] device: running lam, vec totals, overflow flag
+    int32_t* d_k; int64_t* d_lam_off; int64_t* d_vec_off;   // caller-order arrays [n_users]
+    double* d_sig_min;
+};
+
+static int upload_meta(gsi_ctx* ctx, MetaBuilder& mb, char** d_base) {
+    Workspace& ws = WS(ctx);
+    int rc;
+    if ((rc = ws.meta.ensure(ctx, mb.host.size())) != GSI_OK) return rc;
+    if ((rc = ws.h_meta.ensure(ctx, mb.host.size())) != GSI_OK) return rc;
+    // h_meta may still be in flight from the previous chunk's async copy
+    GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(ws.h_meta.p, mb.host.data(), mb.host.size());
+    GSI_CUDA(ctx, cudaMemcpyAsync(ws.meta.p, ws.h_meta.p, mb.host.size(), cudaMemcpyHostToDevice, ctx->stream));
+    *d_base = ws.meta.as<char>();
+    return GSI_OK;
+}
+
+static int finish_chunk(gsi_ctx* ctx, OutJobs J, const RunOut& out, int64_t max_nk) {
+    Workspace& ws = WS(ctx);
+    GsiSpan sp(ctx, GSI_T_COMPACT, 2);
+    out_scan_kernel<<<1, 1024, 0, ctx->stream>>>(J, out.d_totals, out.lam_cap, out.vec_cap, out.d_k, out.d_lam_off, out.d_vec_off);
+    GSI_CUDA(ctx, cudaGetLastError());
+    const unsigned slices = (unsigned)std::max<int64_t>(1, (max_nk + GSI_COMPACT_SLICE - 1) / GSI_COMPACT_SLICE);
+    out_compact_kernel<<<dim3(J.nj, slices), 256, 0, ctx->stream>>>(J, ws.vec_pad.as<double>(), ws.lam_pad.as<double>(), out.d_vec, out.d_lam, out.lam_cap, out.vec_cap);
+    GSI_CUDA(ctx, cudaGetLastError());
+    sp.end();
+    return GSI_OK;
+}
+
+template <int EPT>
+static cudaError_t launch_eig_cta(gsi_ctx* ctx, const SParams& P, int njobs, int nmax) {
+    const int threads = EPT <= 2 ? 256 : (EPT == 3 ? 512 : 1024);
+    eig_cta_kernel<EPT><<<njobs, threads, eig_cta_smem_bytes(nmax), ctx->stream>>>(P);
+    return cudaGetLastError();
+}
+
+// ---- small chunk: one fused kernel per (EPT, smem) class -----------------------------------------
+static int run_small_chunk(gsi_ctx* ctx, const Job* jobs, int nj, const int32_t* d_items, const RunOut& out) {
+    Workspace& ws = WS(ctx);
+    std::vector<int64_t> item_off(nj), vec_off(nj), lam_off(nj), user(nj);
+    std::vector<int32_t> n(nj);
+    int64_t vtot = 0, ltot = 0, max_nk = 0;
+    for (int j = 0; j < nj; ++j) {
+        item_off[j] = jobs[j].item_off; n[j] = jobs[j].n; user[j] = jobs[j].user;
+        vec_off[j] = vtot; lam_off[j] = ltot;
+        vtot += pad_slots(jobs[j].n); ltot += std::max(jobs[j].n, 2);
+        max_nk = std::max(max_nk, pad_slots(jobs[j].n));
+    }
+    MetaBuilder mb;
+    const size_t o_item = mb.add(item_off), o_vec = mb.add(vec_off), o_lam = mb.add(lam_off), o_user = mb.add(user), o_n = mb.add(n);
+    const size_t o_k = mb.reserve(nj * 4), o_sw = mb.reserve(nj * 4), o_vd = mb.reserve(nj * 8), o_ld = mb.reserve(nj * 8);
+    int rc;
+    if ((rc = ws.vec_pad.ensure(ctx, vtot * 8)) != GSI_OK) return rc;
+    if ((rc = ws.lam_pad.ensure(ctx, ltot * 8)) != GSI_OK) return rc;
+    char* base;
+    if ((rc = upload_meta(ctx, mb, &base)) != GSI_OK) return rc;
+    SParams P;
+    P.W = ctx->d_w; P.w_rows = ctx->w_rows; P.items = d_items;
+    P.job_item_off = (const int64_t*)(base + o_item); P.job_n = (const int32_t*)(base + o_n);
+    P.job_vec_off = (const int64_t*)(base + o_vec); P.job_lam_off = (const int64_t*)(base + o_lam);
+    P.sig_min = out.d_sig_min; P.job_k = (int32_t*)(base + o_k); P.job_sweeps = (int32_t*)(base + o_sw);
+    P.lam_pad = ws.lam_pad.as<double>(); P.vec_pad = ws.vec_pad.as<double>();
+    // jobs are sorted by n descending: launch runs that share ceil(n/16)
+    int b = 0;
+    while (b < nj) {
+        const int key = (n[b] + 15) / 16;
+        int e = b;
+        while (e < nj && (n[e] + 15) / 16 == key) ++e;
+        const int nmax = n[b], ept = (nmax + 31) / 32;
+        P.job_base = b;
+        GsiSpan sp(ctx, GSI_T_EIG_CTA, 1);
+        cudaError_t ce;
+        switch (ept) {
+            case 1: ce = launch_eig_cta<1>(ctx, P, e - b, nmax); break;
+            case 2: ce = launch_eig_cta<2>(ctx, P, e - b, nmax); break;
+            case 3: ce = launch_eig_cta<3>(ctx, P, e - b, nmax); break;
+            case 4: ce = launch_eig_cta<4>(ctx, P, e - b, nmax); break;
+            default: ce = launch_eig_cta<5>(ctx, P, e - b, nmax); break;
+        }
+        sp.end();
+        GSI_CUDA(ctx, ce);
+        b = e;
+    }
+    OutJobs J;
+    J.nj = nj; J.n = P.job_n; J.k = P.job_k; J.user = (const int64_t*)(base + o_user);
+    J.vec_pad = P.job_vec_off; J.lam_pad = P.job_lam_off;
+    J.vec_dst = (int64_t*)(base + o_vd); J.lam_dst = (int64_t*)(base + o_ld);
+    return finish_chunk(ctx, J, out, max_nk);
+}
+
+// ---- large chunk: Laplacian kernels, block-Jacobi rounds, finalisation ------------------------------
+static int run_large_chunk(gsi_ctx* ctx, const Job* jobs, int nj, const int32_t* d_items, const RunOut& out) {
+    Workspace& ws = WS(ctx);
+    const int nmax = jobs[0].n;                    // sorted descending
+    const int nb = nb_of(nmax), ncols = nb * GSI_BJ_B, half = nb / 2;
+    const int splits = (ld_of(nmax) + GSI_BJ_ROWS - 1) / GSI_BJ_ROWS;
+    std::vector<int64_t> item_off(nj), vec_off(nj), lam_off(nj), user(nj), g_off(nj), row_off(nj);
+    std::vector<int32_t> n(nj), ld(nj);
+    int64_t vtot = 0, ltot = 0, gtot = 0, rtot = 0, max_nk = 0;
+    for (int j = 0; j < nj; ++j) {
+        item_off[j] = jobs[j].item_off; n[j] = jobs[j].n; user[j] = jobs[j].user; ld[j] = ld_of(jobs[j].n);
+        vec_off[j] = vtot; lam_off[j] = ltot; g_off[j] = gtot; row_off[j] = rtot;
+        vtot += pad_slots(jobs[j].n); ltot += std::max(jobs[j].n, 2);
+        gtot += (int64_t)ld[j] * ncols; rtot += ld[j];
+        max_nk = std::max(max_nk, pad_slots(jobs[j].n));
+    }
+    MetaBuilder mb;
+    const size_t o_item = mb.add(item_off), o_vec = mb.add(vec_off), o_lam = mb.add(lam_off), o_user = mb.add(user),
+                 o_goff = mb.add(g_off), o_roff = mb.add(row_off), o_n = mb.add(n), o_ldim = mb.add(ld);
+    const size_t o_k = mb.reserve(nj * 4), o_vd = mb.reserve(nj * 8), o_ld = mb.reserve(nj * 8), o_sigmax = mb.reserve(nj * 4),
+                 o_done = mb.reserve(nj * 4), o_smax = mb.reserve(nj * 8), o_sw = mb.reserve(nj * 4), o_rem = mb.reserve(16);
+    int rc;
+    if ((rc = ws.vec_pad.ensure(ctx, vtot * 8)) != GSI_OK) return rc;
+    if ((rc = ws.lam_pad.ensure(ctx, ltot * 8)) != GSI_OK) return rc;
+    if ((rc = ws.G.ensure(ctx, gtot * 8)) != GSI_OK) return rc;
+    if ((rc = ws.rows.ensure(ctx, rtot * 16)) != GSI_OK) return rc;
+    if ((rc = ws.cols.ensure(ctx, (size_t)nj * ncols * 16)) != GSI_OK) return rc;
+    if ((rc = ws.perm.ensure(ctx, (size_t)nj * ncols * 4)) != GSI_OK) return rc;
+    if ((rc = ws.hpart.ensure(ctx, (size_t)nj * half * splits * 1024 * 8)) != GSI_OK) return rc;
+    if ((rc = ws.q.ensure(ctx, (size_t)nj * half * 1024 * 8)) != GSI_OK) return rc;
+    if ((rc = ws.h_small.ensure(ctx, 64)) != GSI_OK) return rc;
+    char* base;
+    if ((rc = upload_meta(ctx, mb, &base)) != GSI_OK) return rc;
+    LChunk C;
+    C.nu = nj; C.nb = nb; C.ncols = ncols; C.splits = splits;
+    C.n = (const int32_t*)(base + o_n); C.ld = (const int32_t*)(base + o_ldim);
+    C.g_off = (const int64_t*)(base + o_goff); C.item_off = (const int64_t*)(base + o_item);
+    C.row_off = (const int64_t*)(base + o_roff); C.vec_off = (const int64_t*)(base + o_vec); C.lam_off = (const int64_t*)(base + o_lam);
+    C.G = ws.G.as<double>(); C.deg = ws.rows.as<double>(); C.scale = ws.rows.as<double>() + rtot;
+    C.colnorm = ws.cols.as<double>(); C.colval = ws.cols.as<double>() + (size_t)nj * ncols;
+    C.perm = ws.perm.as<int32_t>();
+    C.sigmax = (unsigned int*)(base + o_sigmax); C.done = (int32_t*)(base + o_done);
+    C.smax = (unsigned long long*)(base + o_smax); C.sweeps = (int32_t*)(base + o_sw);
+    C.k = (int32_t*)(base + o_k); C.remaining = (int32_t*)(base + o_rem);
+    C.Hpart = ws.hpart.as<double>(); C.Q = ws.q.as<double>();
+    cudaStream_t st = ctx->stream;
+    {   // Laplacian stage
+        GsiSpan sp(ctx, GSI_T_LAP, 5);
+        GSI_CUDA(ctx, cudaMemsetAsync(C.G, 0, gtot * 8, st));
+        const int tiles = (nmax + 31) / 32;
+        lap_gather_kernel<<<dim3(tiles * tiles, 1, nj), dim3(32, 8), 0, st>>>(C, ctx->d_w, ctx->w_rows, d_items, tiles);
+        lap_degree_kernel<<<dim3((nmax + 127) / 128, 1, nj), 128, 0, st>>>(C);
+        lap_transform_kernel<<<dim3((nmax + 127) / 128, (nmax + 7) / 8, nj), 128, 0, st>>>(C);
+        lap_sigmin_kernel<<<dim3((nmax + 127) / 128, 1, nj), 128, 0, st>>>(C, out.d_sig_min);
+        lap_symmetrize_kernel<<<dim3(tiles * tiles, 1, nj), dim3(32, 8), 0, st>>>(C, tiles);
+        GSI_CUDA(ctx, cudaGetLastError());
+        sp.end();
+    }
+    int32_t* h_rem = ws.h_small.as<int32_t>();
+    for (int sweep = 0; sweep < GSI_MAX_SWEEPS; ++sweep) {
+        for (int r = 0; r < nb - 1; ++r) {
+            const bool sample = ctx->timing && (r % 8 == 0);
+            if (sample) {
+                GsiSpan a(ctx, GSI_T_BJ_GRAM, 0, 1);
+                bj_gram_kernel<<<dim3(half, splits, nj), 128, 0, st>>>(C, r);
+                a.end();
+                GsiSpan b(ctx, GSI_T_BJ_INNER, 0, 1);
+                bj_inner_kernel<<<dim3(half, 1, nj), 256, 0, st>>>(C, r);
+                b.end();
+                GsiSpan c(ctx, GSI_T_BJ_UPDATE, 0, 1);
+                bj_update_kernel<<<dim3(half, splits, nj), 128, 0, st>>>(C, r);
+                c.end();
+            } else {
+                bj_gram_kernel<<<dim3(half, splits, nj), 128, 0, st>>>(C, r);
+                bj_inner_kernel<<<dim3(half, 1, nj), 256, 0, st>>>(C, r);
+                bj_update_kernel<<<dim3(half, splits, nj), 128, 0, st>>>(C, r);
+            }
+            gsi_count_launch(ctx, GSI_T_BJ_GRAM, 1);
+            gsi_count_launch(ctx, GSI_T_BJ_INNER, 1);
+            gsi_count_launch(ctx, GSI_T_BJ_UPDATE, 1);
+        }
+        GSI_CUDA(ctx, cudaMemsetAsync(C.remaining, 0, 4, st));
+        bj_check_kernel<<<(nj + 255) / 256, 256, 0, st>>>(C);
+        GSI_CUDA(ctx, cudaGetLastError());
+        GSI_CUDA(ctx, cudaMemcpyAsync(h_rem, C.remaining, 4, cudaMemcpyDeviceToHost, st));
+        GSI_CUDA(ctx, cudaStreamSynchronize(st));
+        if (*h_rem == 0) break;
+    }
+    {
+        GsiSpan sp(ctx, GSI_T_FINALIZE, 3);
+        fin_colnorm_kernel<<<dim3((ncols + 7) / 8, 1, nj), 256, 0, st>>>(C);
+        fin_rank_kernel<<<nj, 1024, 0, st>>>(C, ws.lam_pad.as<double>());
+        const int tiles_i = (nmax + 31) / 32, tiles_r = (nmax + 31) / 32;
+        fin_emit_kernel<<<dim3(tiles_i * tiles_r, 1, nj), dim3(32, 8), 0, st>>>(C, ws.vec_pad.as<double>(), tiles_r);
+        GSI_CUDA(ctx, cudaGetLastError());
+        sp.end();
+    }
+    OutJobs J;
+    J.nj = nj; J.n = C.n; J.k = C.k; J.user = (const int64_t*)(base + o_user);
+    J.vec_pad = C.vec_off; J.lam_pad = C.lam_off;
+    J.vec_dst = (int64_t*)(base + o_vd); J.lam_dst = (int64_t*)(base + o_ld);
+    return finish_chunk(ctx, J, out, max_nk);
+}
+
+static int check_csr(gsi_ctx* ctx, int64_t nu, const int64_t* off, const int32_t* items) {
+    if (off[0] != 0) return gsi_fail(ctx, GSI_ERR_INVALID, "offsets[0] must be 0");
+    for (int64_t u = 0; u < nu; ++u) {
+        if (off[u + 1] <= off[u]) return gsi_fail(ctx, GSI_ERR_INVALID, "user %lld has no rated movies", (long long)u);
+        if (items)
+            for (int64_t t = off[u] + 1; t < off[u + 1]; ++t)
+                if (items[t] <= items[t - 1])
+                    return gsi_fail(ctx, GSI_ERR_INVALID, "user %lld: movie ids must be strictly ascending (unique)", (long long)u);
+    }
+    return GSI_OK;
+}
+
+// ---- device API -----------------------------------------------------------------------------
+extern "C" int gsi_precompute_device(gsi_ctx* ctx, int64_t nu, const int64_t* h_offsets, const int32_t* d_items,
+                                     double* d_sig_min, int32_t* d_k, int64_t* d_lam_off, int64_t* d_vec_off,
+                                     double* d_lam, int64_t lam_cap, double* d_vec, int64_t vec_cap, int64_t* totals) {
+    if (!ctx) return gsi_fail(nullptr, GSI_ERR_INVALID, "null context");
+    if (!ctx->d_w) return gsi_fail(ctx, GSI_ERR_STATE, "gsi_precompute: no weight table set (call gsi_set_weights_*)");
+    if (nu < 0 || !h_offsets || (nu > 0 && (!d_items || !d_sig_min || !d_k || !d_lam_off || !d_vec_off || !d_lam || !d_vec)))
+        return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_precompute_device: null argument");
+    GSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = check_csr(ctx, nu, h_offsets, nullptr)) != GSI_OK) return rc;
+    Workspace& ws = WS(ctx);
+    if ((rc = ws.totals.ensure(ctx, 64)) != GSI_OK) return rc;
+    if ((rc = ws.h_small.ensure(ctx, 64)) != GSI_OK) return rc;
+    GSI_CUDA(ctx, cudaMemsetAsync(ws.totals.p, 0, 64, ctx->stream));
+    std::vector<Job> small, large;
+    std::vector<Chunk> chunks;
+    if ((rc = plan(ctx, nu, h_offsets, small, large, chunks)) != GSI_OK) return rc;
+    RunOut out{d_lam, lam_cap, d_vec, vec_cap, ws.totals.as<int64_t>(), d_k, d_lam_off, d_vec_off, d_sig_min};
+    for (const Chunk& c : chunks) {
+        rc = c.large ? run_large_chunk(ctx, large.data() + c.begin, c.end - c.begin, d_items, out)
+                     : run_small_chunk(ctx, small.data() + c.begin, c.end - c.begin, d_items, out);
+        if (rc != GSI_OK) return rc;
+    }
+    int64_t* h_tot = (int64_t*)(ws.h_small.as<char>() + 16);
+    GSI_CUDA(ctx, cudaMemcpyAsync(h_tot, ws.totals.p, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (totals) { totals[0] = h_tot[0]; totals[1] = h_tot[1]; }
+    if (h_tot[2]) return gsi_fail(ctx, GSI_ERR_CAPACITY, "output capacity too small: need lam %lld / vec %lld doubles",
+                                  (long long)h_tot[0], (long long)h_tot[1]);
+    return GSI_OK;
+}
+
+// ---- streaming host API ------------------------------------------------------------------------
+extern "C" int gsi_precompute_stream(gsi_ctx* ctx, int64_t nu, const int64_t* offsets, const int32_t* items,
+                                     gsi_record_sink sink, void* opaque) {
+    if (!ctx) return gsi_fail(nullptr, GSI_ERR_INVALID, "null context");
+    if (!ctx->d_w) return gsi_fail(ctx, GSI_ERR_STATE, "gsi_precompute: no weight table set (call gsi_set_weights_*)");
+    if (nu < 0 || !offsets || !sink || (nu > 0 && !items)) return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_precompute_stream: null argument");
+    GSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = check_csr(ctx, nu, offsets, items)) != GSI_OK) return rc;
+    if (nu == 0) return GSI_OK;
+    Workspace& ws = WS(ctx);
+    const int64_t nnz = offsets[nu];
+    if ((rc = ws.totals.ensure(ctx, 64)) != GSI_OK) return rc;
+    if ((rc = ws.h_small.ensure(ctx, 64)) != GSI_OK) return rc;
+    if ((rc = ws.items.ensure(ctx, nnz * 4)) != GSI_OK) return rc;
+    if ((rc = ws.sig.ensure(ctx, nnz * 8)) != GSI_OK) return rc;
+    if ((rc = ws.outk.ensure(ctx, nu * 4)) != GSI_OK) return rc;
+    if ((rc = ws.outlam.ensure(ctx, nu * 8)) != GSI_OK) return rc;
+    if ((rc = ws.outvec.ensure(ctx, nu * 8)) != GSI_OK) return rc;
+    if ((rc = ws.h_k.ensure(ctx, nu * 4)) != GSI_OK) return rc;
+    if ((rc = ws.h_lamoff.ensure(ctx, nu * 8)) != GSI_OK) return rc;
+    if ((rc = ws.h_vecoff.ensure(ctx, nu * 8)) != GSI_OK) return rc;
+    if ((rc = ws.h_sig.ensure(ctx, nnz * 8)) != GSI_OK) return rc;
+    GSI_CUDA(ctx, cudaMemcpyAsync(ws.items.p, items, nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<Job> small, large;
+    std::vector<Chunk> chunks;
+    if ((rc = plan(ctx, nu, offsets, small, large, chunks)) != GSI_OK) return rc;
+    std::vector<int64_t> rec_user, rec_lam, rec_vec;
+    std::vector<int32_t> rec_n, rec_k;
+    for (const Chunk& c : chunks) {
+        const Job* jobs = (c.large ? large.data() : small.data()) + c.begin;
+        const int nj = c.end - c.begin;
+        int64_t vcap = 0, lcap = 0;
+        for (int j = 0; j < nj; ++j) { vcap += pad_slots(jobs[j].n); lcap += std::max(jobs[j].n, 2); }
+        if ((rc = ws.stage_vec.ensure(ctx, vcap * 8)) != GSI_OK) return rc;
+        if ((rc = ws.stage_lam.ensure(ctx, lcap * 8)) != GSI_OK) return rc;
+        GSI_CUDA(ctx, cudaMemsetAsync(ws.totals.p, 0, 64, ctx->stream));
+        RunOut out{ws.stage_lam.as<double>(), lcap, ws.stage_vec.as<double>(), vcap, ws.totals.as<int64_t>(),
+                   ws.outk.as<int32_t>(), ws.outlam.as<int64_t>(), ws.outvec.as<int64_t>(), ws.sig.as<double>()};
+        rc = c.large ? run_large_chunk(ctx, jobs, nj, ws.items.as<int32_t>(), out)
+                     : run_small_chunk(ctx, jobs, nj, ws.items.as<int32_t>(), out);
+        if (rc != GSI_OK) return rc;
+        int64_t* h_tot = (int64_t*)(ws.h_small.as<char>() + 16);
+        GSI_CUDA(ctx, cudaMemcpyAsync(h_tot, ws.totals.p, 24, cudaMemcpyDeviceToHost, ctx->stream));
+        GSI_CUDA(ctx, cudaMemcpyAsync(ws.h_k.p, ws.outk.p, nu * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        GSI_CUDA(ctx, cudaMemcpyAsync(ws.h_lamoff.p, ws.outlam.p, nu * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        GSI_CUDA(ctx, cudaMemcpyAsync(ws.h_vecoff.p, ws.outvec.p, nu * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        GSI_CUDA(ctx, cudaMemcpyAsync(ws.h_sig.p, ws.sig.p, nnz * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (h_tot[2]) return gsi_fail(ctx, GSI_ERR_CAPACITY, "internal staging overflow");
+        if ((rc = ws.h_stage_lam.ensure(ctx, h_tot[0] * 8)) != GSI_OK) return rc;
+        if ((rc = ws.h_stage_vec.ensure(ctx, h_tot[1] * 8)) != GSI_OK) return rc;
+        GSI_CUDA(ctx, cudaMemcpyAsync(ws.h_stage_lam.p, ws.stage_lam.p, h_tot[0] * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        GSI_CUDA(ctx, cudaMemcpyAsync(ws.h_stage_vec.p, ws.stage_vec.p, h_tot[1] * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        rec_user.resize(nj); rec_lam.resize(nj); rec_vec.resize(nj); rec_n.resize(nj); rec_k.resize(nj);
+        for (int j = 0; j < nj; ++j) {
+            const int64_t u = jobs[j].user;
+            rec_user[j] = u; rec_n[j] = jobs[j].n; rec_k[j] = ws.h_k.as<int32_t>()[u];
+            rec_lam[j] = ws.h_lamoff.as<int64_t>()[u]; rec_vec[j] = ws.h_vecoff.as<int64_t>()[u];
+        }
+        gsi_record_chunk ch;
+        ch.n_records = nj; ch.user_index = rec_user.data(); ch.n = rec_n.data(); ch.k = rec_k.data();
+        ch.lam_off = rec_lam.data(); ch.vec_off = rec_vec.data();
+        ch.lam = ws.h_stage_lam.as<double>(); ch.vec = ws.h_stage_vec.as<double>(); ch.sig_min = ws.h_sig.as<double>();
+        if (sink(opaque, &ch) != 0) return gsi_fail(ctx, GSI_ERR_SINK, "record sink failed");
+    }
+    return GSI_OK;
+}
+
+// ---- array host API (memcpy sink over the streaming path) ----------------------------------------
+struct HostSink {
+    const int64_t* offsets; double* sig_min; int32_t* k; int64_t* lam_off; int64_t* vec_off;
+    double* lam; int64_t lam_cap; double* vec; int64_t vec_cap; int64_t lam_used = 0, vec_used = 0; bool overflow = false;
+};
+static int host_sink(void* opaque, const gsi_record_chunk* ch) {
+    HostSink* s = (HostSink*)opaque;
+    for (int64_t j = 0; j < ch->n_records; ++j) {
+        const int64_t u = ch->user_index[j];
+        const int n = ch->n[j], k = ch->k[j];
+        s->k[u] = k; s->lam_off[u] = s->lam_used; s->vec_off[u] = s->vec_used;
+        if (s->lam_used + k > s->lam_cap || s->vec_used + (int64_t)n * k > s->vec_cap) s->overflow = true;
+        else {
+            memcpy(s->lam + s->lam_used, ch->lam + ch->lam_off[j], (size_t)k * 8);
+            memcpy(s->vec + s->vec_used, ch->vec + ch->vec_off[j], (size_t)n * k * 8);
+        }
+        s->lam_used += k; s->vec_used += (int64_t)n * k;
+        memcpy(s->sig_min + s->offsets[u], ch->sig_min + s->offsets[u], (size_t)n * 8);
+    }
+    return 0;
+}
+extern "C" int gsi_precompute_host(gsi_ctx* ctx, int64_t nu, const int64_t* offsets, const int32_t* items, double* sig_min,
+                                   int32_t* k, int64_t* lam_off, int64_t* vec_off, double* lam, int64_t lam_cap,
+                                   double* vec, int64_t vec_cap, int64_t* totals) {
+    if (!ctx) return gsi_fail(nullptr, GSI_ERR_INVALID, "null context");
+    if (nu > 0 && (!sig_min || !k || !lam_off || !vec_off || !lam || !vec)) return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_precompute_host: null argument");
+    HostSink s{offsets, sig_min, k, lam_off, vec_off, lam, lam_cap, vec, vec_cap};
+    int rc = gsi_precompute_stream(ctx, nu, offsets, items, host_sink, &s);
+    if (totals) { totals[0] = s.lam_used; totals[1] = s.vec_used; }
+    if (rc != GSI_OK) return rc;
+    if (s.overflow) return gsi_fail(ctx, GSI_ERR_CAPACITY, "output capacity too small: need lam %lld / vec %lld doubles",
+                                    (long long)s.lam_used, (long long)s.vec_used);
+    return GSI_OK;
+}
+
+// ---- measurement ---------------------------------------------------------------------------------
+extern "C" int gsi_timing_enable(gsi_ctx* ctx, int on) { if (!ctx) return GSI_ERR_INVALID; ctx->timing = on != 0; return GSI_OK; }
+extern "C" int gsi_timing_reset(gsi_ctx* ctx) {
+    if (!ctx) return GSI_ERR_INVALID;
+    cudaStreamSynchronize(ctx->stream);
+    drain_spans(ctx);
+    for (int i = 0; i < GSI_T_COUNT; ++i) { ctx->t_ms[i] = 0; ctx->t_launch[i] = 0; ctx->t_samples[i] = 0; }
+    return GSI_OK;
+}
+extern "C" int gsi_timing_get(gsi_ctx* ctx, double* ms, int64_t* launches, int64_t* samples) {
+    if (!ctx) return GSI_ERR_INVALID;
+    GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    drain_spans(ctx);
+    for (int i = 0; i < GSI_T_COUNT; ++i) {
+        if (ms) ms[i] = ctx->t_ms[i];
+        if (launches) launches[i] = ctx->t_launch[i];
+        if (samples) samples[i] = ctx->t_samples[i];
+    }
+    return GSI_OK;
+}
+extern "C" int gsi_measure_fp64_tflops(gsi_ctx* ctx, int use_dmma, double* tflops) {
+    if (!ctx || !tflops) return GSI_ERR_INVALID;
+    GSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    Workspace& ws = WS(ctx);
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 14;
+    int rc;
+    if ((rc = ws.probe.ensure(ctx, (size_t)blocks * threads * 8)) != GSI_OK) return rc;
+    cudaEvent_t a, b;
+    GSI_CUDA(ctx, cudaEventCreate(&a));
+    GSI_CUDA(ctx, cudaEventCreate(&b));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        GSI_CUDA(ctx, cudaEventRecord(a, ctx->stream));
+        if (use_dmma) fp64_dmma_probe<<<blocks, threads, 0, ctx->stream>>>(ws.probe.as<double>(), iters);
+        else fp64_fma_probe<<<blocks, threads, 0, ctx->stream>>>(ws.probe.as<double>(), iters);
+        GSI_CUDA(ctx, cudaEventRecord(b, ctx->stream));
+        GSI_CUDA(ctx, cudaEventSynchronize(b));
+        float ms;
+        GSI_CUDA(ctx, cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    // fma probe: 8 FMA per thread per iter; dmma probe: 8 mma (8x8x4 = 256 FMA per warp) per iter
+    const double flop = use_dmma ? (double)blocks * (threads / 32) * iters * 8.0 * 512.0
+                                 : (double)blocks * threads * iters * 8.0 * 2.0;
+    *tflops = flop / (best * 1e-3) / 1e12;
+    return GSI_OK;
+}

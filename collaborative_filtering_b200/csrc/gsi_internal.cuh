@@ -1,0 +1,66 @@
+// Internal declarations shared by the translation units of libgsi.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gsi.h"
+
+#define GSI_WARP 32
+// One-sided Jacobi thresholds (fp64).  A pair is rotated when gamma^2 > ROT2 * alpha * beta; a
+// sweep whose largest pre-rotation ratio^2 is <= STOP2 is the last one (quadratic convergence:
+// a 3e-8 ratio before the sweep leaves ~1e-15 after it).
+#define GSI_ROT2 1e-30
+#define GSI_STOP2 9e-16
+#define GSI_MAX_SWEEPS 40
+
+// CTA-resident solver covers n <= 32 * GSI_S_MAX_EPT
+#define GSI_S_MAX_EPT 5
+#define GSI_S_MAX_N (32 * GSI_S_MAX_EPT)
+
+// block Jacobi (large path): column blocks of GSI_BJ_B, panels of 2*GSI_BJ_B = 32 columns
+#define GSI_BJ_B 16
+#define GSI_BJ_M 32
+#define GSI_BJ_ROWS 512  // rows of a panel handled by one CTA of the Gram / update kernels
+
+struct gsi_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int sm_count = 148;
+    int64_t ws_limit = (int64_t)8 << 30;
+    // weights
+    double* d_w = nullptr;
+    int w_rows = 0;
+    bool own_w = false;
+    // timing
+    bool timing = false;
+    double t_ms[GSI_T_COUNT] = {0};
+    int64_t t_launch[GSI_T_COUNT] = {0};
+    int64_t t_samples[GSI_T_COUNT] = {0};
+    std::vector<cudaEvent_t> ev_pool;
+    struct Span { int cls; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+};
+
+int gsi_fail(gsi_ctx* ctx, int code, const char* fmt, ...);
+
+#define GSI_CUDA(ctx, call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return gsi_fail((ctx), e_ == cudaErrorMemoryAllocation ? GSI_ERR_NOMEM : GSI_ERR_CUDA, \
+                            "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+// timing spans: begin/end around a group of launches of one class on ctx->stream
+struct GsiSpan {
+    gsi_ctx* ctx; int cls; cudaEvent_t a = nullptr, b = nullptr; int64_t launches;
+    // counts `n_launches` launches; when timing is on, the span's time covers `n_timed` of them
+    GsiSpan(gsi_ctx* c, int cls_, int64_t n_launches = 1, int64_t n_timed = -1);
+    void end();
+};
+void gsi_count_launch(gsi_ctx* ctx, int cls, int64_t n);

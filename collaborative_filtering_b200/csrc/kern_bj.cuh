@@ -1,0 +1,471 @@
+// Large path (n > 160): the user's matrix lives in HBM/L2, all SMs cooperate on a chunk of users.
+//
+//   lap_* kernels      gather W -> degree -> normalised Laplacian -> sig_min -> sym(lower)+I
+//                      (precompute_local.cpp:185-249), column-major G[i + j*ld]
+//   bj_* kernels       one-sided BLOCK Jacobi on G: column blocks of 16; each round pairs the
+//                      blocks with the circle ordering and every pair (I,J) does
+//                          H = P^T P            P = [G_I G_J]   (n x 32)     bj_gram   (DMMA)
+//                          Q = one cyclic sweep of two-sided Jacobi on H      bj_inner
+//                          P <- P Q                                           bj_update (DMMA)
+//                      FP64 tensor-core mma.sync m8n8k4 carries both GEMM-shaped steps.
+//   fin_* kernels      column norms -> eigenvalues, ascending rank, cutoff (:252-261), emit
+//
+// All users of a chunk share nb (block count, even) so that every user finishes a sweep on the
+// same round; blocks beyond a user's n are phantom and their pairs exit at once.
+#pragma once
+#include "gsi_internal.cuh"
+#include "kern_eig_cta.cuh"
+
+struct LChunk {
+    int nu;        // users in the chunk
+    int nb;        // column blocks per user (even), uniform over the chunk
+    int ncols;     // nb * 16
+    int splits;    // row splits of a panel (uniform upper bound)
+    const int32_t* n;          // [nu]
+    const int32_t* ld;         // [nu] leading dimension, multiple of 8, rows >= n are zero
+    const int64_t* g_off;      // [nu] offset of the user's G (ld x ncols doubles)
+    const int64_t* item_off;   // [nu] offset into items / sig_min
+    const int64_t* row_off;    // [nu] offset into per-row scratch (deg/scale) and per-column scratch
+    const int64_t* vec_off;    // [nu] offset into vec_pad
+    const int64_t* lam_off;    // [nu] offset into lam_pad
+    double* G;
+    double* deg;               // per-row scratch
+    double* scale;             // per-row scratch
+    double* colnorm;           // [nu * ncols] signed norms
+    double* colval;            // [nu * ncols] eigenvalues
+    int32_t* perm;             // [nu * ncols]
+    unsigned int* sigmax;      // [nu] float bits
+    int32_t* done;             // [nu]
+    unsigned long long* smax;  // [nu]
+    int32_t* sweeps;           // [nu]
+    int32_t* k;                // [nu]
+    int32_t* remaining;        // [1]
+    double* Hpart;             // [nu][nb/2][splits][1024]
+    double* Q;                 // [nu][nb/2][1024]
+};
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------------------
+// Laplacian stage
+// ------------------------------------------------------------------------------------------
+
+// grid (tiles_x * tiles_y, 1, nu), block (32, 8): 32x32 tile through smem so that both the table
+// read (along a W row) and the G write (along a G column) are contiguous.
+__global__ void lap_gather_kernel(LChunk C, const double* __restrict__ W, int w_rows,
+                                  const int32_t* __restrict__ items, int tiles_per_dim) {
+    __shared__ double tile[32][33];
+    __shared__ int idi[32], idj[32];
+    const int u = blockIdx.z;
+    const int n = C.n[u];
+    const int ti = blockIdx.x / tiles_per_dim, tj = blockIdx.x % tiles_per_dim;
+    if (ti * 32 >= n || tj * 32 >= n) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int64_t ioff = C.item_off[u];
+    if (ty == 0) idi[tx] = (ti * 32 + tx < n) ? items[ioff + ti * 32 + tx] : -1;
+    if (ty == 1) idj[tx] = (tj * 32 + tx < n) ? items[ioff + tj * 32 + tx] : -1;
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        const int il = ty + 8 * rr;
+        const unsigned mi = (unsigned)idi[il], mj = (unsigned)idj[tx];
+        double v = 0.0;
+        if (mi < (unsigned)w_rows && mj < (unsigned)w_rows) v = __ldg(W + (size_t)mi * w_rows + mj);
+        tile[il][tx] = v;
+    }
+    __syncthreads();
+    double* G = C.G + C.g_off[u];
+    const int ld = C.ld[u];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        const int jl = ty + 8 * rr;
+        const int i = ti * 32 + tx, j = tj * 32 + jl;
+        if (i < n && j < n) G[i + (size_t)j * ld] = tile[tx][jl];
+    }
+}
+
+// grid (ceil(nmax/128), 1, nu), block 128: thread per row, sequential j order (reference :199-203)
+__global__ void lap_degree_kernel(LChunk C) {
+    const int u = blockIdx.z;
+    const int n = C.n[u];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* G = C.G + C.g_off[u];
+    const int ld = C.ld[u];
+    double d = 0.0;
+    for (int j = 0; j < n; ++j) d = __dadd_rn(d, G[i + (size_t)j * ld]);
+    if (d == 0.0) d = 1.0;
+    C.deg[C.row_off[u] + i] = d;
+    C.scale[C.row_off[u] + i] = __dsqrt_rn(__ddiv_rn(1.0, d));
+}
+
+// grid (ceil(nmax/128), ceil(nmax/8), nu), block 128: 128 rows x 8 columns per CTA
+__global__ void lap_transform_kernel(LChunk C) {
+    const int u = blockIdx.z;
+    const int n = C.n[u];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double* G = C.G + C.g_off[u];
+    const int ld = C.ld[u];
+    const double* deg = C.deg + C.row_off[u];
+    const double* sc = C.scale + C.row_off[u];
+    const double si = sc[i], di = deg[i];
+    const int j0 = blockIdx.y * 8;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+        const int j = j0 + jj;
+        if (j < n) {
+            const double w = G[i + (size_t)j * ld];
+            const double ll = (i == j) ? __dsub_rn(di, w) : __dsub_rn(0.0, w);
+            G[i + (size_t)j * ld] = __dmul_rn(__dmul_rn(si, ll), sc[j]);
+        }
+    }
+}
+
+// thread per row: float accumulator over the full row, j ascending (reference :236-249)
+__global__ void lap_sigmin_kernel(LChunk C, double* __restrict__ sig_min) {
+    const int u = blockIdx.z;
+    const int n = C.n[u];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* G = C.G + C.g_off[u];
+    const int ld = C.ld[u];
+    float acc = 0.f;
+    for (int j = 0; j < n; ++j) {
+        const double x = G[i + (size_t)j * ld];
+        acc = __double2float_rn(__dadd_rn((double)acc, __dmul_rn(x, x)));
+    }
+    const float sig = __fsqrt_rn(acc);
+    sig_min[C.item_off[u] + i] = __dadd_rn((double)sig, 0.01);
+    atomicMax(&C.sigmax[u], __float_as_uint(sig));
+}
+
+// upper <- lower through a 32x32 smem tile (only tiles with ti <= tj do work), diagonal += 1.
+// grid (tiles*tiles, 1, nu), block (32, 8)
+__global__ void lap_symmetrize_kernel(LChunk C, int tiles_per_dim) {
+    __shared__ double tile[32][33];
+    const int u = blockIdx.z;
+    const int n = C.n[u];
+    const int ti = blockIdx.x / tiles_per_dim, tj = blockIdx.x % tiles_per_dim;
+    if (ti > tj || tj * 32 >= n) return;
+    double* G = C.G + C.g_off[u];
+    const int ld = C.ld[u];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    // read the lower tile (rows of block tj, columns of block ti): contiguous along rows
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        const int cl = ty + 8 * rr;
+        const int i = tj * 32 + tx, j = ti * 32 + cl;
+        tile[cl][tx] = (i < n && j < n) ? G[i + (size_t)j * ld] : 0.0;
+    }
+    __syncthreads();
+    // write the upper tile (rows of block ti, columns of block tj)
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        const int cl = ty + 8 * rr;
+        const int i = ti * 32 + tx, j = tj * 32 + cl;
+        if (i < n && j < n) {
+            if (i < j) G[i + (size_t)j * ld] = tile[tx][cl];
+            else if (i == j) G[i + (size_t)j * ld] += 1.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Block Jacobi
+// ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ bool bj_task(const LChunk& C, int u, int round, int slot, int& I, int& J) {
+    if (C.done[u]) return false;
+    circle_pair(C.nb, round, slot, I, J);
+    const int n = C.n[u];
+    return J * GSI_BJ_B < n;     // I < J; a block that starts beyond n is phantom
+}
+
+// grid (nb/2, splits, nu), block 128.  Partial Gram of the 32-column panel over this CTA's rows.
+__global__ void __launch_bounds__(128) bj_gram_kernel(LChunk C, int round) {
+    const int u = blockIdx.z, slot = blockIdx.x, split = blockIdx.y;
+    int I, J;
+    if (!bj_task(C, u, round, slot, I, J)) return;
+    const int ld = C.ld[u];
+    const int r_begin = split * GSI_BJ_ROWS;
+    if (r_begin >= ld) return;
+    const int r_end = min(ld, r_begin + GSI_BJ_ROWS);
+    const double* G = C.G + C.g_off[u];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lr = lane & 3, lc = lane >> 2;
+    // column pointers of the 4 fragments this lane loads: panel column 8t + lc
+    const double* colp[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int cc = 8 * t + lc;
+        const int gc = (cc < GSI_BJ_B) ? I * GSI_BJ_B + cc : J * GSI_BJ_B + (cc - GSI_BJ_B);
+        colp[t] = G + (size_t)gc * ld + lr;
+    }
+    double acc[10][2];
+#pragma unroll
+    for (int t = 0; t < 10; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    for (int r = r_begin + 4 * warp; r < r_end; r += 16) {
+        double f[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) f[t] = colp[t][r];
+        int idx = 0;
+#pragma unroll
+        for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+            for (int tj = ti; tj < 4; ++tj) { dmma884(acc[idx][0], acc[idx][1], f[ti], f[tj]); ++idx; }
+    }
+    __shared__ double red[4][10][64];
+#pragma unroll
+    for (int t = 0; t < 10; ++t) { red[warp][t][lane * 2] = acc[t][0]; red[warp][t][lane * 2 + 1] = acc[t][1]; }
+    __syncthreads();
+    double* H = C.Hpart + (((size_t)u * (C.nb >> 1) + slot) * C.splits + split) * 1024;
+    for (int e = threadIdx.x; e < 640; e += 128) {
+        const int t = e >> 6, w = e & 63;
+        const double v = red[0][t][w] + red[1][t][w] + red[2][t][w] + red[3][t][w];
+        // tile t -> (ti, tj): order (0,0)(0,1)(0,2)(0,3)(1,1)(1,2)(1,3)(2,2)(2,3)(3,3)
+        int ti, tj;
+        if (t < 4) { ti = 0; tj = t; } else if (t < 7) { ti = 1; tj = t - 3; } else if (t < 9) { ti = 2; tj = t - 5; } else { ti = 3; tj = 3; }
+        const int l = w >> 1, el = w & 1;
+        const int a = 8 * ti + (l >> 2), b = 8 * tj + 2 * (l & 3) + el;
+        H[a * 32 + b] = v;
+    }
+}
+
+// grid (nb/2, 1, nu), block 256.  H = sum of partials (upper tiles mirrored); one cyclic sweep of
+// two-sided Jacobi over the 32x32 panel Gram, rotations accumulated into Q.
+__global__ void __launch_bounds__(256) bj_inner_kernel(LChunk C, int round) {
+    const int u = blockIdx.z, slot = blockIdx.x;
+    int I, J;
+    if (!bj_task(C, u, round, slot, I, J)) return;
+    __shared__ double H[32][33];
+    __shared__ double Q[32][33];
+    __shared__ double cs[16][2];
+    __shared__ int pq[16][2];
+    __shared__ unsigned long long sh_max;
+    const int tid = threadIdx.x;
+    const int ld = C.ld[u];
+    const int nsplit = (ld + GSI_BJ_ROWS - 1) / GSI_BJ_ROWS;
+    const double* Hp = C.Hpart + ((size_t)u * (C.nb >> 1) + slot) * C.splits * 1024;
+    for (int e = tid; e < 1024; e += 256) {
+        const int a = e >> 5, b = e & 31;
+        if ((a >> 3) <= (b >> 3)) {
+            double v = 0.0;
+            for (int s = 0; s < nsplit; ++s) v += Hp[(size_t)s * 1024 + e];
+            H[a][b] = v;
+            if ((a >> 3) < (b >> 3)) H[b][a] = v;
+        }
+        Q[a][b] = (a == b) ? 1.0 : 0.0;
+    }
+    if (tid == 0) sh_max = 0ull;
+    __syncthreads();
+    for (int r = 0; r < 31; ++r) {
+        if (tid < 16) {
+            int p, q;
+            circle_pair(32, r, tid, p, q);
+            const double a = H[p][p], b = H[q][q], g = H[p][q];
+            double c = 1.0, s = 0.0, t;
+            const double ab = a * b, g2 = g * g;
+            if (ab > 0.0) {
+                atomicMax(&sh_max, dbits(g2 / ab));
+                if (g2 > GSI_ROT2 * ab) jacobi_cs(a, b, g, c, s, t);
+            }
+            cs[tid][0] = c; cs[tid][1] = s; pq[tid][0] = p; pq[tid][1] = q;
+        }
+        __syncthreads();
+        // column rotations of H and Q: 16 pairs x 32 rows x 2 matrices
+        for (int e = tid; e < 1024; e += 256) {
+            const int t = (e >> 5) & 15, i = e & 31, which = e >> 9;
+            const double c = cs[t][0], s = cs[t][1];
+            if (s != 0.0) {
+                const int p = pq[t][0], q = pq[t][1];
+                double (*M)[33] = which ? Q : H;
+                const double x = M[i][p], y = M[i][q];
+                M[i][p] = c * x - s * y;
+                M[i][q] = s * x + c * y;
+            }
+        }
+        __syncthreads();
+        // row rotations of H
+        for (int e = tid; e < 512; e += 256) {
+            const int t = e >> 5, j = e & 31;
+            const double c = cs[t][0], s = cs[t][1];
+            if (s != 0.0) {
+                const int p = pq[t][0], q = pq[t][1];
+                const double x = H[p][j], y = H[q][j];
+                H[p][j] = c * x - s * y;
+                H[q][j] = s * x + c * y;
+            }
+        }
+        __syncthreads();
+    }
+    double* Qg = C.Q + ((size_t)u * (C.nb >> 1) + slot) * 1024;
+    for (int e = tid; e < 1024; e += 256) Qg[e] = Q[e >> 5][e & 31];
+    if (tid == 0) atomicMax(&C.smax[u], sh_max);
+}
+
+// grid (nb/2, splits, nu), block 128.  P <- P Q for this CTA's rows, in place.
+__global__ void __launch_bounds__(128) bj_update_kernel(LChunk C, int round) {
+    const int u = blockIdx.z, slot = blockIdx.x, split = blockIdx.y;
+    int I, J;
+    if (!bj_task(C, u, round, slot, I, J)) return;
+    const int ld = C.ld[u];
+    const int r_begin = split * GSI_BJ_ROWS;
+    if (r_begin >= ld) return;
+    const int r_end = min(ld, r_begin + GSI_BJ_ROWS);
+    double* G = C.G + C.g_off[u];
+    const double* Qg = C.Q + ((size_t)u * (C.nb >> 1) + slot) * 1024;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lr = lane & 3, lc = lane >> 2;
+    // B fragments: Q[4kk + lr][8nt + lc]
+    double bq[8][4];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) bq[kk][nt] = Qg[(4 * kk + lr) * 32 + 8 * nt + lc];
+    // A fragment kk: P[r0 + lc][4kk + lr]   (panel column 4kk + lr)
+    size_t acol[8];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+        const int cc = 4 * kk + lr;
+        const int gc = (cc < GSI_BJ_B) ? I * GSI_BJ_B + cc : J * GSI_BJ_B + (cc - GSI_BJ_B);
+        acol[kk] = (size_t)gc * ld + lc;
+    }
+    // D fragment nt: out[r0 + lc][8nt + 2lr + e]
+    size_t dcol[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int cc = 8 * nt + 2 * lr + e;
+            const int gc = (cc < GSI_BJ_B) ? I * GSI_BJ_B + cc : J * GSI_BJ_B + (cc - GSI_BJ_B);
+            dcol[nt][e] = (size_t)gc * ld + lc;
+        }
+    for (int r0 = r_begin + 8 * warp; r0 < r_end; r0 += 32) {
+        double a[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) a[kk] = G[acol[kk] + r0];
+        double d[4][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            d[nt][0] = 0.0; d[nt][1] = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) dmma884(d[nt][0], d[nt][1], a[kk], bq[kk][nt]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            G[dcol[nt][0] + r0] = d[nt][0];
+            G[dcol[nt][1] + r0] = d[nt][1];
+        }
+    }
+}
+
+// one thread per user: close the sweep
+__global__ void bj_check_kernel(LChunk C) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= C.nu) return;
+    if (!C.done[u]) {
+        const int sw = ++C.sweeps[u];
+        if (C.smax[u] <= dbits(GSI_STOP2) || sw >= GSI_MAX_SWEEPS) C.done[u] = 1;
+        else atomicAdd(C.remaining, 1);
+        C.smax[u] = 0ull;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Finalisation
+// ------------------------------------------------------------------------------------------
+
+// grid (ceil(ncols/8), 1, nu), block 256: warp per column -> signed norm and eigenvalue
+__global__ void fin_colnorm_kernel(LChunk C) {
+    const int u = blockIdx.z;
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (c >= C.ncols) return;
+    const int lane = threadIdx.x & 31;
+    const int n = C.n[u], ld = C.ld[u];
+    const double* col = C.G + C.g_off[u] + (size_t)c * ld;
+    double a = 0.0, best = -1.0;
+    int arg = 0;
+    for (int i = lane; i < n; i += 32) {
+        const double v = col[i];
+        a = fma(v, v, a);
+        if (fabs(v) > best) { best = fabs(v); arg = i; }
+    }
+    a = warp_sum(a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    if (lane == 0) {
+        const double nr = sqrt(a);
+        // real columns have norm = lambda + 1 >= 1; phantom (zero) columns are marked by norm 0
+        const bool real = nr > 0.5;
+        C.colnorm[(size_t)u * C.ncols + c] = real ? ((col[arg] < 0.0) ? -nr : nr) : 0.0;
+        C.colval[(size_t)u * C.ncols + c] = real ? nr - 1.0 : 1e300;
+    }
+}
+
+// grid (nu), block 1024: ascending rank by counting, cutoff, eigenvalues out
+__global__ void __launch_bounds__(1024) fin_rank_kernel(LChunk C, double* __restrict__ lam_pad) {
+    const int u = blockIdx.x;
+    const int n = C.n[u];
+    const double* val = C.colval + (size_t)u * C.ncols;
+    int32_t* perm = C.perm + (size_t)u * C.ncols;
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    const float thr = __double2float_rn(__dadd_rn((double)__uint_as_float(C.sigmax[u]), 0.01));
+    int local = 0;
+    for (int c = threadIdx.x; c < C.ncols; c += blockDim.x) {
+        const double v = val[c];
+        int rank = 0;
+        for (int o = 0; o < C.ncols; ++o) {
+            const double w = val[o];
+            rank += (w < v || (w == v && o < c)) ? 1 : 0;
+        }
+        perm[rank] = c;
+        if (v < 1e299 && !(v > (double)thr)) ++local;
+    }
+    if (local) atomicAdd(&cnt, local);
+    __syncthreads();
+    const int k = max(cnt, 2);
+    if (threadIdx.x == 0) C.k[u] = k;
+    double* lam = lam_pad + C.lam_off[u];
+    for (int r = threadIdx.x; r < k; r += blockDim.x) lam[r] = (r < n) ? val[perm[r]] : 0.0;
+}
+
+// grid (ceil(kmax/32) * ceil(nmax/32), 1, nu), block (32, 8): vec[i*k + r] = G[i, perm[r]] / norm
+__global__ void fin_emit_kernel(LChunk C, double* __restrict__ vec_pad, int tiles_r) {
+    __shared__ double tile[32][33];
+    const int u = blockIdx.z;
+    const int n = C.n[u], k = C.k[u];
+    const int ti = blockIdx.x / tiles_r, tr = blockIdx.x % tiles_r;
+    if (ti * 32 >= n || tr * 32 >= k) return;
+    const int ld = C.ld[u];
+    const double* G = C.G + C.g_off[u];
+    const int32_t* perm = C.perm + (size_t)u * C.ncols;
+    const double* cn = C.colnorm + (size_t)u * C.ncols;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        const int rl = ty + 8 * rr;
+        const int r = tr * 32 + rl, i = ti * 32 + tx;
+        double v = 0.0;
+        if (r < k && r < n && i < n) { const int c = perm[r]; v = G[i + (size_t)c * ld] / cn[c]; }
+        tile[rl][tx] = v;
+    }
+    __syncthreads();
+    double* vec = vec_pad + C.vec_off[u];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        const int il = ty + 8 * rr;
+        const int i = ti * 32 + il, r = tr * 32 + tx;
+        if (i < n && r < k) vec[(size_t)i * k + r] = tile[tx][il];
+    }
+}

@@ -1,0 +1,151 @@
+/* gsi.h -- C ABI of libgsi.so: the sm_100a implementation of the per-user graph-signal
+ * interpolation path of Dhole/collaborative_filtering.
+ *
+ * The reference exposes no plugin/FFI interface: its boundary is a set of CLI
+ * programs whose math is inlined in main()/apply().  The entry points below are what a C++ host
+ * with the reference's argv/cwd/file behaviour binds instead of that inlined math; each one
+ * cites the reference code it replaces (file:line into the reference tree).  Plain C types,
+ * caller-owned buffers, int status returns, no exceptions across the boundary, one opaque
+ * handle per GPU.  There is no CPU fallback: every entry point fails with GSI_ERR_CUDA when no
+ * device is usable.
+ *
+ * ID conventions (precompute_local.cpp:19,107; knn.cpp:19,103): user ids downstream are
+ * user' = 2147483647 - user; movie ids are used as-is and index the weight table directly
+ * (row/col 0 unused, precompute_local.cpp:153).
+ */
+#ifndef GSI_H_
+#define GSI_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gsi_ctx gsi_ctx;
+
+enum {
+    GSI_OK = 0,
+    GSI_ERR_INVALID = 1,   /* bad argument (null pointer, unsorted/duplicate ids, ...)        */
+    GSI_ERR_CUDA = 2,      /* CUDA runtime error or no device; see gsi_last_error()            */
+    GSI_ERR_NOMEM = 3,     /* device or pinned-host allocation failed                          */
+    GSI_ERR_STATE = 4,     /* call order (e.g. precompute before weights were set)             */
+    GSI_ERR_CAPACITY = 5,  /* caller-provided output buffer too small; totals[] says how much  */
+    GSI_ERR_SINK = 6       /* the record sink returned non-zero                                 */
+};
+
+/* ---- context ------------------------------------------------------------------------------ */
+
+/* One context per GPU.  `stream` is a cudaStream_t (or NULL: the context creates its own
+ * non-blocking stream); all kernels of the context are launched on it. */
+int gsi_create(gsi_ctx** out, int device, void* stream);
+int gsi_destroy(gsi_ctx* ctx);
+/* Last error text of the context (or of the calling thread when ctx is NULL). */
+const char* gsi_last_error(const gsi_ctx* ctx);
+/* Library / build identification, e.g. "gsi 0.1 sm_100a". */
+const char* gsi_version(void);
+/* Device workspace budget in bytes for one chunk of users (default 8 GiB). */
+int gsi_set_workspace_limit(gsi_ctx* ctx, int64_t bytes);
+/* Synchronise the context's stream. */
+int gsi_sync(gsi_ctx* ctx);
+
+/* ---- item-similarity table  (replaces precompute_local.cpp:113-158, the dense `weights`
+ *      MatrixXd filled from ./out_fin_* ; the 2000-id cap of :116 is lifted) ------------------ */
+
+/* Dense directed table, rows x rows doubles, row-major: w[m1 * rows + m2] = weight(m1 -> m2).
+ * Copied to the device (synchronous). */
+int gsi_set_weights_host(gsi_ctx* ctx, const double* w, int rows);
+/* Same, but `d_w` already lives on this context's device; borrowed until the next
+ * gsi_set_weights_* / gsi_destroy. */
+int gsi_set_weights_device(gsi_ctx* ctx, const double* d_w, int rows);
+/* Edge list form of ./out_fin_* ("m1 m2 w" lines): builds the zero-initialised dense table of
+ * (max id + 1)^2 on the device and scatters the edges.  (m1, m2) pairs must be unique (knn2
+ * emits each directed edge once); `rows_out` receives max id + 1. */
+int gsi_set_weights_edges(gsi_ctx* ctx, const int32_t* m1, const int32_t* m2, const double* w,
+                          int64_t n_edges, int* rows_out);
+/* Device pointer and row count of the current table (for NCCL broadcast by the host side). */
+int gsi_get_weights(gsi_ctx* ctx, double** d_w, int* rows);
+
+/* ---- precompute  (replaces compute_eigens(), precompute_local_threads.cpp:100-213, i.e. the
+ *      body of the user loop precompute_local.cpp:165-282: gather W, degree, normalised
+ *      Laplacian, full symmetric eigensolve, sig_min, cutoff) ---------------------------------- *
+ *
+ * Users are given as CSR over rated movie ids: user u owns items[offsets[u] .. offsets[u+1]),
+ * strictly ascending (the reference's per-user map dedups, :108; its iteration order is hash
+ * order, we define ascending -- SURVEY.md B6).
+ *
+ * Per user the call produces what one out_eigen_ record holds (README.md:14-19):
+ *   sig_min[offsets[u] + i]    (double)  ||row_i(L)||_2 (float accumulate) + 0.01     (:169-182)
+ *   k[u]                                 number of kept eigenpairs, >= 2             (:185-194)
+ *   lam[lam_off[u] + j], j < k           eigenvalues ascending
+ *   vec[vec_off[u] + i*k + j]            eigenvectors, row-major n x k (row i = movie i), unit
+ *                                        norm, sign: the largest-|.| component is positive
+ * Records are laid out in PROCESSING order (users are bucketed by n); lam_off / vec_off locate
+ * each user's record and are not monotonic in u.  For n == 1 the reference reads uninitialised
+ * memory (:190-194); we define k = 2, lam = {1, 0}, vec = {1, 0}.
+ */
+
+/* Everything on the device.  d_lam / d_vec have capacity lam_cap / vec_cap doubles; upper
+ * bounds are sum(max(n,2)) and sum(n*max(n,2)).  totals[0], totals[1] (host) receive the doubles
+ * actually used.  Asynchronous on the context's stream except for a few scalar read-backs. */
+int gsi_precompute_device(gsi_ctx* ctx, int64_t n_users, const int64_t* h_offsets,
+                          const int32_t* d_items, double* d_sig_min, int32_t* d_k,
+                          int64_t* d_lam_off, int64_t* d_vec_off, double* d_lam, int64_t lam_cap,
+                          double* d_vec, int64_t vec_cap, int64_t* totals);
+
+/* Host buffers in, host buffers out (copies included).  Same layout as above. */
+int gsi_precompute_host(gsi_ctx* ctx, int64_t n_users, const int64_t* offsets,
+                        const int32_t* items, double* sig_min, int32_t* k, int64_t* lam_off,
+                        int64_t* vec_off, double* lam, int64_t lam_cap, double* vec,
+                        int64_t vec_cap, int64_t* totals);
+
+/* Streaming form for the CLI hosts (the analogue of save_output(),
+ * precompute_local_threads.cpp:89-98: records are handed over as they complete).  The sink is
+ * called once per chunk from the calling thread with pointers into pinned host staging memory
+ * that stay valid until it returns. */
+typedef struct gsi_record_chunk {
+    int64_t n_records;
+    const int64_t* user_index;  /* [n_records] index u of the record in the caller's CSR       */
+    const int32_t* n;           /* [n_records] rated movies                                      */
+    const int32_t* k;           /* [n_records] kept eigenpairs                                   */
+    const int64_t* lam_off;     /* [n_records] into lam                                          */
+    const int64_t* vec_off;     /* [n_records] into vec                                          */
+    const double* lam;
+    const double* vec;
+    const double* sig_min;      /* whole-batch array, index with the caller's offsets[u] + i    */
+} gsi_record_chunk;
+typedef int (*gsi_record_sink)(void* opaque, const gsi_record_chunk* chunk);
+int gsi_precompute_stream(gsi_ctx* ctx, int64_t n_users, const int64_t* offsets,
+                          const int32_t* items, gsi_record_sink sink, void* opaque);
+
+/* ---- measurement helpers ------------------------------------------------------------------- */
+
+/* Accumulated device time (ms, CUDA events on the context's stream) per kernel class since the
+ * last reset, and launch counts.  Classes: see GSI_T_* . */
+enum {
+    GSI_T_EIG_CTA = 0,     /* fused gather+Laplacian+sig_min+CTA-resident Jacobi (n <= 160)     */
+    GSI_T_LAP = 1,         /* gather / degree / Laplacian / sig_min kernels of the large path    */
+    GSI_T_BJ_GRAM = 2,     /* block-Jacobi Gram (DMMA)                                           */
+    GSI_T_BJ_INNER = 3,    /* block-Jacobi 32x32 rotation solve                                  */
+    GSI_T_BJ_UPDATE = 4,   /* block-Jacobi panel update (DMMA)                                   */
+    GSI_T_FINALIZE = 5,    /* norms, sort, cutoff, emit                                          */
+    GSI_T_COMPACT = 6,     /* offset scan + compaction                                           */
+    GSI_T_PREDICT = 7,
+    GSI_T_KNN = 8,
+    GSI_T_COUNT = 9
+};
+int gsi_timing_enable(gsi_ctx* ctx, int on);
+int gsi_timing_reset(gsi_ctx* ctx);
+/* ms[c]: device time of the launches that were bracketed by events; samples[c]: how many launches
+ * that time covers (the block-Jacobi rounds are sampled 1 in 8); launches[c]: all launches. */
+int gsi_timing_get(gsi_ctx* ctx, double* ms /*[GSI_T_COUNT]*/, int64_t* launches /*[GSI_T_COUNT]*/,
+                   int64_t* samples /*[GSI_T_COUNT]*/);
+/* Measured FP64 FMA throughput of this device in TFLOP/s (register-resident DFMA chains on every
+ * SM, CUDA events) -- the roofline denominator for the Jacobi kernels (MEASURED_PEAKS.json holds
+ * only HBM and bf16 tensor numbers).  `use_dmma` != 0 measures mma.sync m8n8k4 f64 instead. */
+int gsi_measure_fp64_tflops(gsi_ctx* ctx, int use_dmma, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSI_H_ */
