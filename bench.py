@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- users/s of the precompute hot path (gather + normalised Laplacian + full symmetric
+eigensolve + sig_min + cutoff) on ML-10M shaped synthetic data.
+
+Workload (per GPU, per step): one 1/8 shard of the ML-10M shape (71,567 users x 10,681 items,
+10.0M ratings; SURVEY.md 8d recipe, seed 31413), the shard a rank holds when the data set is
+user-sharded over an 8-GPU box by the n^3 cost model (LPT).  Weak scaling: rank r processes shard
+r, so --gpus 8 is exactly the whole ML-10M shape per step.  The item-similarity table W
+((N+1)^2 fp64, 913 MB) is generated on rank 0 and replicated with an NCCL broadcast.
+
+  value    users/s, device resident: CSR ids in HBM -> records (sig_min, k, lam, U) in HBM
+  e2e      users/s through the host-facing C ABI (gsi_precompute_stream): pinned host CSR in,
+           records out in pinned host memory, H2D / D2H copies inside the timed region
+  roofline the eigensolve kernels (the dominant device time) against the FP64 FMA peak measured
+           live (MEASURED_PEAKS.json has no FP64 number), algorithmic flops = 9 n^3 per user
+  cpu_baseline  oracle/cpu_ref (C++ restatement of precompute_local_threads.cpp, all host threads)
+           timed on a bounded stratified sample and extrapolated by the n^3 cost model
+
+--impl reference times that same CPU restatement as the reference arm (the reference's own
+binaries cannot be built here: Eigen/Boost/GraphLab are absent).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from collaborative_filtering_b200 import datasets as D  # noqa: E402
+from collaborative_filtering_b200 import shard as SH  # noqa: E402
+
+METRIC = "users/sec Laplacian+eigensolve at ML-10M shape"
+UNIT = "users/s"
+N_SHARDS = 8
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def build_workload(shape: str, rank: int):
+    """Ratings of `shape`, LPT-sharded into 8 by n^3; returns the CSR of shard (rank mod 8)."""
+    r = D.make_ratings(shape)
+    deg = r.degrees()
+    owners = SH.lpt_assign(deg, N_SHARDS)
+    idx = np.nonzero(owners == (rank % N_SHARDS))[0]
+    _, offsets, items, _ = D.subset(r, idx)
+    return r, offsets, items
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv = None
+            log("nvml unavailable:", e)
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        self.stop_flag = True
+        if self.samples:
+            return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: oracle/cpu_ref on a bounded stratified sample, extrapolated by n^3
+# ---------------------------------------------------------------------------------------------
+
+def cpu_reference_rate(weights, offsets, items, budget_s: float = 15.0, threads: int | None = None, seed: int = 0):
+    """users/s of the CPU restatement (reference's dense inverse + 2 GEMMs + eigensolve + text
+    formatting, std::thread pool) for the workload (offsets, items).  Users with n <= N_CAP are
+    sampled uniformly within log2(n) strata; heavier users are extrapolated with the n^3
+    coefficient of the largest measured stratum.  Returns (users_per_s, description, cores)."""
+    from oracle import cpu_ref as C
+    cores = threads or C.hardware_threads()
+    deg = np.diff(offsets)
+    rng = np.random.default_rng(seed)
+    # rough cost model: ~1.2e-9 s per n^3 per core for the honest restatement
+    coef = 1.2e-9
+    total_budget_cost = budget_s * cores / coef            # in n^3 units
+    n_cap = int(min(deg.max(), max(200.0, (total_budget_cost / (4.0 * cores)) ** (1.0 / 3.0))))
+    strata = {}
+    for u, n in enumerate(deg):
+        strata.setdefault(int(np.log2(max(n, 1))), []).append(u)
+    picked, per_stratum = [], {}
+    elig = [s for s in strata if 2 ** s <= n_cap]
+    share = total_budget_cost / max(1, len(elig))
+    for s in sorted(elig):
+        us = np.array([u for u in strata[s] if deg[u] <= n_cap])
+        if len(us) == 0:
+            continue
+        rng.shuffle(us)
+        cost = np.cumsum(deg[us].astype(np.float64) ** 3)
+        m = max(min(len(us), cores), int(np.searchsorted(cost, share)) + 1)
+        us = us[:m]
+        per_stratum[s] = us
+        picked.extend(us.tolist())
+    est_total = 0.0
+    last_coef = None
+    measured_s = 0.0
+    for s in sorted(per_stratum):
+        us = per_stratum[s]
+        off = np.zeros(len(us) + 1, dtype=np.int64)
+        np.cumsum(deg[us], out=off[1:])
+        it = np.concatenate([items[offsets[u]: offsets[u + 1]] for u in us]).astype(np.int32)
+        out = C.precompute(weights, off, it, n_threads=cores, honest=True, format_text=True)
+        measured_s += out["seconds"]
+        c3 = out["seconds"] / float((deg[us].astype(np.float64) ** 3).sum())
+        last_coef = c3
+        all_in = np.array([u for u in strata[s] if deg[u] <= n_cap])
+        est_total += c3 * float((deg[all_in].astype(np.float64) ** 3).sum())
+    heavy = deg[deg > n_cap].astype(np.float64)
+    est_total += (last_coef or coef / cores) * float((heavy ** 3).sum())
+    desc = ("%d of %d users (stratified by log2 n, n <= %d) timed in %.1f s on %d threads with text formatting; "
+            "%d heavier users extrapolated by the n^3 coefficient of the largest stratum"
+            % (len(picked), len(deg), n_cap, measured_s, cores, len(heavy)))
+    return len(deg) / est_total, desc, cores
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    r, offsets, items = build_workload(args.shape, 0)
+    w = D.make_weights(r.n_items)
+    for _ in range(args.warmup):
+        cpu_reference_rate(w, offsets, items, budget_s=1.0)
+    rates, t0 = [], time.perf_counter()
+    desc, cores = "", 0
+    for i in range(args.steps):
+        rate, desc, cores = cpu_reference_rate(w, offsets, items, budget_s=args.cpu_budget, seed=i)
+        rates.append(rate)
+    dt = time.perf_counter() - t0
+    v = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s shape, 1/8 user shard per GPU (LPT by n^3), synthetic W density 0.9" % args.shape,
+                   "users_per_step": int(len(offsets) - 1)},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from collaborative_filtering_b200.api import Context, upper_bounds
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    t_gen = time.time()
+    r, offsets, items = build_workload(args.shape, rank)
+    nu = len(offsets) - 1
+    deg = np.diff(offsets)
+    log("[rank %d] shard: %d users, nnz %d, max n %d, sum 9n^3 = %.3g flop (gen %.1fs)"
+        % (rank, nu, offsets[-1], deg.max(), 9.0 * (deg.astype(np.float64) ** 3).sum(), time.time() - t_gen))
+
+    # item-similarity table: generated on rank 0, replicated by NCCL broadcast (north_star)
+    n1 = r.n_items + 1
+    d_w = torch.empty((n1, n1), dtype=torch.float64, device=dev)
+    if rank == 0:
+        g = torch.Generator(device=dev)
+        g.manual_seed(D.SEED + 1)
+        u = torch.rand((n1, n1), generator=g, device=dev, dtype=torch.float64)
+        keep = torch.rand((n1, n1), generator=g, device=dev) < 0.9
+        wv = torch.round((1.0 - 0.5 * u) * 1e6) / 1e6
+        wv = torch.where(keep, wv, torch.zeros_like(wv)).triu(1)
+        d_w.copy_(wv + wv.T)
+        d_w[0, :] = 0
+        d_w[:, 0] = 0
+        del u, keep, wv
+    if world > 1:
+        dist.broadcast(d_w, src=0)
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream()
+    ctx = Context(local_rank, stream=stream.cuda_stream)
+    ctx.set_workspace_limit(args.workspace_gb << 30)
+    ctx.set_weights(d_w)
+    fp64_peak = ctx.measure_fp64_tflops(False)
+    dmma_peak = ctx.measure_fp64_tflops(True)
+
+    lam_cap, vec_cap = upper_bounds(offsets)
+    d_items = torch.from_numpy(items).to(dev)
+    d_sig = torch.empty(int(offsets[-1]), dtype=torch.float64, device=dev)
+    d_k = torch.empty(nu, dtype=torch.int32, device=dev)
+    d_lo = torch.empty(nu, dtype=torch.int64, device=dev)
+    d_vo = torch.empty(nu, dtype=torch.int64, device=dev)
+    d_lam = torch.empty(lam_cap, dtype=torch.float64, device=dev)
+    d_vec = torch.empty(vec_cap, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step_device():
+        return ctx.precompute_device(offsets, d_items, d_sig, d_k, d_lo, d_vo, d_lam, d_vec)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    # ---- timed region: exactly K steps, CUDA events on the launching stream ----
+    ctx.timing_enable(True)
+    ctx.timing_reset()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        flush.zero_()
+        used = step_device()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.result()
+    ms_total = e0.elapsed_time(e1)
+    timing = ctx.timing()
+    ctx.timing_enable(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    users_total = torch.tensor([nu], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(users_total, op=dist.ReduceOp.SUM)
+    value = float(users_total.item()) * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e through the host-facing C ABI: pinned CSR in, records out in pinned staging ----
+    h_off = offsets
+    h_items = torch.from_numpy(items).pin_memory()
+    d2h = [0]
+
+    def sink(ch):
+        n = np.ctypeslib.as_array(ch.n, shape=(ch.n_records,))
+        k = np.ctypeslib.as_array(ch.k, shape=(ch.n_records,))
+        d2h[0] += int((n.astype(np.int64) * k).sum() * 8 + k.sum() * 8 + n.sum() * 8 + ch.n_records * 20)
+        return 0
+
+    ctx.precompute_stream(h_off, h_items.numpy(), sink)       # warm the staging buffers
+    barrier()
+    d2h[0] = 0
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        ctx.precompute_stream(h_off, h_items.numpy(), sink)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = float(users_total.item()) * args.e2e_steps / float(t.item())
+    h2d_bytes = int(items.nbytes)
+    d2h_bytes = d2h[0] // max(1, args.e2e_steps)
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel group (live CUDA-event times of the timed region) ----
+        def est_ms(name):
+            v = timing[name]
+            return v["ms"] * (v["launches"] / v["samples"]) if v["samples"] else 0.0
+        small = deg[deg <= 160].astype(np.float64)
+        large = deg[deg > 160].astype(np.float64)
+        groups = {
+            "bj_gram+bj_inner+bj_update (block Jacobi, n>160)": (["bj_gram", "bj_inner", "bj_update"], 9.0 * (large ** 3).sum()),
+            "eig_cta (fused gather+Laplacian+Jacobi, n<=160)": (["eig_cta"], 9.0 * (small ** 3).sum()),
+        }
+        kernels = {k: {"ms_per_step": est_ms(k) / args.steps, "launches_per_step": timing[k]["launches"] / args.steps,
+                       "avg_launch_us": (1e3 * timing[k]["ms"] / timing[k]["samples"]) if timing[k]["samples"] else None}
+                   for k in timing if timing[k]["launches"]}
+        top = max(groups, key=lambda g: sum(est_ms(k) for k in groups[g][0]))
+        names, flop = groups[top]
+        top_ms = sum(est_ms(k) for k in names) / args.steps
+        achieved = flop / (top_ms * 1e-3) / 1e12 if top_ms > 0 else 0.0
+        lap_bytes = float((8.0 * large ** 2 + 12.0 * large).sum())          # 8n^2 (fp64 table) + ids + sig_min
+        lap_ms = est_ms("lap") / args.steps
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        roofline = {
+            "kernel": top, "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+            "peak_source": "FP64 FMA peak measured live by gsi_measure_fp64_tflops (MEASURED_PEAKS.json has no FP64 figure); DMMA probe %.1f TF/s" % dmma_peak,
+            "algorithmic_flop_per_launch_group": flop,
+            "executed_vs_algorithmic": "block Jacobi executes ~8 n^3 flop per sweep x ~9 sweeps; only 9 n^3 per user is credited",
+            "secondary": {"kernel": "lap_* (gather+Laplacian+sig_min, n>160)", "bound": "hbm",
+                          "achieved": (lap_bytes / (lap_ms * 1e-3) / 1e9) if lap_ms > 0 else None, "peak": hbm_peak,
+                          "unit": "GB/s", "frac": (lap_bytes / (lap_ms * 1e-3) / 1e9 / hbm_peak) if lap_ms > 0 else None,
+                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
+        }
+        launches = int(sum(v["launches"] for v in timing.values()) // args.steps)
+        # ---- CPU baseline on this box's host cores (bounded sample) ----
+        cpu = None
+        if not args.no_cpu:
+            w_host = d_w.cpu().numpy()
+            rate, desc, cores = cpu_reference_rate(w_host, offsets, items, budget_s=args.cpu_budget)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s shape, 1/8 user shard per GPU (LPT by n^3), synthetic W density 0.9" % args.shape,
+                       "users_per_step_per_gpu": nu, "nnz_per_step_per_gpu": int(offsets[-1]), "max_n": int(deg.max()),
+                       "l2": "256 MiB flush write between steps; working set per step >> 126 MB L2",
+                       "outputs_doubles_per_step": list(used)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "steps": args.e2e_steps},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "kernels": kernels,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gsi", choices=["gsi", "reference"])
+    ap.add_argument("--shape", default="ml-10m", choices=sorted(D.SHAPES))
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workspace-gb", type=int, default=16)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

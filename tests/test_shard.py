@@ -1,0 +1,76 @@
+"""Host-side multi-GPU logic on CPU: LPT user sharding, and a world_size-2 gloo run that checks
+the ranks' shards partition the users and that W replication by broadcast is bit-identical."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from collaborative_filtering_b200 import datasets as D
+from collaborative_filtering_b200 import shard as SH
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_lpt_partition_and_balance():
+    r = D.make_ratings("ml-1m")
+    deg = r.degrees()
+    for world in (1, 2, 4, 8):
+        owner = SH.lpt_assign(deg, world)
+        assert owner.min() == 0 and owner.max() == world - 1
+        parts = [SH.shard_users(deg, k, world) for k in range(world)]
+        allu = np.sort(np.concatenate(parts))
+        assert np.array_equal(allu, np.arange(r.n_users))           # every user exactly once
+        # the heavy tail is spread: imbalance bounded by the single heaviest user
+        heaviest = SH.user_cost(deg).max() / (SH.user_cost(deg).sum() / world)
+        assert SH.imbalance(deg, owner, world) <= max(1.02, heaviest + 1e-9)
+
+
+_WORKER = r"""
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, %r)
+from collaborative_filtering_b200 import datasets as D, shard as SH
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["PORT"],
+                        rank=int(os.environ["RANK"]), world_size=2)
+rank = dist.get_rank()
+r = D.make_ratings("ml-100k")
+mine = SH.shard_users(r.degrees(), rank, 2)
+# W replicated by broadcast from rank 0
+w = torch.from_numpy(D.make_weights(64)) if rank == 0 else torch.zeros((65, 65), dtype=torch.float64)
+dist.broadcast(w, src=0)
+flag = torch.zeros(r.n_users, dtype=torch.int32)
+flag[torch.from_numpy(mine)] = 1
+dist.all_reduce(flag)
+cost = torch.tensor([float(SH.user_cost(r.degrees()[mine]).sum())], dtype=torch.float64)
+costs = [torch.zeros(1, dtype=torch.float64) for _ in range(2)]
+dist.all_gather(costs, cost)
+if rank == 0:
+    assert int(flag.min()) == 1 and int(flag.max()) == 1, "shards must partition the users"
+    assert np.array_equal(w.numpy(), D.make_weights(64))
+    c = [float(x) for x in costs]
+    assert max(c) / (sum(c) / 2) < 1.05, c
+    print("OK", c)
+else:
+    assert np.array_equal(w.numpy(), D.make_weights(64))
+dist.destroy_process_group()
+""" % ROOT
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "OK" in outs[0]
