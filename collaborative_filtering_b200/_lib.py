@@ -49,6 +49,15 @@ SYMBOLS = {
                             [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "gsi_precompute_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                              RECORD_SINK, ctypes.c_void_p]),
+    "gsi_predict_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 8 + [ctypes.c_int64, ctypes.c_void_p,
+                                        ctypes.c_int64] + [ctypes.c_void_p] * 6),
+    "gsi_predict_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 18),
+    "gsi_knn_build_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "gsi_knn_edges_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
+    "gsi_knn_corated_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                            ctypes.c_void_p]),
+    "gsi_knn3_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 6),
     "gsi_timing_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "gsi_timing_reset": (ctypes.c_int, [ctypes.c_void_p]),
     "gsi_timing_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

@@ -161,6 +161,77 @@ class Context:
         cb = _lib.RECORD_SINK(_cb)
         self._check(self._lib.gsi_precompute_stream(self._h, len(offsets) - 1, _ptr(offsets), _ptr(items), cb, None))
 
+    # ---- predict (local_calc_precomp.cpp:217-380) ----
+    def predict(self, recs: Records, ratings, w_lim=None, pair_mask=None) -> dict:
+        """One prediction per (user, rated movie) pair of ``recs`` (gsi_predict_host).
+        ``ratings`` [nnz]: the users' own ratings, aligned with recs.items.  ``w_lim`` [nnz]: cutoff
+        per pair (default: the record's own sig_min, i.e. bug B1 off).  Returns arrays [nnz]."""
+        nnz = int(recs.offsets[-1])
+        ratings = np.ascontiguousarray(ratings, dtype=np.float64)
+        w_lim = np.ascontiguousarray(recs.sig_min if w_lim is None else w_lim, dtype=np.float64)
+        assert len(ratings) == nnz and len(w_lim) == nnz
+        mask = None if pair_mask is None else np.ascontiguousarray(pair_mask, dtype=np.uint8)
+        err = np.zeros(nnz, dtype=np.float32)
+        kk = np.zeros(nnz, dtype=np.int32)
+        pred = np.zeros(nnz, dtype=np.float64)
+        status = np.zeros(nnz, dtype=np.int32)
+        cols = np.zeros(nnz, dtype=np.int32)
+        lam = np.ascontiguousarray(recs.lam, dtype=np.float64)
+        vec = np.ascontiguousarray(recs.vec, dtype=np.float64)
+        self._check(self._lib.gsi_predict_host(
+            self._h, len(recs.offsets) - 1, _ptr(recs.offsets), _ptr(recs.items), _ptr(w_lim), _ptr(ratings),
+            _ptr(np.ascontiguousarray(recs.k, dtype=np.int32)), _ptr(np.ascontiguousarray(recs.lam_off, dtype=np.int64)),
+            _ptr(np.ascontiguousarray(recs.vec_off, dtype=np.int64)), _ptr(lam), len(lam), _ptr(vec), len(vec),
+            _ptr(mask), _ptr(err), _ptr(kk), _ptr(pred), _ptr(status), _ptr(cols)))
+        return dict(err=err, kk=kk, pred=pred, status=status, cols=cols)
+
+    # ---- knn chain (knn.cpp / knn2.cpp / knn3.cpp) ----
+    def knn_build(self, offsets, items, ratings, rows: int, install_weights: bool = True):
+        """knn2 over the TRAIN ratings (CSR by user).  Returns the out_fin_ edges (m1, m2, w float32)
+        in ascending (m1, m2) order; optionally installs the dense table as the context's weights."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        items = np.ascontiguousarray(items, dtype=np.int32)
+        ratings = np.ascontiguousarray(ratings, dtype=np.float32)
+        ne = ctypes.c_int64(0)
+        self._check(self._lib.gsi_knn_build_host(self._h, len(offsets) - 1, _ptr(offsets), _ptr(items), _ptr(ratings), rows,
+                                                 int(install_weights), ctypes.byref(ne)))
+        a = np.zeros(ne.value, dtype=np.int32)
+        b = np.zeros(ne.value, dtype=np.int32)
+        w = np.zeros(ne.value, dtype=np.float32)
+        self._check(self._lib.gsi_knn_edges_host(self._h, _ptr(a), _ptr(b), _ptr(w), ne.value))
+        return a, b, w
+
+    def knn_corated(self, offsets, items, rows: int) -> np.ndarray:
+        """knn step 1 (out_edg_): dense boolean co-rating matrix over ALL users (train + validate)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        items = np.ascontiguousarray(items, dtype=np.int32)
+        co = np.zeros((rows, rows), dtype=np.uint8)
+        self._check(self._lib.gsi_knn_corated_host(self._h, len(offsets) - 1, _ptr(offsets), _ptr(items), rows, _ptr(co)))
+        return co
+
+    def knn3(self, offsets, items, ratings):
+        """knn3 over the validate users.  Returns (avg_mse, err_sum[rows], cnt[rows], has_edge[rows]);
+        avg_mse = sum_m (err_sum/cnt) / num_vertices exactly as knn3.cpp:234-264 (float sums,
+        ascending movie id)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        items = np.ascontiguousarray(items, dtype=np.int32)
+        ratings = np.ascontiguousarray(ratings, dtype=np.float32)
+        rows = ctypes.c_int(0)
+        p = ctypes.c_void_p()
+        self._check(self._lib.gsi_get_weights(self._h, ctypes.byref(p), ctypes.byref(rows)))
+        err = np.zeros(rows.value, dtype=np.float32)
+        cnt = np.zeros(rows.value, dtype=np.int32)
+        has = np.zeros(rows.value, dtype=np.uint8)
+        self._check(self._lib.gsi_knn3_host(self._h, len(offsets) - 1, _ptr(offsets), _ptr(items), _ptr(ratings), _ptr(err),
+                                            _ptr(cnt), _ptr(has)))
+        total = np.float32(0)
+        for m in np.nonzero(cnt)[0]:
+            e = np.float32(err[m] / np.float32(cnt[m]))
+            if not np.isnan(e):
+                total = np.float32(total + e)
+        nv = int(np.count_nonzero((cnt > 0) | (has > 0)))
+        return (float(total) / nv if nv else float("nan")), err, cnt, has
+
     # ---- measurement ----
     def timing_enable(self, on: bool = True):
         self._check(self._lib.gsi_timing_enable(self._h, int(on)))

@@ -13,6 +13,8 @@
 #include "kern_bj.cuh"
 #include "kern_eig_cta.cuh"
 #include "kern_out.cuh"
+#include "kern_predict.cuh"
+#include "kern_knn.cuh"
 
 static thread_local std::string g_tls_err;
 
@@ -91,6 +93,9 @@ struct PinBuf {
 };
 
 struct Workspace {
+    DevBuf k_off, k_items, k_rat, k_cnt, k_num, k_S, k_ecnt, k_eoff, k_ea, k_eb, k_ew, k_co, k_err, k_mcnt, k_has;
+    int64_t knn_edges = 0;
+    DevBuf pred_meta, pred_work, p_off, p_items, p_wlim, p_rat, p_k, p_lamoff, p_vecoff, p_lam, p_vec, p_err, p_kk, p_pred, p_status, p_cols;
     DevBuf meta, vec_pad, lam_pad, G, rows, cols, perm, hpart, q, totals, items, sig, outk, outlam, outvec, stage_vec, stage_lam, probe;
     PinBuf h_meta, h_stage_vec, h_stage_lam, h_small, h_k, h_lamoff, h_vecoff, h_sig;
 };
@@ -146,6 +151,12 @@ extern "C" int gsi_destroy(gsi_ctx* c) {
     DevBuf* d[] = {&w.meta, &w.vec_pad, &w.lam_pad, &w.G, &w.rows, &w.cols, &w.perm, &w.hpart, &w.q, &w.totals, &w.items,
                    &w.sig, &w.outk, &w.outlam, &w.outvec, &w.stage_vec, &w.stage_lam, &w.probe};
     for (auto b : d) b->release();
+    DevBuf* d2[] = {&w.pred_meta, &w.pred_work, &w.p_off, &w.p_items, &w.p_wlim, &w.p_rat, &w.p_k, &w.p_lamoff, &w.p_vecoff,
+                    &w.p_lam, &w.p_vec, &w.p_err, &w.p_kk, &w.p_pred, &w.p_status, &w.p_cols};
+    for (auto b : d2) b->release();
+    DevBuf* d3[] = {&w.k_off, &w.k_items, &w.k_rat, &w.k_cnt, &w.k_num, &w.k_S, &w.k_ecnt, &w.k_eoff, &w.k_ea, &w.k_eb, &w.k_ew,
+                    &w.k_co, &w.k_err, &w.k_mcnt, &w.k_has};
+    for (auto b : d3) b->release();
     PinBuf* p[] = {&w.h_meta, &w.h_stage_vec, &w.h_stage_lam, &w.h_small, &w.h_k, &w.h_lamoff, &w.h_vecoff, &w.h_sig};
     for (auto b : p) b->release();
     if (ctx->own_w && ctx->d_w) cudaFree(ctx->d_w);
@@ -639,6 +650,304 @@ extern "C" int gsi_precompute_host(gsi_ctx* ctx, int64_t nu, const int64_t* offs
     if (rc != GSI_OK) return rc;
     if (s.overflow) return gsi_fail(ctx, GSI_ERR_CAPACITY, "output capacity too small: need lam %lld / vec %lld doubles",
                                     (long long)s.lam_used, (long long)s.vec_used);
+    return GSI_OK;
+}
+
+// ---- predict ------------------------------------------------------------------------------------
+struct PredTask { int64_t pair; int32_t user; int32_t k; int32_t n; };
+
+extern "C" int gsi_predict_device(gsi_ctx* ctx, int64_t nu, const int64_t* h_off, const int32_t* h_k,
+                                  const int64_t* d_off, const int32_t* d_items, const double* d_w_lim,
+                                  const double* d_ratings, const int32_t* d_k, const int64_t* d_lam_off,
+                                  const int64_t* d_vec_off, const double* d_lam, const double* d_vec,
+                                  const uint8_t* pair_mask, float* d_err, int32_t* d_kk, double* d_pred,
+                                  int32_t* d_status, int32_t* d_cols, int64_t* n_pairs_done) {
+    if (!ctx) return gsi_fail(nullptr, GSI_ERR_INVALID, "null context");
+    if (!ctx->d_w) return gsi_fail(ctx, GSI_ERR_STATE, "gsi_predict: no weight table set (call gsi_set_weights_*)");
+    if (nu < 0 || !h_off || !h_k || (nu > 0 && (!d_off || !d_items || !d_w_lim || !d_ratings || !d_k || !d_lam_off || !d_vec_off ||
+                                                  !d_lam || !d_vec || !d_err || !d_kk || !d_pred || !d_status || !d_cols)))
+        return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_predict_device: null argument");
+    GSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    Workspace& ws = WS(ctx);
+    const int64_t nnz = nu ? h_off[nu] : 0;
+    // status defaults to SKIPPED, err to 0
+    if (nnz) {
+        std::vector<int32_t> skipped((size_t)nnz, GSI_PRED_SKIPPED);
+        GSI_CUDA(ctx, cudaMemcpyAsync(d_status, skipped.data(), nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+        GSI_CUDA(ctx, cudaMemsetAsync(d_err, 0, nnz * 4, ctx->stream));
+        GSI_CUDA(ctx, cudaMemsetAsync(d_kk, 0, nnz * 4, ctx->stream));
+        GSI_CUDA(ctx, cudaMemsetAsync(d_pred, 0, nnz * 8, ctx->stream));
+        GSI_CUDA(ctx, cudaMemsetAsync(d_cols, 0, nnz * 4, ctx->stream));
+        GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    // classes by the user's kept-eigenpair count (upper bound of the columns a pair can use)
+    static const int kClassC[] = {16, 32, 48, 64, 96, 128};
+    const int n_smem_classes = 6;
+    std::vector<std::vector<PredTask>> cls(n_smem_classes + 1);
+    for (int64_t u = 0; u < nu; ++u) {
+        const int n = (int)(h_off[u + 1] - h_off[u]);
+        const int k = h_k[u];
+        int c = 0;
+        while (c < n_smem_classes && (k > kClassC[c] || predict_smem_bytes(kClassC[c], n, true) > 200 * 1024)) ++c;
+        for (int i = 0; i < n; ++i) {
+            const int64_t pair = h_off[u] + i;
+            if (pair_mask && !pair_mask[pair]) continue;
+            cls[c].push_back({pair, (int32_t)u, k, n});
+        }
+    }
+    int64_t done = 0;
+    for (int c = 0; c <= n_smem_classes; ++c) {
+        std::vector<PredTask>& tasks = cls[c];
+        if (tasks.empty()) continue;
+        const bool in_smem = c < n_smem_classes;
+        // big-k tasks: descending k so that a wave has similar cost
+        if (!in_smem) std::stable_sort(tasks.begin(), tasks.end(), [](const PredTask& a, const PredTask& b) { return a.k > b.k; });
+        std::vector<int64_t> t_pair(tasks.size());
+        std::vector<int32_t> t_user(tasks.size());
+        int nmax = 0, kmax = 0;
+        for (size_t t = 0; t < tasks.size(); ++t) {
+            t_pair[t] = tasks[t].pair; t_user[t] = tasks[t].user;
+            nmax = std::max(nmax, tasks[t].n); kmax = std::max(kmax, tasks[t].k);
+        }
+        MetaBuilder mb;
+        const size_t o_pair = mb.add(t_pair), o_user = mb.add(t_user);
+        int rc;
+        if ((rc = ws.pred_meta.ensure(ctx, mb.host.size())) != GSI_OK) return rc;
+        GSI_CUDA(ctx, cudaMemcpyAsync(ws.pred_meta.p, mb.host.data(), mb.host.size(), cudaMemcpyHostToDevice, ctx->stream));
+        GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        PredParams P;
+        P.W = ctx->d_w; P.w_rows = ctx->w_rows; P.items = d_items; P.offsets = d_off; P.w_lim = d_w_lim; P.ratings = d_ratings;
+        P.k = d_k; P.lam_off = d_lam_off; P.vec_off = d_vec_off; P.lam = d_lam; P.vec = d_vec;
+        P.task_pair = (const int64_t*)(ws.pred_meta.as<char>() + o_pair);
+        P.task_user = (const int32_t*)(ws.pred_meta.as<char>() + o_user);
+        P.err = d_err; P.kk = d_kk; P.pred = d_pred; P.status = d_status; P.cols_used = d_cols;
+        P.work = nullptr; P.work_stride = 0; P.nmax = nmax; P.m_in_smem = in_smem ? 1 : 0;
+        if (in_smem) {
+            P.cmax = kClassC[c];
+            const size_t smem = predict_smem_bytes(P.cmax, nmax, true);
+            GSI_CUDA(ctx, cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+            const int64_t wave = 1 << 20;
+            for (int64_t b = 0; b < (int64_t)tasks.size(); b += wave) {
+                const int cnt = (int)std::min<int64_t>(wave, tasks.size() - b);
+                P.task_base = (int)b;
+                GsiSpan sp(ctx, GSI_T_PREDICT, 1);
+                predict_kernel<<<cnt, 256, smem, ctx->stream>>>(P);
+                sp.end();
+                GSI_CUDA(ctx, cudaGetLastError());
+            }
+        } else {
+            // waves of CTAs, each with a private kmax^2 scratch in global memory
+            size_t b = 0;
+            while (b < tasks.size()) {
+                const int kwave = tasks[b].k;                       // largest k of this wave (sorted)
+                const int64_t stride = (int64_t)kwave * kwave;
+                int64_t wave = std::max<int64_t>(1, std::min<int64_t>(4 * ctx->sm_count, (ctx->ws_limit / 2) / (stride * 8)));
+                wave = std::min<int64_t>(wave, tasks.size() - b);
+                if ((rc = ws.pred_work.ensure(ctx, (size_t)wave * stride * 8)) != GSI_OK) return rc;
+                P.cmax = kwave; P.work = ws.pred_work.as<double>(); P.work_stride = stride; P.task_base = (int)b;
+                const size_t smem = predict_smem_bytes(P.cmax, nmax, false);
+                if (smem > 220 * 1024) return gsi_fail(ctx, GSI_ERR_INVALID, "predict: user too large for the staging buffers (n=%d, k=%d)", nmax, kwave);
+                GSI_CUDA(ctx, cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+                GsiSpan sp(ctx, GSI_T_PREDICT, 1);
+                predict_kernel<<<(int)wave, 256, smem, ctx->stream>>>(P);
+                sp.end();
+                GSI_CUDA(ctx, cudaGetLastError());
+                b += wave;
+            }
+        }
+        done += (int64_t)tasks.size();
+        GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // pred_meta is reused by the next class
+    }
+    if (n_pairs_done) *n_pairs_done = done;
+    return GSI_OK;
+}
+
+extern "C" int gsi_predict_host(gsi_ctx* ctx, int64_t nu, const int64_t* offsets, const int32_t* items, const double* w_lim,
+                                const double* ratings, const int32_t* k, const int64_t* lam_off, const int64_t* vec_off,
+                                const double* lam, int64_t lam_len, const double* vec, int64_t vec_len, const uint8_t* pair_mask,
+                                float* err, int32_t* kk, double* pred, int32_t* status, int32_t* cols) {
+    if (!ctx) return gsi_fail(nullptr, GSI_ERR_INVALID, "null context");
+    if (nu < 0 || !offsets || (nu > 0 && (!items || !w_lim || !ratings || !k || !lam_off || !vec_off || !lam || !vec || !err || !kk || !pred || !status || !cols)))
+        return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_predict_host: null argument");
+    if (nu == 0) return GSI_OK;
+    GSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    Workspace& ws = WS(ctx);
+    const int64_t nnz = offsets[nu];
+    for (int64_t u = 0; u < nu; ++u) {
+        const int64_t n = offsets[u + 1] - offsets[u];
+        if (n < 1 || k[u] < 1) return gsi_fail(ctx, GSI_ERR_INVALID, "user %lld: empty record", (long long)u);
+        if (lam_off[u] < 0 || lam_off[u] + k[u] > lam_len || vec_off[u] < 0 || vec_off[u] + n * k[u] > vec_len)
+            return gsi_fail(ctx, GSI_ERR_INVALID, "user %lld: record offsets outside lam/vec", (long long)u);
+    }
+    int rc;
+    struct Up { DevBuf* b; const void* src; size_t bytes; };
+    Up ups[] = {{&ws.p_off, offsets, (size_t)(nu + 1) * 8}, {&ws.p_items, items, (size_t)nnz * 4}, {&ws.p_wlim, w_lim, (size_t)nnz * 8},
+                {&ws.p_rat, ratings, (size_t)nnz * 8}, {&ws.p_k, k, (size_t)nu * 4}, {&ws.p_lamoff, lam_off, (size_t)nu * 8},
+                {&ws.p_vecoff, vec_off, (size_t)nu * 8}, {&ws.p_lam, lam, (size_t)lam_len * 8}, {&ws.p_vec, vec, (size_t)vec_len * 8}};
+    for (auto& x : ups) {
+        if ((rc = x.b->ensure(ctx, x.bytes)) != GSI_OK) return rc;
+        GSI_CUDA(ctx, cudaMemcpyAsync(x.b->p, x.src, x.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if ((rc = ws.p_err.ensure(ctx, nnz * 4)) != GSI_OK) return rc;
+    if ((rc = ws.p_kk.ensure(ctx, nnz * 4)) != GSI_OK) return rc;
+    if ((rc = ws.p_pred.ensure(ctx, nnz * 8)) != GSI_OK) return rc;
+    if ((rc = ws.p_status.ensure(ctx, nnz * 4)) != GSI_OK) return rc;
+    if ((rc = ws.p_cols.ensure(ctx, nnz * 4)) != GSI_OK) return rc;
+    GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    rc = gsi_predict_device(ctx, nu, offsets, k, ws.p_off.as<int64_t>(), ws.p_items.as<int32_t>(), ws.p_wlim.as<double>(),
+                            ws.p_rat.as<double>(), ws.p_k.as<int32_t>(), ws.p_lamoff.as<int64_t>(), ws.p_vecoff.as<int64_t>(),
+                            ws.p_lam.as<double>(), ws.p_vec.as<double>(), pair_mask, ws.p_err.as<float>(), ws.p_kk.as<int32_t>(),
+                            ws.p_pred.as<double>(), ws.p_status.as<int32_t>(), ws.p_cols.as<int32_t>(), nullptr);
+    if (rc != GSI_OK) return rc;
+    GSI_CUDA(ctx, cudaMemcpyAsync(err, ws.p_err.p, nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GSI_CUDA(ctx, cudaMemcpyAsync(kk, ws.p_kk.p, nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GSI_CUDA(ctx, cudaMemcpyAsync(pred, ws.p_pred.p, nnz * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GSI_CUDA(ctx, cudaMemcpyAsync(status, ws.p_status.p, nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GSI_CUDA(ctx, cudaMemcpyAsync(cols, ws.p_cols.p, nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GSI_OK;
+}
+
+// ---- knn chain ------------------------------------------------------------------------------------
+static int knn_upload_csr(gsi_ctx* ctx, int64_t nu, const int64_t* off, const int32_t* items, const float* ratings, int* nmax) {
+    Workspace& ws = WS(ctx);
+    int rc;
+    if (off[0] != 0) return gsi_fail(ctx, GSI_ERR_INVALID, "offsets[0] must be 0");
+    int mx = 0;
+    for (int64_t u = 0; u < nu; ++u) {
+        if (off[u + 1] < off[u]) return gsi_fail(ctx, GSI_ERR_INVALID, "offsets must be non-decreasing");
+        mx = std::max<int64_t>(mx, off[u + 1] - off[u]);
+    }
+    *nmax = mx;
+    const int64_t nnz = off[nu];
+    if ((rc = ws.k_off.ensure(ctx, (nu + 1) * 8)) != GSI_OK) return rc;
+    if ((rc = ws.k_items.ensure(ctx, std::max<int64_t>(nnz, 1) * 4)) != GSI_OK) return rc;
+    GSI_CUDA(ctx, cudaMemcpyAsync(ws.k_off.p, off, (nu + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    GSI_CUDA(ctx, cudaMemcpyAsync(ws.k_items.p, items, nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (ratings) {
+        if ((rc = ws.k_rat.ensure(ctx, std::max<int64_t>(nnz, 1) * 4)) != GSI_OK) return rc;
+        GSI_CUDA(ctx, cudaMemcpyAsync(ws.k_rat.p, ratings, nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return GSI_OK;
+}
+
+extern "C" int gsi_knn_build_host(gsi_ctx* ctx, int64_t nu, const int64_t* off, const int32_t* items, const float* ratings,
+                                  int rows, int install_weights, int64_t* n_edges) {
+    if (!ctx) return gsi_fail(nullptr, GSI_ERR_INVALID, "null context");
+    if (nu < 0 || rows < 1 || !off || (nu > 0 && (!items || !ratings))) return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_knn_build_host: bad argument");
+    GSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    Workspace& ws = WS(ctx);
+    int rc, nmax = 0;
+    if ((rc = knn_upload_csr(ctx, nu, off, items, ratings, &nmax)) != GSI_OK) return rc;
+    const size_t nn = (size_t)rows * rows;
+    if ((rc = ws.k_cnt.ensure(ctx, nn * 4)) != GSI_OK) return rc;
+    if ((rc = ws.k_num.ensure(ctx, nn * 4)) != GSI_OK) return rc;
+    if ((rc = ws.k_S.ensure(ctx, nn * 4)) != GSI_OK) return rc;
+    if ((rc = ws.k_ecnt.ensure(ctx, (size_t)(rows + 1) * 8)) != GSI_OK) return rc;
+    if ((rc = ws.k_eoff.ensure(ctx, (size_t)(rows + 1) * 8)) != GSI_OK) return rc;
+    if ((rc = ws.h_small.ensure(ctx, 64)) != GSI_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    GSI_CUDA(ctx, cudaMemsetAsync(ws.k_cnt.p, 0, nn * 4, st));
+    GSI_CUDA(ctx, cudaMemsetAsync(ws.k_num.p, 0, nn * 4, st));
+    GSI_CUDA(ctx, cudaMemsetAsync(ws.k_S.p, 0, nn * 4, st));
+    GsiSpan sp(ctx, GSI_T_KNN, 4);
+    if (nu > 0 && nmax > 1)
+        knn_accumulate_kernel<<<dim3((unsigned)nu, (nmax + 127) / 128), 128, 0, st>>>(ws.k_off.as<int64_t>(), ws.k_items.as<int32_t>(), ws.k_rat.as<float>(),
+                                                                               rows, ws.k_cnt.as<int>(), ws.k_num.as<float>(), ws.k_S.as<float>());
+    knn_finalize_kernel<<<rows, 256, 0, st>>>(rows, ws.k_cnt.as<int>(), ws.k_num.as<float>(), ws.k_S.as<float>(), 0, ws.k_ecnt.as<int64_t>(),
+                                               nullptr, nullptr, nullptr, nullptr, nullptr);
+    knn_scan_kernel<<<1, 1024, 0, st>>>(rows, ws.k_ecnt.as<int64_t>(), ws.k_eoff.as<int64_t>());
+    GSI_CUDA(ctx, cudaGetLastError());
+    int64_t* h_ne = (int64_t*)(ws.h_small.as<char>() + 48);
+    GSI_CUDA(ctx, cudaMemcpyAsync(h_ne, ws.k_eoff.as<int64_t>() + rows, 8, cudaMemcpyDeviceToHost, st));
+    GSI_CUDA(ctx, cudaStreamSynchronize(st));
+    const int64_t ne = *h_ne;
+    ws.knn_edges = ne;
+    if ((rc = ws.k_ea.ensure(ctx, std::max<int64_t>(ne, 1) * 4)) != GSI_OK) return rc;
+    if ((rc = ws.k_eb.ensure(ctx, std::max<int64_t>(ne, 1) * 4)) != GSI_OK) return rc;
+    if ((rc = ws.k_ew.ensure(ctx, std::max<int64_t>(ne, 1) * 4)) != GSI_OK) return rc;
+    double* Wd = nullptr;
+    if (install_weights) {
+        drop_weights(ctx);
+        GSI_CUDA(ctx, cudaMalloc((void**)&ctx->d_w, nn * sizeof(double)));
+        ctx->own_w = true; ctx->w_rows = rows;
+        GSI_CUDA(ctx, cudaMemsetAsync(ctx->d_w, 0, nn * sizeof(double), st));
+        Wd = ctx->d_w;
+    }
+    knn_finalize_kernel<<<rows, 256, 0, st>>>(rows, ws.k_cnt.as<int>(), ws.k_num.as<float>(), ws.k_S.as<float>(), 1, ws.k_ecnt.as<int64_t>(),
+                                               ws.k_eoff.as<int64_t>(), ws.k_ea.as<int32_t>(), ws.k_eb.as<int32_t>(), ws.k_ew.as<float>(), Wd);
+    sp.end();
+    GSI_CUDA(ctx, cudaGetLastError());
+    GSI_CUDA(ctx, cudaStreamSynchronize(st));
+    if (n_edges) *n_edges = ne;
+    return GSI_OK;
+}
+
+extern "C" int gsi_knn_edges_host(gsi_ctx* ctx, int32_t* m1, int32_t* m2, float* w, int64_t cap) {
+    if (!ctx) return gsi_fail(nullptr, GSI_ERR_INVALID, "null context");
+    Workspace& ws = WS(ctx);
+    const int64_t ne = ws.knn_edges;
+    if (cap < ne) return gsi_fail(ctx, GSI_ERR_CAPACITY, "edge buffers too small: need %lld", (long long)ne);
+    if (ne == 0) return GSI_OK;
+    if (!m1 || !m2 || !w) return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_knn_edges_host: null argument");
+    GSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    GSI_CUDA(ctx, cudaMemcpyAsync(m1, ws.k_ea.p, ne * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GSI_CUDA(ctx, cudaMemcpyAsync(m2, ws.k_eb.p, ne * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GSI_CUDA(ctx, cudaMemcpyAsync(w, ws.k_ew.p, ne * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GSI_OK;
+}
+
+extern "C" int gsi_knn_corated_host(gsi_ctx* ctx, int64_t nu, const int64_t* off, const int32_t* items, int rows, uint8_t* co) {
+    if (!ctx) return gsi_fail(nullptr, GSI_ERR_INVALID, "null context");
+    if (nu < 0 || rows < 1 || !off || !co || (nu > 0 && !items)) return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_knn_corated_host: bad argument");
+    GSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    Workspace& ws = WS(ctx);
+    int rc, nmax = 0;
+    if ((rc = knn_upload_csr(ctx, nu, off, items, nullptr, &nmax)) != GSI_OK) return rc;
+    const size_t nn = (size_t)rows * rows;
+    if ((rc = ws.k_co.ensure(ctx, nn)) != GSI_OK) return rc;
+    GSI_CUDA(ctx, cudaMemsetAsync(ws.k_co.p, 0, nn, ctx->stream));
+    GsiSpan sp(ctx, GSI_T_KNN, 1);
+    if (nu > 0 && nmax > 1)
+        knn_corated_kernel<<<dim3((unsigned)nu, (nmax + 127) / 128), 128, 0, ctx->stream>>>(ws.k_off.as<int64_t>(), ws.k_items.as<int32_t>(), rows,
+                                                                                         ws.k_co.as<unsigned char>());
+    sp.end();
+    GSI_CUDA(ctx, cudaGetLastError());
+    GSI_CUDA(ctx, cudaMemcpyAsync(co, ws.k_co.p, nn, cudaMemcpyDeviceToHost, ctx->stream));
+    GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GSI_OK;
+}
+
+extern "C" int gsi_knn3_host(gsi_ctx* ctx, int64_t nu, const int64_t* off, const int32_t* items, const float* ratings,
+                             float* movie_err_sum, int32_t* movie_cnt, uint8_t* has_edge) {
+    if (!ctx) return gsi_fail(nullptr, GSI_ERR_INVALID, "null context");
+    if (!ctx->d_w) return gsi_fail(ctx, GSI_ERR_STATE, "gsi_knn3: no weight table set");
+    if (nu < 0 || !off || !movie_err_sum || !movie_cnt || !has_edge || (nu > 0 && (!items || !ratings)))
+        return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_knn3_host: bad argument");
+    GSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    Workspace& ws = WS(ctx);
+    const int rows = ctx->w_rows;
+    int rc, nmax = 0;
+    if ((rc = knn_upload_csr(ctx, nu, off, items, ratings, &nmax)) != GSI_OK) return rc;
+    if ((rc = ws.k_err.ensure(ctx, (size_t)rows * 4)) != GSI_OK) return rc;
+    if ((rc = ws.k_mcnt.ensure(ctx, (size_t)rows * 4)) != GSI_OK) return rc;
+    if ((rc = ws.k_has.ensure(ctx, (size_t)rows)) != GSI_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    GSI_CUDA(ctx, cudaMemsetAsync(ws.k_err.p, 0, (size_t)rows * 4, st));
+    GSI_CUDA(ctx, cudaMemsetAsync(ws.k_mcnt.p, 0, (size_t)rows * 4, st));
+    GSI_CUDA(ctx, cudaMemsetAsync(ws.k_has.p, 0, (size_t)rows, st));
+    GsiSpan sp(ctx, GSI_T_KNN, 2);
+    if (nu > 0 && nmax > 0)
+        knn3_kernel<<<dim3((unsigned)nu, (nmax + 127) / 128), 128, 0, st>>>(ws.k_off.as<int64_t>(), ws.k_items.as<int32_t>(), ws.k_rat.as<float>(),
+                                                                     ctx->d_w, rows, ws.k_err.as<float>(), ws.k_mcnt.as<int>());
+    knn3_vertices_kernel<<<rows, 256, 0, st>>>(ctx->d_w, rows, ws.k_has.as<unsigned char>());
+    sp.end();
+    GSI_CUDA(ctx, cudaGetLastError());
+    GSI_CUDA(ctx, cudaMemcpyAsync(movie_err_sum, ws.k_err.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, st));
+    GSI_CUDA(ctx, cudaMemcpyAsync(movie_cnt, ws.k_mcnt.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, st));
+    GSI_CUDA(ctx, cudaMemcpyAsync(has_edge, ws.k_has.p, (size_t)rows, cudaMemcpyDeviceToHost, st));
+    GSI_CUDA(ctx, cudaStreamSynchronize(st));
     return GSI_OK;
 }
 

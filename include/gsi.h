@@ -118,6 +118,72 @@ typedef int (*gsi_record_sink)(void* opaque, const gsi_record_chunk* chunk);
 int gsi_precompute_stream(gsi_ctx* ctx, int64_t n_users, const int64_t* offsets,
                           const int32_t* items, gsi_record_sink sink, void* opaque);
 
+/* ---- predict  (replaces neigh_program::gather/apply, local_calc_precomp.cpp:200-380: for every
+ *      (movie m, test user u) pair select the known rows K = rated(u) n out-neighbours(m), cut the
+ *      spectrum at the per-movie sig_min, drop empty columns, solve the band-limited least squares
+ *      problem and return the clamped squared error) ------------------------------------------- *
+ *
+ * The users' records are given in the layout gsi_precompute_* produces (what load_precomputed_data
+ * :406-482 parses from out_eigen_).  The item graph is not passed separately: edge m -> j exists iff
+ * (float)weights(m, j) > 0.1 (graph_loader :122-136), and the dense table set with
+ * gsi_set_weights_* holds exactly the out_fin_ lines the reference builds its graph from.
+ *
+ *   w_lim[offsets[u] + i]    cutoff for the pair (u, movie i).  The reference reads
+ *                            sigs_min[movie_ind] from a vector that is never cleared between
+ *                            records (bug B1, :414,437,440,271); the host decides whether to pass
+ *                            that or the record's own sig_min.
+ *   ratings[offsets[u] + i]  the user's own rating of movie i (out_test_rat_, float -> double
+ *                            :138-160); it is both the ground truth of pair (u, i) and a known
+ *                            rating for the user's other pairs.
+ *   pair_mask                optional [nnz] bytes; 0 skips the pair (--pct sampling is per movie,
+ *                            :221).  NULL = every pair.
+ * Outputs, all [nnz], aligned with items: err (float, (real - clamp(pred,1,5))^2 :322-327,357),
+ * kk (#K :359), pred (unclamped), status (GSI_PRED_*), cols (columns used).
+ * Ill-posed pairs (kk < cols, or a non-positive Cholesky pivot; the reference inverts the singular
+ * Gram blindly, B3) get pred = mean of the known ratings; kk == 0 gives NaN as in the reference.
+ */
+enum { GSI_PRED_OK = 0, GSI_PRED_EMPTY = 1, GSI_PRED_UNDERDETERMINED = 2, GSI_PRED_SINGULAR = 3, GSI_PRED_SKIPPED = 4 };
+
+int gsi_predict_host(gsi_ctx* ctx, int64_t n_users, const int64_t* offsets, const int32_t* items,
+                     const double* w_lim, const double* ratings, const int32_t* k,
+                     const int64_t* lam_off, const int64_t* vec_off, const double* lam,
+                     int64_t lam_len, const double* vec, int64_t vec_len, const uint8_t* pair_mask,
+                     float* err, int32_t* kk, double* pred, int32_t* status, int32_t* cols);
+
+/* Same with every array already on the device (records straight from gsi_precompute_device;
+ * h_offsets and h_k are host copies the planner needs).  pair_mask is a host array or NULL. */
+int gsi_predict_device(gsi_ctx* ctx, int64_t n_users, const int64_t* h_offsets, const int32_t* h_k,
+                       const int64_t* d_offsets, const int32_t* d_items, const double* d_w_lim,
+                       const double* d_ratings, const int32_t* d_k, const int64_t* d_lam_off,
+                       const int64_t* d_vec_off, const double* d_lam, const double* d_vec,
+                       const uint8_t* pair_mask, float* d_err, int32_t* d_kk, double* d_pred,
+                       int32_t* d_status, int32_t* d_cols, int64_t* n_pairs_done);
+
+/* ---- knn chain  (replaces the GraphLab vertex programs of knn.cpp:160-298, the edge transform
+ *      weights_calc knn2.cpp:127-146 and knn_program / error_vertex_data knn3.cpp:185-256) ------ *
+ *
+ * Ratings are CSR by user (ids ascending, unique), `rows` = max movie id + 1.
+ */
+
+/* knn2: cosine weight of every directed item pair over its common TRAIN raters (float
+ * accumulators, > 5 common raters, knn2.cpp:127-146) -> the out_fin_ edge list (w > 0.01,
+ * :155-163), kept on the device in ascending (m1, m2) order.  With install_weights != 0 the dense
+ * table of the context is (re)built from those edges exactly as precompute_local would read them
+ * back from the out_fin_ text (weights rounded to 6 significant digits). */
+int gsi_knn_build_host(gsi_ctx* ctx, int64_t n_users, const int64_t* offsets, const int32_t* items,
+                       const float* ratings, int rows, int install_weights, int64_t* n_edges);
+/* Copies the edge list of the last gsi_knn_build_host to the host (cap >= n_edges). */
+int gsi_knn_edges_host(gsi_ctx* ctx, int32_t* m1, int32_t* m2, float* w, int64_t cap);
+/* knn step 1, out_edg_*: co[a * rows + b] = 1 iff some user (train OR validate role,
+ * knn.cpp:218-227) rated both a and b, a != b. */
+int gsi_knn_corated_host(gsi_ctx* ctx, int64_t n_users, const int64_t* offsets, const int32_t* items,
+                         int rows, uint8_t* co);
+/* knn3 over the context's weight table and the validate users' ratings: per movie the float sum of
+ * (r - round(pred))^2 and the number of test ratings (knn3.cpp:234-256), plus has_edge[m] = movie
+ * m is an endpoint of a kept edge ((float)w > 0.1) -- together they give num_vertices (:263). */
+int gsi_knn3_host(gsi_ctx* ctx, int64_t n_users, const int64_t* offsets, const int32_t* items,
+                  const float* ratings, float* movie_err_sum, int32_t* movie_cnt, uint8_t* has_edge);
+
 /* ---- measurement helpers ------------------------------------------------------------------- */
 
 /* Accumulated device time (ms, CUDA events on the context's stream) per kernel class since the
