@@ -101,7 +101,7 @@ def test_ml100k_precompute_then_predict_vs_oracle(ctx):
     fed the GPU's own records.  Also exercises the global-scratch path (k > 128)."""
     from collaborative_filtering_b200 import datasets as D
     r = D.make_ratings("ml-100k")
-    w = D.make_weights(r.n_items, density=0.35)
+    w = D.make_weights(r.n_items, density=0.9)
     deg = r.degrees()
     order = np.argsort(deg)
     pick = np.sort(np.concatenate([order[:6], order[len(order) // 2: len(order) // 2 + 6], order[-3:]]))
