@@ -1,0 +1,88 @@
+// Shared body of precompute_local / precompute_local_threads: same cwd-relative inputs and the same
+// out_eigen_ record layout as the reference (precompute_local.cpp:84-282,
+// precompute_local_threads.cpp:215-317); the per-user math is one gsi_precompute_stream() call.
+#pragma once
+#include <atomic>
+#include <thread>
+
+#include "host_io.hpp"
+
+namespace gsihost {
+
+struct EigenSink {
+    const Csr* csr; FILE* out; int n_threads; size_t done = 0;
+};
+
+// one out_eigen_ record (precompute_local.cpp:265-278): every token followed by a space
+inline void format_record(const Csr& csr, const gsi_record_chunk* ch, int64_t j, std::string& s) {
+    const int64_t u = ch->user_index[j];
+    const int n = ch->n[j], k = ch->k[j];
+    char buf[64];
+    int len = snprintf(buf, sizeof buf, "%u %d %d ", csr.users[u], n, k);
+    s.append(buf, len);
+    const double* sig = ch->sig_min + csr.offsets[u];
+    for (int i = 0; i < n; ++i) {
+        len = snprintf(buf, sizeof buf, "%d %g ", csr.items[csr.offsets[u] + i], sig[i]);
+        s.append(buf, len);
+    }
+    s.push_back('\n');
+    const double* lam = ch->lam + ch->lam_off[j];
+    for (int i = 0; i < k; ++i) append_g(s, lam[i]);
+    s.push_back('\n');
+    const double* vec = ch->vec + ch->vec_off[j];
+    for (int64_t t = 0; t < (int64_t)n * k; ++t) append_g(s, vec[t]);
+    s.push_back('\n');
+}
+
+// the analogue of save_output() (precompute_local_threads.cpp:89-98): records are appended as the
+// chunks complete; formatting is spread over n_threads host threads, file order = processing order
+inline int eigen_sink(void* opaque, const gsi_record_chunk* ch) {
+    EigenSink* S = (EigenSink*)opaque;
+    const int64_t nr = ch->n_records;
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(S->n_threads, nr));
+    std::vector<std::string> parts(nt);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; ++t)
+        pool.emplace_back([&, t]() {
+            const int64_t b = nr * t / nt, e = nr * (t + 1) / nt;
+            for (int64_t j = b; j < e; ++j) format_record(*S->csr, ch, j, parts[t]);
+        });
+    for (auto& th : pool) th.join();
+    for (auto& p : parts)
+        if (!p.empty() && fwrite(p.data(), 1, p.size(), S->out) != p.size()) return 1;
+    S->done += (size_t)nr;
+    printf("%g%%\n", 100.0 * (double)S->done / (double)(S->csr->users.size()));
+    return 0;
+}
+
+inline int precompute_main(int n_threads) {
+    const std::string path = "movielens/", suffix = ".validate";
+    std::vector<Triple> rows;
+    for (const std::string& f : list_files(path, [&](const std::string& n) { return ends_with(n, suffix); })) {
+        printf("Reading file: %s\n", f.c_str());
+        read_triples(f, rows);
+    }
+    Csr csr = build_csr(rows, /*map_user=*/true);        // users[INT_MAX - user][movie] = rating  :107-108
+    std::vector<double> table;
+    int wrows = 1;
+    load_weights_table(table, wrows);
+    FILE* out = fopen("out_eigen_", "w");               // truncate :150-151
+    if (!out) { perror("out_eigen_"); return 1; }
+    printf("Number of movies: %d\n", wrows - 1);
+    printf("Number of users: %zu\n", csr.users.size());
+    if (csr.users.empty()) { fclose(out); return 0; }
+    gsi_ctx* ctx = nullptr;
+    const char* dev = getenv("GSI_DEVICE");
+    if (gsi_create(&ctx, dev ? atoi(dev) : 0, nullptr) != GSI_OK) { fclose(out); return fail(nullptr, "gsi_create"); }
+    int rc = gsi_set_weights_host(ctx, table.data(), wrows);
+    std::vector<double>().swap(table);
+    if (rc != GSI_OK) { fclose(out); return fail(ctx, "gsi_set_weights_host"); }
+    EigenSink sink{&csr, out, n_threads};
+    rc = gsi_precompute_stream(ctx, (int64_t)csr.users.size(), csr.offsets.data(), csr.items.data(), eigen_sink, &sink);
+    fclose(out);
+    if (rc != GSI_OK) return fail(ctx, "gsi_precompute_stream");
+    gsi_destroy(ctx);
+    return 0;
+}
+
+}  // namespace gsihost
