@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -38,8 +39,9 @@ static cudaEvent_t take_event(gsi_ctx* ctx) {
 }
 GsiSpan::GsiSpan(gsi_ctx* c, int cls_, int64_t n_launches, int64_t n_timed) : ctx(c), cls(cls_), launches(n_launches) {
     ctx->t_launch[cls] += n_launches;
-    if (ctx->timing) {
-        ctx->t_samples[cls] += (n_timed < 0 ? n_launches : n_timed);
+    const int64_t timed = n_timed < 0 ? n_launches : n_timed;
+    if (ctx->timing && timed > 0) {
+        ctx->t_samples[cls] += timed;
         a = take_event(ctx); b = take_event(ctx); cudaEventRecord(a, ctx->stream);
     }
 }
@@ -136,6 +138,9 @@ extern "C" int gsi_create(gsi_ctx** out, int device, void* stream) {
     GSI_CUDA(ctx, set_smem_attr<3>());
     GSI_CUDA(ctx, set_smem_attr<4>());
     GSI_CUDA(ctx, set_smem_attr<5>());
+    const char* bm = getenv("GSI_BJ_M");
+    ctx->bj_m = (bm && atoi(bm) == 32) ? 32 : 64;
+    GSI_CUDA(ctx, cudaFuncSetAttribute(bj_inner_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 65 * 8));
     *out = ctx;
     return GSI_OK;
 }
@@ -242,7 +247,7 @@ struct Chunk { bool large; int begin, end; };   // [begin, end) into the sorted 
 
 static inline int64_t pad_slots(int n) { return (int64_t)n * std::max(n, 2); }
 static inline int ld_of(int n) { return (n + 7) & ~7; }
-static inline int nb_of(int n) { int nb = (n + GSI_BJ_B - 1) / GSI_BJ_B; return nb + (nb & 1); }
+static inline int nb_of(int n, int B) { int nb = (n + B - 1) / B; return nb + (nb & 1); }
 
 static int plan(gsi_ctx* ctx, int64_t nu, const int64_t* off, std::vector<Job>& small, std::vector<Job>& large,
                 std::vector<Chunk>& chunks) {
@@ -261,13 +266,14 @@ static int plan(gsi_ctx* ctx, int64_t nu, const int64_t* off, std::vector<Job>& 
     int b = 0;
     while (b < (int)large.size()) {
         const int nmax = large[b].n;
-        const int nb = nb_of(nmax), ncols = nb * GSI_BJ_B;
+        const int B = ctx->bj_m / 2, MM = ctx->bj_m * ctx->bj_m;
+        const int nb = nb_of(nmax, B), ncols = nb * B;
         int64_t used = 0;
         int e = b;
         while (e < (int)large.size() && e - b < 60000) {
             const int n = large[e].n;
             if (e > b && (double)n < 0.7 * nmax) break;
-            const int64_t need = (int64_t)ld_of(n) * ncols + pad_slots(n) + (int64_t)(nb / 2) * 1024 * (1 + (ld_of(nmax) + GSI_BJ_ROWS - 1) / GSI_BJ_ROWS);
+            const int64_t need = (int64_t)ld_of(n) * ncols + pad_slots(n) + (int64_t)(nb / 2) * MM * (1 + (ld_of(nmax) + GSI_BJ_ROWS - 1) / GSI_BJ_ROWS);
             if (e > b && used + need > budget) break;
             used += need; ++e;
         }
@@ -403,7 +409,8 @@ static int run_small_chunk(gsi_ctx* ctx, const Job* jobs, int nj, const int32_t*
 static int run_large_chunk(gsi_ctx* ctx, const Job* jobs, int nj, const int32_t* d_items, const RunOut& out) {
     Workspace& ws = WS(ctx);
     const int nmax = jobs[0].n;                    // sorted descending
-    const int nb = nb_of(nmax), ncols = nb * GSI_BJ_B, half = nb / 2;
+    const int M = ctx->bj_m, B = M / 2, MM = M * M;
+    const int nb = nb_of(nmax, B), ncols = nb * B, half = nb / 2;
     const int splits = (ld_of(nmax) + GSI_BJ_ROWS - 1) / GSI_BJ_ROWS;
     std::vector<int64_t> item_off(nj), vec_off(nj), lam_off(nj), user(nj), g_off(nj), row_off(nj);
     std::vector<int32_t> n(nj), ld(nj);
@@ -427,8 +434,8 @@ static int run_large_chunk(gsi_ctx* ctx, const Job* jobs, int nj, const int32_t*
     if ((rc = ws.rows.ensure(ctx, rtot * 16)) != GSI_OK) return rc;
     if ((rc = ws.cols.ensure(ctx, (size_t)nj * ncols * 16)) != GSI_OK) return rc;
     if ((rc = ws.perm.ensure(ctx, (size_t)nj * ncols * 4)) != GSI_OK) return rc;
-    if ((rc = ws.hpart.ensure(ctx, (size_t)nj * half * splits * 1024 * 8)) != GSI_OK) return rc;
-    if ((rc = ws.q.ensure(ctx, (size_t)nj * half * 1024 * 8)) != GSI_OK) return rc;
+    if ((rc = ws.hpart.ensure(ctx, (size_t)nj * half * splits * MM * 8)) != GSI_OK) return rc;
+    if ((rc = ws.q.ensure(ctx, (size_t)nj * half * MM * 8)) != GSI_OK) return rc;
     if ((rc = ws.h_small.ensure(ctx, 64)) != GSI_OK) return rc;
     char* base;
     if ((rc = upload_meta(ctx, mb, &base)) != GSI_OK) return rc;
@@ -458,28 +465,22 @@ static int run_large_chunk(gsi_ctx* ctx, const Job* jobs, int nj, const int32_t*
         sp.end();
     }
     int32_t* h_rem = ws.h_small.as<int32_t>();
+    const size_t inner_smem = (size_t)2 * M * (M + 1) * sizeof(double);
+    auto launch_round = [&](int r, bool sample) {
+        const dim3 g3(half, splits, nj), g1(half, 1, nj);
+        GsiSpan a(ctx, GSI_T_BJ_GRAM, 1, sample ? 1 : 0);
+        if (M == 64) bj_gram_kernel<64><<<g3, 128, 0, st>>>(C, r); else bj_gram_kernel<32><<<g3, 128, 0, st>>>(C, r);
+        a.end();
+        GsiSpan b(ctx, GSI_T_BJ_INNER, 1, sample ? 1 : 0);
+        if (M == 64) bj_inner_kernel<64><<<g1, 512, inner_smem, st>>>(C, r); else bj_inner_kernel<32><<<g1, 256, inner_smem, st>>>(C, r);
+        b.end();
+        GsiSpan c(ctx, GSI_T_BJ_UPDATE, 1, sample ? 1 : 0);
+        if (M == 64) bj_update_kernel<64><<<g3, 128, 0, st>>>(C, r); else bj_update_kernel<32><<<g3, 128, 0, st>>>(C, r);
+        c.end();
+    };
     for (int sweep = 0; sweep < GSI_MAX_SWEEPS; ++sweep) {
-        for (int r = 0; r < nb - 1; ++r) {
-            const bool sample = ctx->timing && (r % 8 == 0);
-            if (sample) {
-                GsiSpan a(ctx, GSI_T_BJ_GRAM, 0, 1);
-                bj_gram_kernel<<<dim3(half, splits, nj), 128, 0, st>>>(C, r);
-                a.end();
-                GsiSpan b(ctx, GSI_T_BJ_INNER, 0, 1);
-                bj_inner_kernel<<<dim3(half, 1, nj), 256, 0, st>>>(C, r);
-                b.end();
-                GsiSpan c(ctx, GSI_T_BJ_UPDATE, 0, 1);
-                bj_update_kernel<<<dim3(half, splits, nj), 128, 0, st>>>(C, r);
-                c.end();
-            } else {
-                bj_gram_kernel<<<dim3(half, splits, nj), 128, 0, st>>>(C, r);
-                bj_inner_kernel<<<dim3(half, 1, nj), 256, 0, st>>>(C, r);
-                bj_update_kernel<<<dim3(half, splits, nj), 128, 0, st>>>(C, r);
-            }
-            gsi_count_launch(ctx, GSI_T_BJ_GRAM, 1);
-            gsi_count_launch(ctx, GSI_T_BJ_INNER, 1);
-            gsi_count_launch(ctx, GSI_T_BJ_UPDATE, 1);
-        }
+        // diagonal round first (within-block pairs), then the nb-1 circle rounds (cross pairs)
+        for (int r = -1; r < nb - 1; ++r) launch_round(r, ctx->timing && ((r + 1) % 8 == 0));
         GSI_CUDA(ctx, cudaMemsetAsync(C.remaining, 0, 4, st));
         bj_check_kernel<<<(nj + 255) / 256, 256, 0, st>>>(C);
         GSI_CUDA(ctx, cudaGetLastError());

@@ -20,9 +20,7 @@
 #define GSI_S_MAX_EPT 5
 #define GSI_S_MAX_N (32 * GSI_S_MAX_EPT)
 
-// block Jacobi (large path): column blocks of GSI_BJ_B, panels of 2*GSI_BJ_B = 32 columns
-#define GSI_BJ_B 16
-#define GSI_BJ_M 32
+// block Jacobi (large path): panels of M columns = two blocks of M/2; M is 64 (default) or 32
 #define GSI_BJ_ROWS 512  // rows of a panel handled by one CTA of the Gram / update kernels
 
 struct gsi_ctx {
@@ -32,6 +30,7 @@ struct gsi_ctx {
     std::string err;
     int sm_count = 148;
     int64_t ws_limit = (int64_t)8 << 30;
+    int bj_m = 64;
     // weights
     double* d_w = nullptr;
     int w_rows = 0;

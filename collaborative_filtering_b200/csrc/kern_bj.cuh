@@ -2,10 +2,10 @@
 //
 //   lap_* kernels      gather W -> degree -> normalised Laplacian -> sig_min -> sym(lower)+I
 //                      (precompute_local.cpp:185-249), column-major G[i + j*ld]
-//   bj_* kernels       one-sided BLOCK Jacobi on G: column blocks of 16; each round pairs the
+//   bj_* kernels       one-sided BLOCK Jacobi on G: column blocks of B = M/2; each round pairs the
 //                      blocks with the circle ordering and every pair (I,J) does
-//                          H = P^T P            P = [G_I G_J]   (n x 32)     bj_gram   (DMMA)
-//                          Q = one cyclic sweep of two-sided Jacobi on H      bj_inner
+//                          H = P^T P            P = [G_I G_J]   (n x M)      bj_gram   (DMMA)
+//                          Q = one sweep of two-sided Jacobi rotations on H   bj_inner
 //                          P <- P Q                                           bj_update (DMMA)
 //                      FP64 tensor-core mma.sync m8n8k4 carries both GEMM-shaped steps.
 //   fin_* kernels      column norms -> eigenvalues, ascending rank, cutoff (:252-261), emit
@@ -19,7 +19,7 @@
 struct LChunk {
     int nu;        // users in the chunk
     int nb;        // column blocks per user (even), uniform over the chunk
-    int ncols;     // nb * 16
+    int ncols;     // nb * B
     int splits;    // row splits of a panel (uniform upper bound)
     const int32_t* n;          // [nu]
     const int32_t* ld;         // [nu] leading dimension, multiple of 8, rows >= n are zero
@@ -40,8 +40,8 @@ struct LChunk {
     int32_t* sweeps;           // [nu]
     int32_t* k;                // [nu]
     int32_t* remaining;        // [1]
-    double* Hpart;             // [nu][nb/2][splits][1024]
-    double* Q;                 // [nu][nb/2][1024]
+    double* Hpart;             // [nu][nb/2][splits][M*M]
+    double* Q;                 // [nu][nb/2][M*M]
 };
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
@@ -175,21 +175,36 @@ __global__ void lap_symmetrize_kernel(LChunk C, int tiles_per_dim) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Block Jacobi
+// Block Jacobi.  Templated on the panel width M (two column blocks of B = M/2).
+//   round >= 0 : circle ordering over the nb blocks, inner sweep over the B*B CROSS pairs only
+//   round <  0 : "diagonal" round, pairs (2s, 2s+1), full cyclic sweep over all M(M-1)/2 pairs --
+//                once per sweep, so that every column pair of the matrix is rotated once per sweep
 // ------------------------------------------------------------------------------------------
 
+template <int M>
 __device__ __forceinline__ bool bj_task(const LChunk& C, int u, int round, int slot, int& I, int& J) {
     if (C.done[u]) return false;
-    circle_pair(C.nb, round, slot, I, J);
-    const int n = C.n[u];
-    return J * GSI_BJ_B < n;     // I < J; a block that starts beyond n is phantom
+    if (round < 0) { I = 2 * slot; J = 2 * slot + 1; }
+    else circle_pair(C.nb, round, slot, I, J);
+    // I < J.  Circle rounds: nothing to do when block J is phantom (all-zero columns).  Diagonal
+    // round: block I still has to be orthogonalised within itself.
+    return (round < 0 ? I : J) * (M / 2) < C.n[u];
 }
 
-// grid (nb/2, splits, nu), block 128.  Partial Gram of the 32-column panel over this CTA's rows.
+template <int M>
+__device__ __forceinline__ int panel_col(int cc, int I, int J) {
+    return (cc < M / 2) ? I * (M / 2) + cc : J * (M / 2) + (cc - M / 2);
+}
+
+// grid (nb/2, splits, nu), block 128.  Partial Gram H = P^T P of the M-column panel over this
+// CTA's rows; DMMA fragments come straight from global/L2 (each element is loaded exactly once per
+// warp), next k-step prefetched while the current one is multiplied.
+template <int M>
 __global__ void __launch_bounds__(128) bj_gram_kernel(LChunk C, int round) {
+    constexpr int T = M / 8, NT = T * (T + 1) / 2;
     const int u = blockIdx.z, slot = blockIdx.x, split = blockIdx.y;
     int I, J;
-    if (!bj_task(C, u, round, slot, I, J)) return;
+    if (!bj_task<M>(C, u, round, slot, I, J)) return;
     const int ld = C.ld[u];
     const int r_begin = split * GSI_BJ_ROWS;
     if (r_begin >= ld) return;
@@ -197,169 +212,177 @@ __global__ void __launch_bounds__(128) bj_gram_kernel(LChunk C, int round) {
     const double* G = C.G + C.g_off[u];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lr = lane & 3, lc = lane >> 2;
-    // column pointers of the 4 fragments this lane loads: panel column 8t + lc
-    const double* colp[4];
+    const double* colp[T];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const int cc = 8 * t + lc;
-        const int gc = (cc < GSI_BJ_B) ? I * GSI_BJ_B + cc : J * GSI_BJ_B + (cc - GSI_BJ_B);
-        colp[t] = G + (size_t)gc * ld + lr;
+    for (int t = 0; t < T; ++t) colp[t] = G + (size_t)panel_col<M>(8 * t + lc, I, J) * ld + lr;
+    double acc[NT][2];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    int r = r_begin + 4 * warp;
+    double f[T], g[T];
+    if (r < r_end) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) f[t] = colp[t][r];
     }
-    double acc[10][2];
+    for (; r < r_end; r += 16) {
+        const int rn = r + 16;
+        if (rn < r_end) {
 #pragma unroll
-    for (int t = 0; t < 10; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
-    for (int r = r_begin + 4 * warp; r < r_end; r += 16) {
-        double f[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) f[t] = colp[t][r];
+            for (int t = 0; t < T; ++t) g[t] = colp[t][rn];
+        }
         int idx = 0;
 #pragma unroll
-        for (int ti = 0; ti < 4; ++ti)
+        for (int ti = 0; ti < T; ++ti)
 #pragma unroll
-            for (int tj = ti; tj < 4; ++tj) { dmma884(acc[idx][0], acc[idx][1], f[ti], f[tj]); ++idx; }
+            for (int tj = ti; tj < T; ++tj) { dmma884(acc[idx][0], acc[idx][1], f[ti], f[tj]); ++idx; }
+#pragma unroll
+        for (int t = 0; t < T; ++t) f[t] = g[t];
     }
-    __shared__ double red[4][10][64];
+    // deterministic reduction over the 4 warps: warp w adds its tiles in turn
+    __shared__ double Hs[M * M];
+    for (int w = 0; w < 4; ++w) {
+        if (warp == w) {
+            int idx = 0;
 #pragma unroll
-    for (int t = 0; t < 10; ++t) { red[warp][t][lane * 2] = acc[t][0]; red[warp][t][lane * 2 + 1] = acc[t][1]; }
-    __syncthreads();
-    double* H = C.Hpart + (((size_t)u * (C.nb >> 1) + slot) * C.splits + split) * 1024;
-    for (int e = threadIdx.x; e < 640; e += 128) {
-        const int t = e >> 6, w = e & 63;
-        const double v = red[0][t][w] + red[1][t][w] + red[2][t][w] + red[3][t][w];
-        // tile t -> (ti, tj): order (0,0)(0,1)(0,2)(0,3)(1,1)(1,2)(1,3)(2,2)(2,3)(3,3)
-        int ti, tj;
-        if (t < 4) { ti = 0; tj = t; } else if (t < 7) { ti = 1; tj = t - 3; } else if (t < 9) { ti = 2; tj = t - 5; } else { ti = 3; tj = 3; }
-        const int l = w >> 1, el = w & 1;
-        const int a = 8 * ti + (l >> 2), b = 8 * tj + 2 * (l & 3) + el;
-        H[a * 32 + b] = v;
+            for (int ti = 0; ti < T; ++ti)
+#pragma unroll
+                for (int tj = ti; tj < T; ++tj) {
+                    const int a = 8 * ti + lc, b = 8 * tj + 2 * lr;
+                    if (w == 0) { Hs[a * M + b] = acc[idx][0]; Hs[a * M + b + 1] = acc[idx][1]; }
+                    else { Hs[a * M + b] += acc[idx][0]; Hs[a * M + b + 1] += acc[idx][1]; }
+                    ++idx;
+                }
+        }
+        __syncthreads();
+    }
+    double* H = C.Hpart + (((size_t)u * (C.nb >> 1) + slot) * C.splits + split) * (M * M);
+    for (int e = threadIdx.x; e < M * M; e += 128) {
+        const int a = e / M, b = e % M;
+        if ((a >> 3) <= (b >> 3)) H[e] = Hs[e];
     }
 }
 
-// grid (nb/2, 1, nu), block 256.  H = sum of partials (upper tiles mirrored); one cyclic sweep of
-// two-sided Jacobi over the 32x32 panel Gram, rotations accumulated into Q.
-__global__ void __launch_bounds__(256) bj_inner_kernel(LChunk C, int round) {
+// grid (nb/2, 1, nu), block 8*M.  H = sum of partials (upper tiles mirrored); one sweep of
+// two-sided Jacobi on the M x M panel Gram, rotations accumulated into Q.
+template <int M>
+__global__ void __launch_bounds__(8 * M) bj_inner_kernel(LChunk C, int round) {
+    constexpr int B = M / 2, LDH = M + 1, NTHR = 8 * M;
     const int u = blockIdx.z, slot = blockIdx.x;
     int I, J;
-    if (!bj_task(C, u, round, slot, I, J)) return;
-    __shared__ double H[32][33];
-    __shared__ double Q[32][33];
-    __shared__ double cs[16][2];
-    __shared__ int pq[16][2];
+    if (!bj_task<M>(C, u, round, slot, I, J)) return;
+    extern __shared__ double sm_inner[];
+    double* H = sm_inner;                 // [M][LDH]
+    double* Q = H + M * LDH;              // [M][LDH]
+    __shared__ double cs[B][2];
+    __shared__ int pq[B][2];
     __shared__ unsigned long long sh_max;
     const int tid = threadIdx.x;
     const int ld = C.ld[u];
     const int nsplit = (ld + GSI_BJ_ROWS - 1) / GSI_BJ_ROWS;
-    const double* Hp = C.Hpart + ((size_t)u * (C.nb >> 1) + slot) * C.splits * 1024;
-    for (int e = tid; e < 1024; e += 256) {
-        const int a = e >> 5, b = e & 31;
+    const double* Hp = C.Hpart + ((size_t)u * (C.nb >> 1) + slot) * C.splits * (M * M);
+    for (int e = tid; e < M * M; e += NTHR) {
+        const int a = e / M, b = e % M;
         if ((a >> 3) <= (b >> 3)) {
             double v = 0.0;
-            for (int s = 0; s < nsplit; ++s) v += Hp[(size_t)s * 1024 + e];
-            H[a][b] = v;
-            if ((a >> 3) < (b >> 3)) H[b][a] = v;
+            for (int s = 0; s < nsplit; ++s) v += Hp[(size_t)s * (M * M) + e];
+            H[a * LDH + b] = v;
+            if ((a >> 3) < (b >> 3)) H[b * LDH + a] = v;
         }
-        Q[a][b] = (a == b) ? 1.0 : 0.0;
+        Q[a * LDH + b] = (a == b) ? 1.0 : 0.0;
     }
     if (tid == 0) sh_max = 0ull;
     __syncthreads();
-    for (int r = 0; r < 31; ++r) {
-        if (tid < 16) {
+    const bool full = round < 0;
+    const int nrounds = full ? M - 1 : B;
+    for (int r = 0; r < nrounds; ++r) {
+        if (tid < B) {
             int p, q;
-            circle_pair(32, r, tid, p, q);
-            const double a = H[p][p], b = H[q][q], g = H[p][q];
+            if (full) circle_pair(M, r, tid, p, q);
+            else { p = tid; q = B + ((tid + r) & (B - 1)); }
+            const double a = H[p * LDH + p], b = H[q * LDH + q], g = H[p * LDH + q];
             double c = 1.0, s = 0.0, t;
             const double ab = a * b, g2 = g * g;
             if (ab > 0.0) {
-                atomicMax(&sh_max, dbits(g2 / ab));
+                if (g2 > GSI_STOP2 * ab) atomicMax(&sh_max, dbits(g2 / ab));
                 if (g2 > GSI_ROT2 * ab) jacobi_cs(a, b, g, c, s, t);
             }
             cs[tid][0] = c; cs[tid][1] = s; pq[tid][0] = p; pq[tid][1] = q;
         }
         __syncthreads();
-        // column rotations of H and Q: 16 pairs x 32 rows x 2 matrices
-        for (int e = tid; e < 1024; e += 256) {
-            const int t = (e >> 5) & 15, i = e & 31, which = e >> 9;
+        // column rotations of H and Q: B pairs x M rows x 2 matrices
+        for (int e = tid; e < 2 * B * M; e += NTHR) {
+            const int i = e % M, t = (e / M) % B, which = e / (M * B);
             const double c = cs[t][0], s = cs[t][1];
             if (s != 0.0) {
                 const int p = pq[t][0], q = pq[t][1];
-                double (*M)[33] = which ? Q : H;
-                const double x = M[i][p], y = M[i][q];
-                M[i][p] = c * x - s * y;
-                M[i][q] = s * x + c * y;
+                double* Mx = which ? Q : H;
+                const double x = Mx[i * LDH + p], y = Mx[i * LDH + q];
+                Mx[i * LDH + p] = c * x - s * y;
+                Mx[i * LDH + q] = s * x + c * y;
             }
         }
         __syncthreads();
         // row rotations of H
-        for (int e = tid; e < 512; e += 256) {
-            const int t = e >> 5, j = e & 31;
+        for (int e = tid; e < B * M; e += NTHR) {
+            const int j = e % M, t = e / M;
             const double c = cs[t][0], s = cs[t][1];
             if (s != 0.0) {
                 const int p = pq[t][0], q = pq[t][1];
-                const double x = H[p][j], y = H[q][j];
-                H[p][j] = c * x - s * y;
-                H[q][j] = s * x + c * y;
+                const double x = H[p * LDH + j], y = H[q * LDH + j];
+                H[p * LDH + j] = c * x - s * y;
+                H[q * LDH + j] = s * x + c * y;
             }
         }
         __syncthreads();
     }
-    double* Qg = C.Q + ((size_t)u * (C.nb >> 1) + slot) * 1024;
-    for (int e = tid; e < 1024; e += 256) Qg[e] = Q[e >> 5][e & 31];
-    if (tid == 0) atomicMax(&C.smax[u], sh_max);
+    double* Qg = C.Q + ((size_t)u * (C.nb >> 1) + slot) * (M * M);
+    for (int e = tid; e < M * M; e += NTHR) Qg[e] = Q[(e / M) * LDH + (e % M)];
+    if (tid == 0 && sh_max) atomicMax(&C.smax[u], sh_max);
 }
 
-// grid (nb/2, splits, nu), block 128.  P <- P Q for this CTA's rows, in place.
+// grid (nb/2, splits, nu), block 128.  P <- P Q for this CTA's rows, in place.  Q sits in shared
+// memory with a leading dimension that makes the B-fragment loads conflict free; every warp
+// handles 8-row groups: M/4 A-fragment loads, M/8 * M/4 DMMAs, M/8 * 2 stores per lane.
+template <int M>
 __global__ void __launch_bounds__(128) bj_update_kernel(LChunk C, int round) {
+    constexpr int T = M / 8, KS = M / 4, LDQ = M + 4;
     const int u = blockIdx.z, slot = blockIdx.x, split = blockIdx.y;
     int I, J;
-    if (!bj_task(C, u, round, slot, I, J)) return;
+    if (!bj_task<M>(C, u, round, slot, I, J)) return;
     const int ld = C.ld[u];
     const int r_begin = split * GSI_BJ_ROWS;
     if (r_begin >= ld) return;
     const int r_end = min(ld, r_begin + GSI_BJ_ROWS);
     double* G = C.G + C.g_off[u];
-    const double* Qg = C.Q + ((size_t)u * (C.nb >> 1) + slot) * 1024;
+    const double* Qg = C.Q + ((size_t)u * (C.nb >> 1) + slot) * (M * M);
+    __shared__ double Qs[M * LDQ];
+    for (int e = threadIdx.x; e < M * M; e += 128) Qs[(e / M) * LDQ + (e % M)] = Qg[e];
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lr = lane & 3, lc = lane >> 2;
-    // B fragments: Q[4kk + lr][8nt + lc]
-    double bq[8][4];
-#pragma unroll
-    for (int kk = 0; kk < 8; ++kk)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) bq[kk][nt] = Qg[(4 * kk + lr) * 32 + 8 * nt + lc];
-    // A fragment kk: P[r0 + lc][4kk + lr]   (panel column 4kk + lr)
-    size_t acol[8];
-#pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-        const int cc = 4 * kk + lr;
-        const int gc = (cc < GSI_BJ_B) ? I * GSI_BJ_B + cc : J * GSI_BJ_B + (cc - GSI_BJ_B);
-        acol[kk] = (size_t)gc * ld + lc;
-    }
-    // D fragment nt: out[r0 + lc][8nt + 2lr + e]
-    size_t dcol[4][2];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int cc = 8 * nt + 2 * lr + e;
-            const int gc = (cc < GSI_BJ_B) ? I * GSI_BJ_B + cc : J * GSI_BJ_B + (cc - GSI_BJ_B);
-            dcol[nt][e] = (size_t)gc * ld + lc;
-        }
+    // A fragment kk: P[r0 + lc][4kk + lr];  D fragment nt: out[r0 + lc][8nt + 2lr + {0,1}]
+    const int c_lo = panel_col<M>(lr, I, J), c_hi = panel_col<M>(M / 2 + lr, I, J);       // columns 4kk+lr: kk < KS/2 in block I, else J
+    const int d_lo = panel_col<M>(2 * lr, I, J), d_hi = panel_col<M>(M / 2 + 2 * lr, I, J);
     for (int r0 = r_begin + 8 * warp; r0 < r_end; r0 += 32) {
-        double a[8];
+        double a[KS];
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) a[kk] = G[acol[kk] + r0];
-        double d[4][2];
+        for (int kk = 0; kk < KS; ++kk) {
+            const int gc = (kk < KS / 2 ? c_lo : c_hi - M / 2) + 4 * kk;
+            a[kk] = G[(size_t)gc * ld + r0 + lc];
+        }
+        double d[T][2];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < T; ++nt) {
             d[nt][0] = 0.0; d[nt][1] = 0.0;
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) dmma884(d[nt][0], d[nt][1], a[kk], bq[kk][nt]);
+            for (int kk = 0; kk < KS; ++kk) dmma884(d[nt][0], d[nt][1], a[kk], Qs[(4 * kk + lr) * LDQ + 8 * nt + lc]);
         }
         __syncwarp();
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-            G[dcol[nt][0] + r0] = d[nt][0];
-            G[dcol[nt][1] + r0] = d[nt][1];
+        for (int nt = 0; nt < T; ++nt) {
+            const int gc = (nt < T / 2 ? d_lo : d_hi - M / 2) + 8 * nt;
+            G[(size_t)gc * ld + r0 + lc] = d[nt][0];
+            G[(size_t)(gc + 1) * ld + r0 + lc] = d[nt][1];
         }
     }
 }
