@@ -252,3 +252,17 @@ class Context:
         v = ctypes.c_double(0)
         self._check(self._lib.gsi_measure_fp64_tflops(self._h, int(dmma), ctypes.byref(v)))
         return v.value
+
+    # ---- stage-wise test hook of the large-n eigensolver (gsi_debug_eigh) ----
+    def debug_eigh(self, a: np.ndarray, thr: float = 1e30, team: int = 0):
+        """Runs tridiagonalisation / divide & conquer / back-transform on one dense symmetric matrix
+        and returns dict(d, e, tau, v, lam, u, k); see include/gsi.h."""
+        a = np.asfortranarray(a, dtype=np.float64)
+        n = a.shape[0]
+        d = np.zeros(n); e = np.zeros(max(n - 1, 1)); tau = np.zeros(max(n - 1, 1))
+        v = np.zeros((n, n), order="F"); lam = np.zeros(n); u = np.zeros((n, n), order="F")
+        k = ctypes.c_int32(0)
+        self._check(self._lib.gsi_debug_eigh(self._h, n, _ptr(a), ctypes.c_float(thr), team, _ptr(d), _ptr(e), _ptr(tau),
+                                             _ptr(v), _ptr(lam), _ptr(u), ctypes.byref(k)))
+        kk = int(k.value)
+        return dict(d=d, e=e[:n - 1], tau=tau[:n - 1], v=v, lam=lam, u=u[:, :kk], k=kk)

@@ -16,6 +16,9 @@
 #include "kern_out.cuh"
 #include "kern_predict.cuh"
 #include "kern_knn.cuh"
+#include "kern_trd.cuh"
+#include "kern_dc.cuh"
+#include "kern_bt.cuh"
 
 static thread_local std::string g_tls_err;
 
@@ -99,6 +102,7 @@ struct Workspace {
     int64_t knn_edges = 0;
     DevBuf pred_meta, pred_work, p_off, p_items, p_wlim, p_rat, p_k, p_lamoff, p_vecoff, p_lam, p_vec, p_err, p_kk, p_pred, p_status, p_cols;
     DevBuf meta, vec_pad, lam_pad, G, rows, cols, perm, hpart, q, totals, items, sig, outk, outlam, outvec, stage_vec, stage_lam, probe;
+    DevBuf hhA, hhQa, hhQb, hhS, hhvec, hhivec, trd_acol, trd_ypart, trd_part, trd_panels;
     PinBuf h_meta, h_stage_vec, h_stage_lam, h_small, h_k, h_lamoff, h_vecoff, h_sig;
 };
 
@@ -140,6 +144,8 @@ extern "C" int gsi_create(gsi_ctx** out, int device, void* stream) {
     GSI_CUDA(ctx, set_smem_attr<5>());
     const char* bm = getenv("GSI_BJ_M");
     ctx->bj_m = (bm && atoi(bm) == 32) ? 32 : 64;
+    const char* lp = getenv("GSI_LARGE");          // "bj": one-sided block Jacobi (kept for comparison); default Householder + D&C
+    ctx->large_bj = lp && strcmp(lp, "bj") == 0;
     GSI_CUDA(ctx, cudaFuncSetAttribute(bj_inner_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 65 * 8));
     *out = ctx;
     return GSI_OK;
@@ -162,6 +168,8 @@ extern "C" int gsi_destroy(gsi_ctx* c) {
     DevBuf* d3[] = {&w.k_off, &w.k_items, &w.k_rat, &w.k_cnt, &w.k_num, &w.k_S, &w.k_ecnt, &w.k_eoff, &w.k_ea, &w.k_eb, &w.k_ew,
                     &w.k_co, &w.k_err, &w.k_mcnt, &w.k_has};
     for (auto b : d3) b->release();
+    DevBuf* d4[] = {&w.hhA, &w.hhQa, &w.hhQb, &w.hhS, &w.hhvec, &w.hhivec, &w.trd_acol, &w.trd_ypart, &w.trd_part, &w.trd_panels};
+    for (auto b : d4) b->release();
     PinBuf* p[] = {&w.h_meta, &w.h_stage_vec, &w.h_stage_lam, &w.h_small, &w.h_k, &w.h_lamoff, &w.h_vecoff, &w.h_sig};
     for (auto b : p) b->release();
     if (ctx->own_w && ctx->d_w) cudaFree(ctx->d_w);
@@ -247,6 +255,9 @@ struct Chunk { bool large; int begin, end; };   // [begin, end) into the sorted 
 
 static inline int64_t pad_slots(int n) { return (int64_t)n * std::max(n, 2); }
 static inline int ld_of(int n) { return (n + 7) & ~7; }
+static inline int hh_np(int n) { return (n + 63) & ~63; }
+// workspace of one user on the Householder path: A, Qa, Qb, S (np^2 each) + vectors
+static inline int64_t hh_ws_doubles(int n) { const int64_t np = hh_np(n); return 4 * np * np + 32 * np; }
 static inline int nb_of(int n, int B) { int nb = (n + B - 1) / B; return nb + (nb & 1); }
 
 static int plan(gsi_ctx* ctx, int64_t nu, const int64_t* off, std::vector<Job>& small, std::vector<Job>& large,
@@ -264,6 +275,18 @@ static int plan(gsi_ctx* ctx, int64_t nu, const int64_t* off, std::vector<Job>& 
     // large first (longest jobs first), then small
     const int64_t budget = ctx->ws_limit / (int64_t)sizeof(double);
     int b = 0;
+    while (b < (int)large.size() && !ctx->large_bj) {
+        // Householder path: any mix of sizes, bounded by the workspace (4 np^2 doubles per user)
+        int64_t used = 0;
+        int e = b;
+        while (e < (int)large.size() && e - b < 60000) {
+            const int64_t need = hh_ws_doubles(large[e].n);
+            if (e > b && used + need > budget) break;
+            used += need; ++e;
+        }
+        chunks.push_back({true, b, e});
+        b = e;
+    }
     while (b < (int)large.size()) {
         const int nmax = large[b].n;
         const int B = ctx->bj_m / 2, MM = ctx->bj_m * ctx->bj_m;
@@ -460,7 +483,7 @@ static int run_large_chunk(gsi_ctx* ctx, const Job* jobs, int nj, const int32_t*
         lap_degree_kernel<<<dim3((nmax + 127) / 128, 1, nj), 128, 0, st>>>(C);
         lap_transform_kernel<<<dim3((nmax + 127) / 128, (nmax + 7) / 8, nj), 128, 0, st>>>(C);
         lap_sigmin_kernel<<<dim3((nmax + 127) / 128, 1, nj), 128, 0, st>>>(C, out.d_sig_min);
-        lap_symmetrize_kernel<<<dim3(tiles * tiles, 1, nj), dim3(32, 8), 0, st>>>(C, tiles);
+        lap_symmetrize_kernel<<<dim3(tiles * tiles, 1, nj), dim3(32, 8), 0, st>>>(C, tiles, 1.0);
         GSI_CUDA(ctx, cudaGetLastError());
         sp.end();
     }
@@ -504,6 +527,8 @@ static int run_large_chunk(gsi_ctx* ctx, const Job* jobs, int nj, const int32_t*
     return finish_chunk(ctx, J, out, max_nk);
 }
 
+#include "hh_host.cuh"
+
 static int check_csr(gsi_ctx* ctx, int64_t nu, const int64_t* off, const int32_t* items) {
     if (off[0] != 0) return gsi_fail(ctx, GSI_ERR_INVALID, "offsets[0] must be 0");
     for (int64_t u = 0; u < nu; ++u) {
@@ -536,7 +561,7 @@ extern "C" int gsi_precompute_device(gsi_ctx* ctx, int64_t nu, const int64_t* h_
     if ((rc = plan(ctx, nu, h_offsets, small, large, chunks)) != GSI_OK) return rc;
     RunOut out{d_lam, lam_cap, d_vec, vec_cap, ws.totals.as<int64_t>(), d_k, d_lam_off, d_vec_off, d_sig_min};
     for (const Chunk& c : chunks) {
-        rc = c.large ? run_large_chunk(ctx, large.data() + c.begin, c.end - c.begin, d_items, out)
+        rc = c.large ? (ctx->large_bj ? run_large_chunk : run_hh_chunk)(ctx, large.data() + c.begin, c.end - c.begin, d_items, out)
                      : run_small_chunk(ctx, small.data() + c.begin, c.end - c.begin, d_items, out);
         if (rc != GSI_OK) return rc;
     }
@@ -588,7 +613,7 @@ extern "C" int gsi_precompute_stream(gsi_ctx* ctx, int64_t nu, const int64_t* of
         GSI_CUDA(ctx, cudaMemsetAsync(ws.totals.p, 0, 64, ctx->stream));
         RunOut out{ws.stage_lam.as<double>(), lcap, ws.stage_vec.as<double>(), vcap, ws.totals.as<int64_t>(),
                    ws.outk.as<int32_t>(), ws.outlam.as<int64_t>(), ws.outvec.as<int64_t>(), ws.sig.as<double>()};
-        rc = c.large ? run_large_chunk(ctx, jobs, nj, ws.items.as<int32_t>(), out)
+        rc = c.large ? (ctx->large_bj ? run_large_chunk : run_hh_chunk)(ctx, jobs, nj, ws.items.as<int32_t>(), out)
                      : run_small_chunk(ctx, jobs, nj, ws.items.as<int32_t>(), out);
         if (rc != GSI_OK) return rc;
         int64_t* h_tot = (int64_t*)(ws.h_small.as<char>() + 16);

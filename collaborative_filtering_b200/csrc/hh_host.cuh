@@ -1,0 +1,311 @@
+// Host side of the large path (n > GSI_S_MAX_N): Householder tridiagonalisation -> divide & conquer
+// -> back-transformation.  Included by gsi.cu after its helpers (DevBuf, Workspace, MetaBuilder,
+// upload_meta, finish_chunk, Job, RunOut).
+#pragma once
+
+struct HhPlan {
+    int nj = 0;
+    std::vector<HJob> jobs;
+    std::vector<DcLeaf> leaves;
+    std::vector<DcNode> nodes;            // ordered by level, then job
+    std::vector<int> lvl_begin;           // [Lmax + 2]; level l nodes are [lvl_begin[l], lvl_begin[l+1])
+    std::vector<int> lvl_mmax;            // [Lmax + 1]
+    std::vector<int2> bt_items;
+    int64_t mtot = 0, rtot = 0, vtot = 0, ltot = 0, max_nk = 0;
+    int Lmax = 0, npmax = 0, nmax = 0;
+};
+
+
+static void hh_cuts(int n, int& L, std::vector<int>& cuts) {
+    L = 0;
+    while (((n + (1 << L) - 1) >> L) > 24) ++L;
+    const int nl = 1 << L;
+    cuts.assign(nl + 1, 0);
+    for (int i = 1; i < nl; ++i) cuts[i] = (int)((((int64_t)n * i / nl) + 4) / 8 * 8);
+    cuts[nl] = n;
+}
+
+static void hh_build_plan(const Job* jobs, int nj, HhPlan& pl) {
+    pl = HhPlan();
+    pl.nj = nj;
+    pl.jobs.resize(nj);
+    std::vector<std::vector<int>> cuts(nj);
+    for (int j = 0; j < nj; ++j) {
+        HJob& h = pl.jobs[j];
+        h.n = jobs[j].n; h.np = hh_np(h.n); h.pad_ = 0;
+        h.m_off = pl.mtot; h.r_off = pl.rtot; h.item_off = jobs[j].item_off; h.vec_off = pl.vtot; h.lam_off = pl.ltot;
+        hh_cuts(h.n, h.levels, cuts[j]);
+        pl.mtot += (int64_t)h.np * h.np; pl.rtot += h.np;
+        pl.vtot += (int64_t)h.n * std::max(h.n, 2); pl.ltot += std::max(h.n, 2);
+        pl.max_nk = std::max<int64_t>(pl.max_nk, (int64_t)h.n * std::max(h.n, 2));
+        pl.Lmax = std::max(pl.Lmax, h.levels); pl.npmax = std::max(pl.npmax, h.np); pl.nmax = std::max(pl.nmax, h.n);
+        const int nl = 1 << h.levels;
+        for (int i = 0; i < nl; ++i) pl.leaves.push_back({j, cuts[j][i], cuts[j][i + 1] - cuts[j][i]});
+    }
+    pl.lvl_begin.assign(pl.Lmax + 2, 0);
+    pl.lvl_mmax.assign(pl.Lmax + 1, 0);
+    for (int l = 1; l <= pl.Lmax; ++l) {
+        pl.lvl_begin[l] = (int)pl.nodes.size();
+        for (int j = 0; j < nj; ++j) {
+            const int L = pl.jobs[j].levels;
+            if (L < l) continue;
+            const int step = 1 << l, half = step >> 1, cnt = 1 << (L - l);
+            for (int i = 0; i < cnt; ++i) {
+                const int off = cuts[j][i * step], mid = cuts[j][i * step + half], end = cuts[j][(i + 1) * step];
+                pl.nodes.push_back({j, off, mid - off, end - mid, l == L ? 1 : 0, 0});
+                pl.lvl_mmax[l] = std::max(pl.lvl_mmax[l], end - off);
+            }
+        }
+    }
+    pl.lvl_begin[pl.Lmax + 1] = (int)pl.nodes.size();
+    // back-transform work items, largest users first (jobs are sorted by n descending)
+    for (int j = 0; j < nj; ++j)
+        for (int cb = 0; cb * BT_CB < pl.jobs[j].n; ++cb) pl.bt_items.push_back(make_int2(j, cb));
+}
+
+struct HhDev {           // device views of one chunk
+    const HJob* jobs; const DcLeaf* leaves; const DcNode* nodes; const int2* bt_items;
+    DcState* state; int32_t* tile_off; unsigned int* sigmax; int32_t* kuser; int* ctl;
+    double *A, *Qa, *Qb, *S;
+    double *d, *e, *tau, *lamA, *lamB, *dk, *zk, *zhat, *dctau, *lamk, *dval, *ds, *zs, *sgn, *deg, *scale, *rot;
+    int32_t *orig, *gmap, *colsrc, *dsrc, *pos_nd, *pos_df, *src;
+    int64_t* user; int64_t* vec_dst; int64_t* lam_dst; int32_t* n_arr; int32_t* ld_arr; int64_t* moff_arr; int64_t* ioff_arr;
+    int64_t* roff_arr; int64_t* voff_arr; int64_t* loff_arr;
+};
+
+#define HH_CTL_INTS 1024       // [0] trd queue, [1] bt queue, [16 .. 16+148) slots, [256 .. 256+148) barrier counters
+
+static int hh_alloc(gsi_ctx* ctx, const HhPlan& pl, const Job* jobs, HhDev& D) {
+    Workspace& ws = WS(ctx);
+    int rc;
+    const int nj = pl.nj;
+    if ((rc = ws.hhA.ensure(ctx, pl.mtot * 8)) != GSI_OK) return rc;
+    if ((rc = ws.hhQa.ensure(ctx, pl.mtot * 8)) != GSI_OK) return rc;
+    if ((rc = ws.hhQb.ensure(ctx, pl.mtot * 8)) != GSI_OK) return rc;
+    if ((rc = ws.hhS.ensure(ctx, pl.mtot * 8)) != GSI_OK) return rc;
+    if ((rc = ws.hhvec.ensure(ctx, (size_t)pl.rtot * 8 * 21)) != GSI_OK) return rc;
+    if ((rc = ws.hhivec.ensure(ctx, (size_t)pl.rtot * 4 * 7)) != GSI_OK) return rc;
+    if ((rc = ws.vec_pad.ensure(ctx, pl.vtot * 8)) != GSI_OK) return rc;
+    if ((rc = ws.lam_pad.ensure(ctx, pl.ltot * 8)) != GSI_OK) return rc;
+    std::vector<int64_t> user(nj), moff(nj), ioff(nj), roff(nj), voff(nj), loff(nj);
+    std::vector<int32_t> n(nj), ld(nj);
+    for (int j = 0; j < nj; ++j) {
+        user[j] = jobs[j].user; moff[j] = pl.jobs[j].m_off; ioff[j] = pl.jobs[j].item_off; roff[j] = pl.jobs[j].r_off;
+        voff[j] = pl.jobs[j].vec_off; loff[j] = pl.jobs[j].lam_off; n[j] = pl.jobs[j].n; ld[j] = pl.jobs[j].np;
+    }
+    MetaBuilder mb;
+    const size_t o_jobs = mb.add(pl.jobs), o_leaves = mb.add(pl.leaves), o_nodes = mb.add(pl.nodes), o_items = mb.add(pl.bt_items);
+    const size_t o_user = mb.add(user), o_moff = mb.add(moff), o_ioff = mb.add(ioff), o_roff = mb.add(roff), o_voff = mb.add(voff),
+                 o_loff = mb.add(loff), o_n = mb.add(n), o_ld = mb.add(ld);
+    const size_t o_state = mb.reserve(std::max<size_t>(1, pl.nodes.size()) * sizeof(DcState));
+    const size_t o_tile = mb.reserve((2 * pl.nodes.size() + 2) * 4);
+    const size_t o_sig = mb.reserve((size_t)nj * 4), o_ku = mb.reserve((size_t)nj * 4), o_ctl = mb.reserve(HH_CTL_INTS * 4);
+    const size_t o_vd = mb.reserve((size_t)nj * 8), o_ldst = mb.reserve((size_t)nj * 8);
+    char* base;
+    if ((rc = upload_meta(ctx, mb, &base)) != GSI_OK) return rc;
+    D.jobs = (const HJob*)(base + o_jobs); D.leaves = (const DcLeaf*)(base + o_leaves); D.nodes = (const DcNode*)(base + o_nodes);
+    D.bt_items = (const int2*)(base + o_items); D.state = (DcState*)(base + o_state); D.tile_off = (int32_t*)(base + o_tile);
+    D.sigmax = (unsigned int*)(base + o_sig); D.kuser = (int32_t*)(base + o_ku); D.ctl = (int*)(base + o_ctl);
+    D.user = (int64_t*)(base + o_user); D.vec_dst = (int64_t*)(base + o_vd); D.lam_dst = (int64_t*)(base + o_ldst);
+    D.n_arr = (int32_t*)(base + o_n); D.ld_arr = (int32_t*)(base + o_ld); D.moff_arr = (int64_t*)(base + o_moff);
+    D.ioff_arr = (int64_t*)(base + o_ioff); D.roff_arr = (int64_t*)(base + o_roff); D.voff_arr = (int64_t*)(base + o_voff);
+    D.loff_arr = (int64_t*)(base + o_loff);
+    D.A = ws.hhA.as<double>(); D.Qa = ws.hhQa.as<double>(); D.Qb = ws.hhQb.as<double>(); D.S = ws.hhS.as<double>();
+    double* v = ws.hhvec.as<double>();
+    const int64_t r = pl.rtot;
+    D.d = v; D.e = v + r; D.tau = v + 2 * r; D.lamA = v + 3 * r; D.lamB = v + 4 * r; D.dk = v + 5 * r; D.zk = v + 6 * r;
+    D.zhat = v + 7 * r; D.dctau = v + 8 * r; D.lamk = v + 9 * r; D.dval = v + 10 * r; D.ds = v + 11 * r; D.zs = v + 12 * r;
+    D.sgn = v + 13 * r; D.deg = v + 14 * r; D.scale = v + 15 * r; D.rot = v + 16 * r;      // rot: 4 r
+    int32_t* iv = ws.hhivec.as<int32_t>();
+    D.orig = iv; D.gmap = iv + r; D.colsrc = iv + 2 * r; D.dsrc = iv + 3 * r; D.pos_nd = iv + 4 * r; D.pos_df = iv + 5 * r; D.src = iv + 6 * r;
+    cudaStream_t st = ctx->stream;
+    GSI_CUDA(ctx, cudaMemsetAsync(D.A, 0, pl.mtot * 8, st));
+    GSI_CUDA(ctx, cudaMemsetAsync(D.Qa, 0, pl.mtot * 8, st));
+    GSI_CUDA(ctx, cudaMemsetAsync(D.Qb, 0, pl.mtot * 8, st));
+    return GSI_OK;
+}
+
+// team size of the tridiagonalisation for a class of `count` users whose largest padded size is np
+static int hh_team_size(gsi_ctx* ctx, int np, int count, int forced) {
+    const int sms = ctx->sm_count;
+    const int tmin = (np + 1023) / 1024;
+    if (forced > 0) return std::min(sms, std::max(forced, tmin));
+    if (np > 4096) return sms;
+    int t = 1;
+    while (2 * t <= sms / std::max(count, 1)) t *= 2;      // few users: give each of them more SMs
+    return std::min(sms, std::max(t, tmin));
+}
+
+static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_team) {
+    Workspace& ws = WS(ctx);
+    cudaStream_t st = ctx->stream;
+    const int nj = pl.nj;
+    int rc;
+    // ---------------- tridiagonalisation: classes of similar size share a launch
+    {
+        int b = 0;
+        while (b < nj) {
+            const int npb = pl.jobs[b].np;
+            int e = b;
+            auto cls = [](int np) { return np > 4096 ? 3 : (np > 2048 ? 2 : (np > 1024 ? 1 : 0)); };
+            while (e < nj && cls(pl.jobs[e].np) == cls(npb)) ++e;
+            const int T = hh_team_size(ctx, npb, e - b, forced_team);
+            const int teams = std::max(1, std::min(ctx->sm_count / T, e - b));
+            int stages = 4;
+            while (stages > 2 && trd_smem_bytes(npb, stages) > 227 * 1024) --stages;
+            const size_t smem = trd_smem_bytes(npb, stages);
+            if (smem > 227 * 1024) return gsi_fail(ctx, GSI_ERR_INVALID, "user with n = %d does not fit the tridiagonalisation kernel", pl.jobs[b].n);
+            if ((rc = ws.trd_acol.ensure(ctx, (size_t)teams * npb * 8)) != GSI_OK) return rc;
+            if ((rc = ws.trd_ypart.ensure(ctx, (size_t)teams * T * npb * 8)) != GSI_OK) return rc;
+            if ((rc = ws.trd_part.ensure(ctx, (size_t)teams * T * TRD_PART * 8 + (size_t)teams * 2 * HH_NB * 8)) != GSI_OK) return rc;
+            if ((rc = ws.trd_panels.ensure(ctx, (size_t)2 * teams * npb * HH_NB * 8)) != GSI_OK) return rc;
+            TrdParams P;
+            P.jobs = D.jobs + b; P.njobs = e - b; P.queue = D.ctl; P.A = D.A; P.d = D.d; P.e = D.e; P.tau = D.tau;
+            P.T = T; P.npmax = npb; P.stages = stages;
+            P.acol = ws.trd_acol.as<double>(); P.ypart = ws.trd_ypart.as<double>(); P.part = ws.trd_part.as<double>();
+            P.tot = P.part + (size_t)teams * T * TRD_PART;
+            P.Vp = ws.trd_panels.as<double>(); P.Wp = P.Vp + (size_t)teams * npb * HH_NB;
+            P.bar = (unsigned*)(D.ctl + 256); P.slot = D.ctl + 16;
+            GSI_CUDA(ctx, cudaMemsetAsync(D.ctl, 0, HH_CTL_INTS * 4, st));
+            GSI_CUDA(ctx, cudaFuncSetAttribute(trd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GsiSpan sp(ctx, GSI_T_TRD, 1);
+            void* args[] = {&P};
+            GSI_CUDA(ctx, cudaLaunchCooperativeKernel((void*)trd_kernel, dim3(teams * T), dim3(TRD_THREADS), args, smem, st));
+            sp.end();
+            b = e;
+        }
+    }
+    // ---------------- divide & conquer
+    DcParams P;
+    P.jobs = D.jobs; P.nodes = D.nodes; P.state = D.state; P.Qa = D.Qa; P.Qb = D.Qb; P.S = D.S; P.lamA = D.lamA; P.lamB = D.lamB;
+    P.e = D.e; P.dk = D.dk; P.zk = D.zk; P.zhat = D.zhat; P.tau = D.dctau; P.lamk = D.lamk; P.dval = D.dval;
+    P.orig = D.orig; P.gmap = D.gmap; P.colsrc = D.colsrc; P.dsrc = D.dsrc; P.pos_nd = D.pos_nd; P.pos_df = D.pos_df;
+    P.ds = D.ds; P.zs = D.zs; P.src = D.src; P.rot = D.rot; P.sigmax = D.sigmax; P.kuser = D.kuser;
+    {
+        GsiSpan sp(ctx, GSI_T_DC, 1);
+        const int nl = (int)pl.leaves.size();
+        dc_leaf_kernel<<<(nl + 3) / 4, 128, 0, st>>>(D.jobs, D.leaves, nl, D.d, D.e, D.lamA, D.Qa);
+        sp.end();
+        GSI_CUDA(ctx, cudaGetLastError());
+    }
+    const size_t gemm_smem = (size_t)DCG_STAGES * DCG_STAGE_DBL * sizeof(double);
+    GSI_CUDA(ctx, cudaFuncSetAttribute(dc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
+    for (int l = 1; l <= pl.Lmax; ++l) {
+        P.node0 = pl.lvl_begin[l]; P.nnodes = pl.lvl_begin[l + 1] - pl.lvl_begin[l]; P.in_b = (l - 1) & 1;
+        const int mmax = pl.lvl_mmax[l];
+        {
+            GsiSpan sp(ctx, GSI_T_DC, 6);
+            dc_deflate_kernel<<<P.nnodes, 256, 0, st>>>(P);
+            dc_secular_kernel<<<dim3((mmax + 127) / 128, P.nnodes), 128, 0, st>>>(P);
+            dc_rank_kernel<<<P.nnodes, 256, 0, st>>>(P);
+            dc_zhat_kernel<<<dim3((mmax + 7) / 8, P.nnodes), 256, 0, st>>>(P);
+            dc_vectors_kernel<<<dim3((mmax + 7) / 8, P.nnodes), 256, 0, st>>>(P);
+            dc_plan_kernel<<<1, 1024, 0, st>>>(P, D.tile_off);
+            sp.end();
+        }
+        {
+            GsiSpan sp(ctx, GSI_T_DC_GEMM, 2);
+            dc_gemm_kernel<<<2 * ctx->sm_count, 256, gemm_smem, st>>>(P, D.tile_off);
+            dc_copy_kernel<<<dim3((mmax + 7) / 8, P.nnodes), 256, 0, st>>>(P);
+            sp.end();
+        }
+        GSI_CUDA(ctx, cudaGetLastError());
+    }
+    // ---------------- back-transformation
+    BtParams B;
+    B.jobs = D.jobs; B.njobs = nj; B.A = D.A; B.tau = D.tau; B.S = D.S; B.Qa = D.Qa; B.Qb = D.Qb; B.kuser = D.kuser;
+    B.items = D.bt_items; B.nitems = (int)pl.bt_items.size(); B.queue = D.ctl + 1;
+    {
+        GsiSpan sp(ctx, GSI_T_BT, 2);
+        GSI_CUDA(ctx, cudaFuncSetAttribute(bt_formt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_formt_smem_bytes()));
+        GSI_CUDA(ctx, cudaFuncSetAttribute(bt_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_smem_bytes()));
+        bt_formt_kernel<<<dim3((pl.nmax - 1 + BT_NB - 1) / BT_NB, nj), 256, bt_formt_smem_bytes(), st>>>(B);
+        GSI_CUDA(ctx, cudaMemsetAsync(D.ctl + 1, 0, 4, st));
+        bt_apply_kernel<<<ctx->sm_count, 256, bt_smem_bytes(), st>>>(B);
+        sp.end();
+        GSI_CUDA(ctx, cudaGetLastError());
+    }
+    return GSI_OK;
+}
+
+static BtParams hh_bt_params(const HhPlan& pl, const HhDev& D) {
+    BtParams B;
+    B.jobs = D.jobs; B.njobs = pl.nj; B.A = D.A; B.tau = D.tau; B.S = D.S; B.Qa = D.Qa; B.Qb = D.Qb; B.kuser = D.kuser;
+    B.items = D.bt_items; B.nitems = (int)pl.bt_items.size(); B.queue = D.ctl + 1;
+    return B;
+}
+
+// ---- large chunk through the Householder path --------------------------------------------------------
+static int run_hh_chunk(gsi_ctx* ctx, const Job* jobs, int nj, const int32_t* d_items, const RunOut& out) {
+    Workspace& ws = WS(ctx);
+    cudaStream_t st = ctx->stream;
+    HhPlan pl;
+    hh_build_plan(jobs, nj, pl);
+    HhDev D;
+    int rc;
+    if ((rc = hh_alloc(ctx, pl, jobs, D)) != GSI_OK) return rc;
+    {   // Laplacian stage (shared with the block-Jacobi path): sym(lower(L)) without the +1 shift
+        LChunk C;
+        memset(&C, 0, sizeof C);
+        C.nu = nj; C.n = D.n_arr; C.ld = D.ld_arr; C.g_off = D.moff_arr; C.item_off = D.ioff_arr; C.row_off = D.roff_arr;
+        C.G = D.A; C.deg = D.deg; C.scale = D.scale; C.sigmax = D.sigmax;
+        const int nmax = pl.nmax, tiles = (nmax + 31) / 32;
+        GsiSpan sp(ctx, GSI_T_LAP, 5);
+        lap_gather_kernel<<<dim3(tiles * tiles, 1, nj), dim3(32, 8), 0, st>>>(C, ctx->d_w, ctx->w_rows, d_items, tiles);
+        lap_degree_kernel<<<dim3((nmax + 127) / 128, 1, nj), 128, 0, st>>>(C);
+        lap_transform_kernel<<<dim3((nmax + 127) / 128, (nmax + 7) / 8, nj), 128, 0, st>>>(C);
+        lap_sigmin_kernel<<<dim3((nmax + 127) / 128, 1, nj), 128, 0, st>>>(C, out.d_sig_min);
+        lap_symmetrize_kernel<<<dim3(tiles * tiles, 1, nj), dim3(32, 8), 0, st>>>(C, tiles, 0.0);
+        sp.end();
+        GSI_CUDA(ctx, cudaGetLastError());
+    }
+    if ((rc = hh_solve(ctx, pl, D, 0)) != GSI_OK) return rc;
+    {
+        GsiSpan sp(ctx, GSI_T_BT, 2);
+        BtParams B = hh_bt_params(pl, D);
+        emit_sign_kernel<<<dim3((pl.nmax + 7) / 8, nj), 256, 0, st>>>(B, D.sgn);
+        const int tiles = (pl.nmax + 31) / 32;
+        emit_vec_kernel<<<dim3(tiles * tiles, 1, nj), dim3(32, 8), 0, st>>>(B, D.sgn, D.lamA, D.lamB, ws.vec_pad.as<double>(),
+                                                                          ws.lam_pad.as<double>(), tiles);
+        sp.end();
+        GSI_CUDA(ctx, cudaGetLastError());
+    }
+    OutJobs J;
+    J.nj = nj; J.n = D.n_arr; J.k = D.kuser; J.user = D.user; J.vec_pad = D.voff_arr; J.lam_pad = D.loff_arr;
+    J.vec_dst = D.vec_dst; J.lam_dst = D.lam_dst;
+    return finish_chunk(ctx, J, out, pl.max_nk);
+}
+
+// ---- stage-wise test hook ---------------------------------------------------------------------------
+extern "C" int gsi_debug_eigh(gsi_ctx* ctx, int n, const double* a, float thr, int team, double* d, double* e, double* tau,
+                              double* v, double* lam, double* u, int32_t* k) {
+    if (!ctx) return gsi_fail(nullptr, GSI_ERR_INVALID, "null context");
+    if (!a || n < 33 || n > 17664) return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_debug_eigh: need a matrix with 33 <= n <= 17664");
+    GSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    Job job{0, n, 0};
+    HhPlan pl;
+    hh_build_plan(&job, 1, pl);
+    HhDev D;
+    int rc;
+    if ((rc = hh_alloc(ctx, pl, &job, D)) != GSI_OK) return rc;
+    const int np = pl.jobs[0].np;
+    GSI_CUDA(ctx, cudaMemcpy2DAsync(D.A, (size_t)np * 8, a, (size_t)n * 8, (size_t)n * 8, n, cudaMemcpyHostToDevice, st));
+    // the cutoff kernel computes (float)(sigmax + 0.01); hand it sigmax = thr - 0.01 (test hook only)
+    const float sm = thr - 0.01f;
+    GSI_CUDA(ctx, cudaMemcpyAsync(D.sigmax, &sm, 4, cudaMemcpyHostToDevice, st));
+    GSI_CUDA(ctx, cudaStreamSynchronize(st));
+    if ((rc = hh_solve(ctx, pl, D, team)) != GSI_OK) return rc;
+    GSI_CUDA(ctx, cudaStreamSynchronize(st));
+    int32_t kk = 0;
+    GSI_CUDA(ctx, cudaMemcpy(&kk, D.kuser, 4, cudaMemcpyDeviceToHost));
+    if (k) *k = kk;
+    if (d) GSI_CUDA(ctx, cudaMemcpy(d, D.d, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    if (e) GSI_CUDA(ctx, cudaMemcpy(e, D.e, (size_t)(n - 1) * 8, cudaMemcpyDeviceToHost));
+    if (tau) GSI_CUDA(ctx, cudaMemcpy(tau, D.tau, (size_t)(n - 1) * 8, cudaMemcpyDeviceToHost));
+    if (v) GSI_CUDA(ctx, cudaMemcpy2D(v, (size_t)n * 8, D.A, (size_t)np * 8, (size_t)n * 8, n, cudaMemcpyDeviceToHost));
+    const bool in_b = pl.jobs[0].levels & 1;
+    if (lam) GSI_CUDA(ctx, cudaMemcpy(lam, in_b ? D.lamB : D.lamA, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    if (u && kk > 0) GSI_CUDA(ctx, cudaMemcpy2D(u, (size_t)n * 8, in_b ? D.Qb : D.Qa, (size_t)np * 8, (size_t)n * 8, kk, cudaMemcpyDeviceToHost));
+    return GSI_OK;
+}

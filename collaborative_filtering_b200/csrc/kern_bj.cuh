@@ -143,9 +143,9 @@ __global__ void lap_sigmin_kernel(LChunk C, double* __restrict__ sig_min) {
     atomicMax(&C.sigmax[u], __float_as_uint(sig));
 }
 
-// upper <- lower through a 32x32 smem tile (only tiles with ti <= tj do work), diagonal += 1.
+// upper <- lower through a 32x32 smem tile (only tiles with ti <= tj do work), diagonal += shift.
 // grid (tiles*tiles, 1, nu), block (32, 8)
-__global__ void lap_symmetrize_kernel(LChunk C, int tiles_per_dim) {
+__global__ void lap_symmetrize_kernel(LChunk C, int tiles_per_dim, double shift) {
     __shared__ double tile[32][33];
     const int u = blockIdx.z;
     const int n = C.n[u];
@@ -169,7 +169,7 @@ __global__ void lap_symmetrize_kernel(LChunk C, int tiles_per_dim) {
         const int i = ti * 32 + tx, j = tj * 32 + cl;
         if (i < n && j < n) {
             if (i < j) G[i + (size_t)j * ld] = tile[tx][cl];
-            else if (i == j) G[i + (size_t)j * ld] += 1.0;
+            else if (i == j) G[i + (size_t)j * ld] += shift;
         }
     }
 }

@@ -1,0 +1,298 @@
+// Large path, stage 3: back-transformation  U = H_0 H_1 ... H_{n-2} Z  of the kept eigenvectors of T
+// (Eigen does this inside SelfAdjointEigenSolver, precompute_local.cpp:231) and the record emit
+// (cutoff :252-261, row-major n x k as the text writer :263-280 walks it).
+//
+//   bt_formt_kernel   per 64-reflector panel: G = V^T V, the compact-WY T (dlarft, forward/columnwise),
+//                     and VT = V T stored in the (now free) S buffer
+//   bt_apply_kernel   persistent; a work item is a 32-column block of Z of one user.  The columns of Z
+//                     are independent, so a CTA walks all panels (last to first) of its block with no
+//                     inter-CTA synchronisation:   X = V^T Z_blk ;  Z_blk -= VT X    (DMMA m8n8k4,
+//                     operands staged with cp.async, double buffered)
+//   emit_sign_kernel / emit_vec_kernel   sign convention (largest |component| positive) + transpose
+#pragma once
+#include "gsi_internal.cuh"
+#include "kern_trd.cuh"
+#include "ptx.cuh"
+
+#define BT_NB 64
+#define BT_CB 32          // columns of Z per work item
+#define BT_LD 68          // shared-memory leading dimension (conflict-free DMMA fragments, 16-byte aligned)
+
+struct BtParams {
+    const HJob* jobs;
+    int njobs;
+    double* A;            // reflectors: column j holds v_j (1 at row j+1, zeros above)
+    const double* tau;    // [r_off + j]
+    double* S;            // VT (same layout as A)
+    double* Qa; double* Qb;   // Z lives in Qb when the user's level count is odd, else Qa
+    const int32_t* kuser;     // [jobs] kept columns
+    // work list
+    const int2* items;    // (job, column block), sorted by cost descending
+    int nitems;
+    int* queue;
+};
+
+// grid (max panels, njobs), block 256, dynamic smem 3 * 64*65 doubles
+static inline size_t bt_formt_smem_bytes() { return (size_t)3 * 64 * 65 * sizeof(double); }
+__global__ void __launch_bounds__(256) bt_formt_kernel(BtParams P) {
+    extern __shared__ __align__(16) double formt_smem[];
+    const HJob jb = P.jobs[blockIdx.y];
+    const int n = jb.n, np = jb.np, ld = jb.np;
+    const int j0 = blockIdx.x * BT_NB;
+    if (j0 >= n - 1) return;
+    const int b = min(BT_NB, n - 1 - j0);
+    const double* V = P.A + jb.m_off + (size_t)j0 * ld;       // column c of the panel: V + c*ld
+    double* VT = P.S + jb.m_off + (size_t)j0 * ld;
+    const double* tau = P.tau + jb.r_off + j0;
+    double* Vs = formt_smem;            // chunk: 64 rows x 64 cols, [row][col] padded to 65
+    double* G = Vs + 64 * 65;
+    double* Tm = G + 64 * 65;
+    const int tid = threadIdx.x;
+    const int tr = tid >> 4, tc = tid & 15;                    // thread owns rows 4tr.., cols 4tc.. of a 64x64 result
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+    for (int r0 = j0; r0 < np; r0 += 64) {
+        __syncthreads();
+        for (int e = tid; e < 64 * 64; e += 256) {
+            const int c = e >> 6, r = e & 63;
+            Vs[r * 65 + c] = (c < b) ? V[(size_t)c * ld + r0 + r] : 0.0;
+        }
+        __syncthreads();
+        for (int r = 0; r < 64; ++r) {
+            double x[4], y[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { x[a] = Vs[r * 65 + 4 * tr + a]; y[a] = Vs[r * 65 + 4 * tc + a]; }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = fma(x[a], y[c], acc[a][c]);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { G[(4 * tr + a) * 65 + 4 * tc + c] = acc[a][c]; Tm[(4 * tr + a) * 65 + 4 * tc + c] = 0.0; }
+    __syncthreads();
+    // T(j,j) = tau_j ;  T(0:j, j) = -tau_j * T(0:j, 0:j) * G(0:j, j)
+    for (int j = 0; j < b; ++j) {
+        const double tj = tau[j];
+        if (tid < j) {
+            double s = 0.0;
+            for (int l = tid; l < j; ++l) s = fma(Tm[tid * 65 + l], G[l * 65 + j], s);
+            Tm[tid * 65 + j] = -tj * s;
+        } else if (tid == j) Tm[j * 65 + j] = tj;
+        __syncthreads();
+    }
+    // VT = V T, 64-row chunks (T upper triangular, zero elsewhere)
+    for (int r0 = j0; r0 < np; r0 += 64) {
+        __syncthreads();
+        for (int e = tid; e < 64 * 64; e += 256) {
+            const int c = e >> 6, r = e & 63;
+            Vs[r * 65 + c] = (c < b) ? V[(size_t)c * ld + r0 + r] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+        for (int l = 0; l < b; ++l) {
+            double x[4], y[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { x[a] = Vs[(4 * tr + a) * 65 + l]; y[a] = Tm[l * 65 + 4 * tc + a]; }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = fma(x[a], y[c], acc[a][c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (4 * tc + c < b) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a) VT[(size_t)(4 * tc + c) * ld + r0 + 4 * tr + a] = acc[a][c];
+            }
+    }
+}
+
+// smem: 2 stages x (V chunk 64x64 + Z chunk 64x32) + X (64 x 32)
+#define BT_STAGE_DBL (BT_NB * BT_LD + BT_CB * BT_LD)
+static inline size_t bt_smem_bytes() { return (size_t)(2 * BT_STAGE_DBL + BT_CB * BT_LD) * sizeof(double); }
+
+__global__ void __launch_bounds__(256, 1) bt_apply_kernel(BtParams P) {
+    extern __shared__ __align__(16) double bt_smem[];
+    __shared__ int item_s;
+    double* Xs = bt_smem + 2 * BT_STAGE_DBL;       // [zcol][k] , k = reflector index within the panel
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fk = lane & 3, fr = lane >> 2;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) item_s = atomicAdd(P.queue, 1);
+        __syncthreads();
+        const int it = item_s;
+        if (it >= P.nitems) break;
+        const int2 item = P.items[it];
+        const HJob jb = P.jobs[item.x];
+        const int lim = P.kuser[item.x];
+        const int c0 = item.y * BT_CB;
+        if (c0 >= lim) continue;
+        const int n = jb.n, np = jb.np, ld = jb.np;
+        double* Z = ((jb.levels & 1) ? P.Qb : P.Qa) + jb.m_off + (size_t)c0 * ld;
+        const int npanels = (n - 1 + BT_NB - 1) / BT_NB;
+        for (int p = npanels - 1; p >= 0; --p) {
+            const int j0 = p * BT_NB;
+            const double* V = P.A + jb.m_off + (size_t)j0 * ld;
+            const double* VT = P.S + jb.m_off + (size_t)j0 * ld;
+            const int nch = (np - j0) / 64, b = min(BT_NB, n - 1 - j0);
+            // ---------------- phase 1: X = V^T Z  (64 x 32), K = rows j0 .. np
+            auto load1 = [&](int ch, int stg) {
+                double* Vs = bt_smem + (size_t)stg * BT_STAGE_DBL;
+                double* Zs = Vs + BT_NB * BT_LD;
+                const int r0 = j0 + ch * 64;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {           // V chunk: 64 cols x 32 16-byte chunks
+                    const int e = tid + t * 256, c = e >> 5, r2 = (e & 31) * 2;
+                    cp_async16_zfill(Vs + c * BT_LD + r2, V + (size_t)c * ld + r0 + r2, c < b);
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {           // Z chunk: 32 cols x 32 chunks
+                    const int e = tid + t * 256, c = e >> 5, r2 = (e & 31) * 2;
+                    cp_async16(Zs + c * BT_LD + r2, Z + (size_t)c * ld + r0 + r2);
+                }
+            };
+            double acc[4][2];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { acc[a][0] = 0.0; acc[a][1] = 0.0; }
+            __syncthreads();
+            load1(0, 0);
+            cp_async_commit();
+            for (int ch = 0; ch < nch; ++ch) {
+                if (ch + 1 < nch) load1(ch + 1, (ch + 1) & 1);
+                cp_async_commit();
+                cp_async_wait<1>();
+                __syncthreads();
+                const double* Vs = bt_smem + (size_t)(ch & 1) * BT_STAGE_DBL;
+                const double* Zs = Vs + BT_NB * BT_LD;
+                // D[vcol][zcol] += V[k][vcol] * Z[k][zcol];  warp -> vcol block, 4 zcol blocks
+#pragma unroll 4
+                for (int k4 = 0; k4 < 64; k4 += 4) {
+                    const double a = Vs[(8 * warp + fr) * BT_LD + k4 + fk];
+#pragma unroll
+                    for (int zb = 0; zb < 4; ++zb) {
+                        const double bq = Zs[(8 * zb + fr) * BT_LD + k4 + fk];
+                        dmma(acc[zb][0], acc[zb][1], a, bq);
+                    }
+                }
+                __syncthreads();
+            }
+            // X -> smem as Xs[zcol][vcol]: lane holds D[vcol = 8 warp + fr][zcol = 8 zb + 2 fk + {0,1}]
+#pragma unroll
+            for (int zb = 0; zb < 4; ++zb) {
+                Xs[(8 * zb + 2 * fk) * BT_LD + 8 * warp + fr] = acc[zb][0];
+                Xs[(8 * zb + 2 * fk + 1) * BT_LD + 8 * warp + fr] = acc[zb][1];
+            }
+            __syncthreads();
+            // ---------------- phase 2: Z -= VT X, 64-row chunks; warp -> 8-row block, 4 zcol blocks
+            auto load2 = [&](int ch, int stg) {
+                double* Ts = bt_smem + (size_t)stg * BT_STAGE_DBL;
+                const int r0 = j0 + ch * 64;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int e = tid + t * 256, c = e >> 5, r2 = (e & 31) * 2;
+                    cp_async16_zfill(Ts + c * BT_LD + r2, VT + (size_t)c * ld + r0 + r2, c < b);
+                }
+            };
+            load2(0, 0);
+            cp_async_commit();
+            for (int ch = 0; ch < nch; ++ch) {
+                if (ch + 1 < nch) load2(ch + 1, (ch + 1) & 1);
+                cp_async_commit();
+                const int r0 = j0 + ch * 64;
+                // D[zcol][row]: init with Z, subtract the product
+                double d[4][2];
+                double2* zp[4];
+#pragma unroll
+                for (int zb = 0; zb < 4; ++zb) {
+                    zp[zb] = (double2*)(Z + (size_t)(8 * zb + fr) * ld + r0 + 8 * warp + 2 * fk);
+                    d[zb][0] = 0.0; d[zb][1] = 0.0;
+                }
+                cp_async_wait<1>();
+                __syncthreads();
+                const double* Ts = bt_smem + (size_t)(ch & 1) * BT_STAGE_DBL;
+#pragma unroll 4
+                for (int k4 = 0; k4 < 64; k4 += 4) {
+                    const double bq = Ts[(k4 + fk) * BT_LD + 8 * warp + fr];        // VT[row][k]
+#pragma unroll
+                    for (int zb = 0; zb < 4; ++zb) {
+                        const double a = Xs[(8 * zb + fr) * BT_LD + k4 + fk];       // X[k][zcol]
+                        dmma(d[zb][0], d[zb][1], a, bq);
+                    }
+                }
+#pragma unroll
+                for (int zb = 0; zb < 4; ++zb) {
+                    double2 z = *zp[zb];
+                    z.x -= d[zb][0]; z.y -= d[zb][1];
+                    *zp[zb] = z;
+                }
+                __syncthreads();
+            }
+            cp_async_wait<0>();
+        }
+    }
+}
+
+// grid (ceil(npmax/8), njobs), block 256: warp per kept column -> sign (largest |component| positive,
+// first on ties), stored as +-1 in sgn[r_off + col]
+__global__ void __launch_bounds__(256) emit_sign_kernel(BtParams P, double* __restrict__ sgn) {
+    const HJob jb = P.jobs[blockIdx.y];
+    const int col = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int lim = P.kuser[blockIdx.y];
+    if (col >= lim || col >= jb.n) return;
+    const double* z = ((jb.levels & 1) ? P.Qb : P.Qa) + jb.m_off + (size_t)col * jb.np;
+    double best = -1.0;
+    int arg = 0;
+    for (int i = lane; i < jb.n; i += 32) {
+        const double v = fabs(z[i]);
+        if (v > best) { best = v; arg = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    if (lane == 0) sgn[jb.r_off + col] = (z[arg] < 0.0) ? -1.0 : 1.0;
+}
+
+// grid (tiles_i * tiles_r, 1, njobs), block (32, 8): vec[i*k + r] = sgn[r] * Z[i, r]; lam[r]
+__global__ void emit_vec_kernel(BtParams P, const double* __restrict__ sgn, const double* __restrict__ lamA,
+                                const double* __restrict__ lamB, double* __restrict__ vec_pad,
+                                double* __restrict__ lam_pad, int tiles_r) {
+    __shared__ double tile[32][33];
+    const HJob jb = P.jobs[blockIdx.z];
+    const int n = jb.n, k = P.kuser[blockIdx.z];
+    const int ti = blockIdx.x / tiles_r, tr = blockIdx.x % tiles_r;
+    if (ti * 32 >= n || tr * 32 >= k) return;
+    const double* Z = ((jb.levels & 1) ? P.Qb : P.Qa) + jb.m_off;
+    const int ld = jb.np, tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        const int rl = ty + 8 * rr;
+        const int r = tr * 32 + rl, i = ti * 32 + tx;
+        tile[rl][tx] = (r < k && i < n) ? Z[(size_t)r * ld + i] * sgn[jb.r_off + r] : 0.0;
+    }
+    __syncthreads();
+    double* vec = vec_pad + jb.vec_off;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        const int il = ty + 8 * rr;
+        const int i = ti * 32 + il, r = tr * 32 + tx;
+        if (i < n && r < k) vec[(size_t)i * k + r] = tile[tx][il];
+    }
+    if (ti == 0 && ty == 0) {
+        const int r = tr * 32 + tx;
+        const double* lam = ((jb.levels & 1) ? lamB : lamA) + jb.r_off;
+        if (r < k) lam_pad[jb.lam_off + r] = lam[r];
+    }
+}

@@ -198,7 +198,11 @@ enum {
     GSI_T_COMPACT = 6,     /* offset scan + compaction                                           */
     GSI_T_PREDICT = 7,
     GSI_T_KNN = 8,
-    GSI_T_COUNT = 9
+    GSI_T_TRD = 9,         /* Householder tridiagonalisation (large path)                        */
+    GSI_T_DC = 10,         /* divide & conquer on the tridiagonal: secular/deflation kernels      */
+    GSI_T_DC_GEMM = 11,    /* divide & conquer merge GEMMs (DMMA)                                 */
+    GSI_T_BT = 12,         /* back-transformation of the kept eigenvectors (DMMA) + emit          */
+    GSI_T_COUNT = 13
 };
 int gsi_timing_enable(gsi_ctx* ctx, int on);
 int gsi_timing_reset(gsi_ctx* ctx);
@@ -210,6 +214,20 @@ int gsi_timing_get(gsi_ctx* ctx, double* ms /*[GSI_T_COUNT]*/, int64_t* launches
  * SM, CUDA events) -- the roofline denominator for the Jacobi kernels (MEASURED_PEAKS.json holds
  * only HBM and bf16 tensor numbers).  `use_dmma` != 0 measures mma.sync m8n8k4 f64 instead. */
 int gsi_measure_fp64_tflops(gsi_ctx* ctx, int use_dmma, double* tflops);
+
+/* ---- stage-wise test hook of the large-n eigensolver ---------------------------------------- *
+ * Runs the Householder / divide-and-conquer / back-transform pipeline that gsi_precompute_* uses for
+ * n > GSI large-path threshold on ONE dense symmetric matrix given by the caller (host, n x n,
+ * column-major, n >= 33), and returns the intermediate results so that each stage can be compared
+ * with the oracle on its own (tests/test_eigh_stages_gpu.py):
+ *   d[n], e[n-1], tau[n-1]   tridiagonal T and Householder scalars;  V[n*n] reflectors (column j:
+ *                            v_j with v_j[j+1] = 1, zeros above)
+ *   lam[n]                   eigenvalues of T (= of A), ascending
+ *   U[n*k]                   eigenvectors of A for lam <= thr (at least 2), column-major n x k
+ * `team` is the number of CTAs that cooperate on the matrix (0 = the planner's choice).  Any output
+ * pointer may be NULL. */
+int gsi_debug_eigh(gsi_ctx* ctx, int n, const double* a, float thr, int team, double* d, double* e,
+                   double* tau, double* v, double* lam, double* u, int32_t* k);
 
 #ifdef __cplusplus
 }
