@@ -146,6 +146,8 @@ extern "C" int gsi_create(gsi_ctx** out, int device, void* stream) {
     ctx->bj_m = (bm && atoi(bm) == 32) ? 32 : 64;
     const char* lp = getenv("GSI_LARGE");          // "bj": one-sided block Jacobi (kept for comparison); default Householder + D&C
     ctx->large_bj = lp && strcmp(lp, "bj") == 0;
+    const char* tr = getenv("GSI_TRACE");
+    ctx->trace = tr && atoi(tr) != 0;
     GSI_CUDA(ctx, cudaFuncSetAttribute(bj_inner_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 65 * 8));
     *out = ctx;
     return GSI_OK;
@@ -463,6 +465,7 @@ static int run_large_chunk(gsi_ctx* ctx, const Job* jobs, int nj, const int32_t*
     char* base;
     if ((rc = upload_meta(ctx, mb, &base)) != GSI_OK) return rc;
     LChunk C;
+    C.tiled = 0;
     C.nu = nj; C.nb = nb; C.ncols = ncols; C.splits = splits;
     C.n = (const int32_t*)(base + o_n); C.ld = (const int32_t*)(base + o_ldim);
     C.g_off = (const int64_t*)(base + o_goff); C.item_off = (const int64_t*)(base + o_item);

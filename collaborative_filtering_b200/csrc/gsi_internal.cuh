@@ -31,6 +31,7 @@ struct gsi_ctx {
     int sm_count = 148;
     int64_t ws_limit = (int64_t)8 << 30;
     int bj_m = 64;
+    bool trace = false;        // GSI_TRACE=1: per-launch timing lines on stderr (synchronising; diagnostics only)
     bool large_bj = false;     // GSI_LARGE=bj: block-Jacobi large path instead of Householder + D&C
     // weights
     double* d_w = nullptr;

@@ -128,12 +128,11 @@ static int hh_alloc(gsi_ctx* ctx, const HhPlan& pl, const Job* jobs, HhDev& D) {
 // team size of the tridiagonalisation for a class of `count` users whose largest padded size is np
 static int hh_team_size(gsi_ctx* ctx, int np, int count, int forced) {
     const int sms = ctx->sm_count;
-    const int tmin = (np + 1023) / 1024;
-    if (forced > 0) return std::min(sms, std::max(forced, tmin));
+    if (forced > 0) return std::min(sms, forced);
     if (np > 4096) return sms;
-    int t = 1;
+    int t = (np > 2048) ? 8 : (np > 1024 ? 2 : 1);
     while (2 * t <= sms / std::max(count, 1)) t *= 2;      // few users: give each of them more SMs
-    return std::min(sms, std::max(t, tmin));
+    return std::min(sms, t);
 }
 
 static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_team) {
@@ -152,8 +151,8 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
             const int T = hh_team_size(ctx, npb, e - b, forced_team);
             const int teams = std::max(1, std::min(ctx->sm_count / T, e - b));
             int stages = 4;
-            while (stages > 2 && trd_smem_bytes(npb, stages) > 227 * 1024) --stages;
-            const size_t smem = trd_smem_bytes(npb, stages);
+            while (stages > 1 && trd_smem_bytes(npb, stages, T) > 227 * 1024) --stages;
+            const size_t smem = trd_smem_bytes(npb, stages, T);
             if (smem > 227 * 1024) return gsi_fail(ctx, GSI_ERR_INVALID, "user with n = %d does not fit the tridiagonalisation kernel", pl.jobs[b].n);
             if ((rc = ws.trd_acol.ensure(ctx, (size_t)teams * npb * 8)) != GSI_OK) return rc;
             if ((rc = ws.trd_ypart.ensure(ctx, (size_t)teams * T * npb * 8)) != GSI_OK) return rc;
@@ -161,17 +160,35 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
             if ((rc = ws.trd_panels.ensure(ctx, (size_t)2 * teams * npb * HH_NB * 8)) != GSI_OK) return rc;
             TrdParams P;
             P.jobs = D.jobs + b; P.njobs = e - b; P.queue = D.ctl; P.A = D.A; P.d = D.d; P.e = D.e; P.tau = D.tau;
-            P.T = T; P.npmax = npb; P.stages = stages;
+            P.T = T; P.npmax = npb; P.stages = stages; P.own_max = (npb / 64 + T - 1) / T;
             P.acol = ws.trd_acol.as<double>(); P.ypart = ws.trd_ypart.as<double>(); P.part = ws.trd_part.as<double>();
             P.tot = P.part + (size_t)teams * T * TRD_PART;
             P.Vp = ws.trd_panels.as<double>(); P.Wp = P.Vp + (size_t)teams * npb * HH_NB;
             P.bar = (unsigned*)(D.ctl + 256); P.slot = D.ctl + 16;
+            P.prof = ctx->trace ? (long long*)(D.ctl + 512) : nullptr;
             GSI_CUDA(ctx, cudaMemsetAsync(D.ctl, 0, HH_CTL_INTS * 4, st));
             GSI_CUDA(ctx, cudaFuncSetAttribute(trd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             GsiSpan sp(ctx, GSI_T_TRD, 1);
             void* args[] = {&P};
+            cudaEvent_t ta = nullptr, tb = nullptr;
+            if (ctx->trace) { cudaEventCreate(&ta); cudaEventCreate(&tb); cudaEventRecord(ta, st); }
             GSI_CUDA(ctx, cudaLaunchCooperativeKernel((void*)trd_kernel, dim3(teams * T), dim3(TRD_THREADS), args, smem, st));
             sp.end();
+            if (ctx->trace) {
+                cudaEventRecord(tb, st); cudaEventSynchronize(tb);
+                float ms = 0.f; cudaEventElapsedTime(&ms, ta, tb);
+                double n3 = 0; for (int j = b; j < e; ++j) n3 += (double)pl.jobs[j].n * pl.jobs[j].n * pl.jobs[j].n;
+                fprintf(stderr, "[gsi trace] trd: %d users n=%d..%d T=%d teams=%d stages=%d  %.2f ms  (sum n^3 = %.3g, symv bytes %.3g -> %.1f GB/s)\n",
+                        e - b, pl.jobs[b].n, pl.jobs[e - 1].n, T, teams, stages, ms, n3, n3 * 8 / 6, n3 * 8 / 6 / (ms * 1e-3) / 1e9);
+                long long pr[12];
+                cudaMemcpy(pr, D.ctl + 512, sizeof pr, cudaMemcpyDeviceToHost);
+                static const char* nm[12] = {"dots", "bar1", "scal", "symv", "ywr", "bar2", "preC", "rows", "dots+A0", "bar3", "syr2k", "bar4"};
+                long long tot = 0; for (int i = 0; i < 12; ++i) tot += pr[i];
+                fprintf(stderr, "[gsi trace]   CTA0 cycles %%:");
+                for (int i = 0; i < 12; ++i) fprintf(stderr, " %s %.1f", nm[i], 100.0 * pr[i] / std::max<long long>(tot, 1));
+                fprintf(stderr, "  (total %.1f ms @1.965GHz)\n", tot / 1.965e6);
+                cudaEventDestroy(ta); cudaEventDestroy(tb);
+            }
             b = e;
         }
     }
@@ -248,7 +265,7 @@ static int run_hh_chunk(gsi_ctx* ctx, const Job* jobs, int nj, const int32_t* d_
         LChunk C;
         memset(&C, 0, sizeof C);
         C.nu = nj; C.n = D.n_arr; C.ld = D.ld_arr; C.g_off = D.moff_arr; C.item_off = D.ioff_arr; C.row_off = D.roff_arr;
-        C.G = D.A; C.deg = D.deg; C.scale = D.scale; C.sigmax = D.sigmax;
+        C.G = D.A; C.deg = D.deg; C.scale = D.scale; C.sigmax = D.sigmax; C.tiled = 1;
         const int nmax = pl.nmax, tiles = (nmax + 31) / 32;
         GsiSpan sp(ctx, GSI_T_LAP, 5);
         lap_gather_kernel<<<dim3(tiles * tiles, 1, nj), dim3(32, 8), 0, st>>>(C, ctx->d_w, ctx->w_rows, d_items, tiles);
@@ -290,7 +307,11 @@ extern "C" int gsi_debug_eigh(gsi_ctx* ctx, int n, const double* a, float thr, i
     int rc;
     if ((rc = hh_alloc(ctx, pl, &job, D)) != GSI_OK) return rc;
     const int np = pl.jobs[0].np;
-    GSI_CUDA(ctx, cudaMemcpy2DAsync(D.A, (size_t)np * 8, a, (size_t)n * 8, (size_t)n * 8, n, cudaMemcpyHostToDevice, st));
+    const int NT = np >> 6;
+    std::vector<double> tiled((size_t)np * np, 0.0);
+    for (int cc = 0; cc < n; ++cc)
+        for (int r = 0; r < n; ++r) tiled[hh_tidx(r, cc, NT)] = a[(size_t)cc * n + r];
+    GSI_CUDA(ctx, cudaMemcpyAsync(D.A, tiled.data(), tiled.size() * 8, cudaMemcpyHostToDevice, st));
     // the cutoff kernel computes (float)(sigmax + 0.01); hand it sigmax = thr - 0.01 (test hook only)
     const float sm = thr - 0.01f;
     GSI_CUDA(ctx, cudaMemcpyAsync(D.sigmax, &sm, 4, cudaMemcpyHostToDevice, st));
@@ -303,7 +324,11 @@ extern "C" int gsi_debug_eigh(gsi_ctx* ctx, int n, const double* a, float thr, i
     if (d) GSI_CUDA(ctx, cudaMemcpy(d, D.d, (size_t)n * 8, cudaMemcpyDeviceToHost));
     if (e) GSI_CUDA(ctx, cudaMemcpy(e, D.e, (size_t)(n - 1) * 8, cudaMemcpyDeviceToHost));
     if (tau) GSI_CUDA(ctx, cudaMemcpy(tau, D.tau, (size_t)(n - 1) * 8, cudaMemcpyDeviceToHost));
-    if (v) GSI_CUDA(ctx, cudaMemcpy2D(v, (size_t)n * 8, D.A, (size_t)np * 8, (size_t)n * 8, n, cudaMemcpyDeviceToHost));
+    if (v) {
+        GSI_CUDA(ctx, cudaMemcpy(tiled.data(), D.A, tiled.size() * 8, cudaMemcpyDeviceToHost));
+        for (int cc = 0; cc < n; ++cc)
+            for (int r = 0; r < n; ++r) v[(size_t)cc * n + r] = tiled[hh_tidx(r, cc, NT)];
+    }
     const bool in_b = pl.jobs[0].levels & 1;
     if (lam) GSI_CUDA(ctx, cudaMemcpy(lam, in_b ? D.lamB : D.lamA, (size_t)n * 8, cudaMemcpyDeviceToHost));
     if (u && kk > 0) GSI_CUDA(ctx, cudaMemcpy2D(u, (size_t)n * 8, in_b ? D.Qb : D.Qa, (size_t)np * 8, (size_t)n * 8, kk, cudaMemcpyDeviceToHost));

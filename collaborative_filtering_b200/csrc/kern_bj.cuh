@@ -42,7 +42,14 @@ struct LChunk {
     int32_t* remaining;        // [1]
     double* Hpart;             // [nu][nb/2][splits][M*M]
     double* Q;                 // [nu][nb/2][M*M]
+    int tiled;                 // 1: G is tile-major (64x64 tiles, ld = 64-padded n) -- the Householder path
 };
+
+// offset of element (i, j) of a user's matrix
+__device__ __forceinline__ size_t lap_idx(const LChunk& C, int ld, int i, int j) {
+    if (C.tiled) return (((size_t)(j >> 6) * (ld >> 6) + (i >> 6)) << 12) + ((j & 63) << 6) + (i & 63);
+    return (size_t)i + (size_t)j * ld;
+}
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -83,7 +90,7 @@ __global__ void lap_gather_kernel(LChunk C, const double* __restrict__ W, int w_
     for (int rr = 0; rr < 4; ++rr) {
         const int jl = ty + 8 * rr;
         const int i = ti * 32 + tx, j = tj * 32 + jl;
-        if (i < n && j < n) G[i + (size_t)j * ld] = tile[tx][jl];
+        if (i < n && j < n) G[lap_idx(C, ld, i, j)] = tile[tx][jl];
     }
 }
 
@@ -96,7 +103,7 @@ __global__ void lap_degree_kernel(LChunk C) {
     const double* G = C.G + C.g_off[u];
     const int ld = C.ld[u];
     double d = 0.0;
-    for (int j = 0; j < n; ++j) d = __dadd_rn(d, G[i + (size_t)j * ld]);
+    for (int j = 0; j < n; ++j) d = __dadd_rn(d, G[lap_idx(C, ld, i, j)]);
     if (d == 0.0) d = 1.0;
     C.deg[C.row_off[u] + i] = d;
     C.scale[C.row_off[u] + i] = __dsqrt_rn(__ddiv_rn(1.0, d));
@@ -118,9 +125,9 @@ __global__ void lap_transform_kernel(LChunk C) {
     for (int jj = 0; jj < 8; ++jj) {
         const int j = j0 + jj;
         if (j < n) {
-            const double w = G[i + (size_t)j * ld];
+            const double w = G[lap_idx(C, ld, i, j)];
             const double ll = (i == j) ? __dsub_rn(di, w) : __dsub_rn(0.0, w);
-            G[i + (size_t)j * ld] = __dmul_rn(__dmul_rn(si, ll), sc[j]);
+            G[lap_idx(C, ld, i, j)] = __dmul_rn(__dmul_rn(si, ll), sc[j]);
         }
     }
 }
@@ -135,7 +142,7 @@ __global__ void lap_sigmin_kernel(LChunk C, double* __restrict__ sig_min) {
     const int ld = C.ld[u];
     float acc = 0.f;
     for (int j = 0; j < n; ++j) {
-        const double x = G[i + (size_t)j * ld];
+        const double x = G[lap_idx(C, ld, i, j)];
         acc = __double2float_rn(__dadd_rn((double)acc, __dmul_rn(x, x)));
     }
     const float sig = __fsqrt_rn(acc);
@@ -159,7 +166,7 @@ __global__ void lap_symmetrize_kernel(LChunk C, int tiles_per_dim, double shift)
     for (int rr = 0; rr < 4; ++rr) {
         const int cl = ty + 8 * rr;
         const int i = tj * 32 + tx, j = ti * 32 + cl;
-        tile[cl][tx] = (i < n && j < n) ? G[i + (size_t)j * ld] : 0.0;
+        tile[cl][tx] = (i < n && j < n) ? G[lap_idx(C, ld, i, j)] : 0.0;
     }
     __syncthreads();
     // write the upper tile (rows of block ti, columns of block tj)
@@ -168,8 +175,8 @@ __global__ void lap_symmetrize_kernel(LChunk C, int tiles_per_dim, double shift)
         const int cl = ty + 8 * rr;
         const int i = ti * 32 + tx, j = tj * 32 + cl;
         if (i < n && j < n) {
-            if (i < j) G[i + (size_t)j * ld] = tile[tx][cl];
-            else if (i == j) G[i + (size_t)j * ld] += shift;
+            if (i < j) G[lap_idx(C, ld, i, j)] = tile[tx][cl];
+            else if (i == j) G[lap_idx(C, ld, i, j)] += shift;
         }
     }
 }

@@ -21,7 +21,7 @@
 struct BtParams {
     const HJob* jobs;
     int njobs;
-    double* A;            // reflectors: column j holds v_j (1 at row j+1, zeros above)
+    double* A;            // reflectors, tile-major: column j holds v_j (1 at row j+1, zeros above within the panel)
     const double* tau;    // [r_off + j]
     double* S;            // VT (same layout as A)
     double* Qa; double* Qb;   // Z lives in Qb when the user's level count is odd, else Qa
@@ -41,8 +41,9 @@ __global__ void __launch_bounds__(256) bt_formt_kernel(BtParams P) {
     const int j0 = blockIdx.x * BT_NB;
     if (j0 >= n - 1) return;
     const int b = min(BT_NB, n - 1 - j0);
-    const double* V = P.A + jb.m_off + (size_t)j0 * ld;       // column c of the panel: V + c*ld
-    double* VT = P.S + jb.m_off + (size_t)j0 * ld;
+    const int NT = np >> 6;
+    const double* Auser = P.A + jb.m_off;                     // tile-major: rows r0.., panel columns = tile (r0/64, j0/64)
+    double* VT = P.S + jb.m_off + (size_t)j0 * ld;            // column-major
     const double* tau = P.tau + jb.r_off + j0;
     double* Vs = formt_smem;            // chunk: 64 rows x 64 cols, [row][col] padded to 65
     double* G = Vs + 64 * 65;
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(256) bt_formt_kernel(BtParams P) {
         __syncthreads();
         for (int e = tid; e < 64 * 64; e += 256) {
             const int c = e >> 6, r = e & 63;
-            Vs[r * 65 + c] = (c < b) ? V[(size_t)c * ld + r0 + r] : 0.0;
+            Vs[r * 65 + c] = (c < b) ? Auser[(((size_t)(j0 >> 6) * NT + (r0 >> 6)) << 12) + (c << 6) + r] : 0.0;
         }
         __syncthreads();
         for (int r = 0; r < 64; ++r) {
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(256) bt_formt_kernel(BtParams P) {
         __syncthreads();
         for (int e = tid; e < 64 * 64; e += 256) {
             const int c = e >> 6, r = e & 63;
-            Vs[r * 65 + c] = (c < b) ? V[(size_t)c * ld + r0 + r] : 0.0;
+            Vs[r * 65 + c] = (c < b) ? Auser[(((size_t)(j0 >> 6) * NT + (r0 >> 6)) << 12) + (c << 6) + r] : 0.0;
         }
         __syncthreads();
 #pragma unroll
@@ -142,7 +143,8 @@ __global__ void __launch_bounds__(256, 1) bt_apply_kernel(BtParams P) {
         const int npanels = (n - 1 + BT_NB - 1) / BT_NB;
         for (int p = npanels - 1; p >= 0; --p) {
             const int j0 = p * BT_NB;
-            const double* V = P.A + jb.m_off + (size_t)j0 * ld;
+            const int NT = np >> 6;
+            const double* Vt = P.A + jb.m_off + (((size_t)(j0 >> 6) * NT) << 12);   // tile column of the panel (tile-major A)
             const double* VT = P.S + jb.m_off + (size_t)j0 * ld;
             const int nch = (np - j0) / 64, b = min(BT_NB, n - 1 - j0);
             // ---------------- phase 1: X = V^T Z  (64 x 32), K = rows j0 .. np
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(256, 1) bt_apply_kernel(BtParams P) {
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {           // V chunk: 64 cols x 32 16-byte chunks
                     const int e = tid + t * 256, c = e >> 5, r2 = (e & 31) * 2;
-                    cp_async16_zfill(Vs + c * BT_LD + r2, V + (size_t)c * ld + r0 + r2, c < b);
+                    cp_async16_zfill(Vs + c * BT_LD + r2, Vt + ((size_t)(r0 >> 6) << 12) + (c << 6) + r2, c < b);
                 }
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {           // Z chunk: 32 cols x 32 chunks

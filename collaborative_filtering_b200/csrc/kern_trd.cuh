@@ -2,11 +2,12 @@
 // Eigen's SelfAdjointEigenSolver does at precompute_local.cpp:231), one persistent kernel.
 //
 // A TEAM of T co-resident CTAs (T = 1 .. all SMs) works on one user at a time and pulls users from a
-// queue.  The matrix is stored full (np x np, column-major, np = 64-padded) but only the 64 x 64
-// tiles on or below the diagonal are ever read or updated -- half the HBM bytes of a full symv.
+// queue.  The matrix is stored TILE-MAJOR (np x np, np = 64-padded, 64 x 64 column-major tiles, each
+// 32 KB contiguous: tile (I, J) at ((J * NT + I) << 12)), so one bulk copy moves a tile; only the tiles
+// on or below the diagonal are ever read or updated -- half the HBM bytes of a full symv.
 // Per column j of a 64-wide panel (LAPACK dlatrd scheme, updates deferred to the end of the panel):
 //
-//   phase A   acol = A[:,j] - V W[j,:]^T - W V[j,:]^T           rows are owned cyclically (256-row
+//   phase A   acol = A[:,j] - V W[j,:]^T - W V[j,:]^T           rows are owned cyclically (64-row
 //             partial ||acol[j+2:]||^2, partial W^T acol, V^T acol   blocks) by the team's CTAs
 //   -- team barrier 1 --
 //   phase B   beta, tau, v = scale * x'  (x' = acol with x'[j+1] = alpha - beta)
@@ -25,11 +26,11 @@
 #define HH_TS 64          // tile edge
 #define HH_NB 64          // panel width
 #define TRD_THREADS 256
-#define TRD_MAXR 4        // 256-row blocks a CTA may own: np <= 1024 * T
 #define TRD_PART 136      // doubles per CTA: [0] norm^2, [1] x'Ax', [2..66) W^T acol, [66..130) V^T acol
-#define TRD_STAGE_DBL (HH_TS * HH_TS + 2 * HH_TS)
+#define TRD_STAGE_DBL (HH_TS * HH_TS)
 #define TRD_SYR_LD 68     // k-stride of the syr2k operand panels in shared memory (conflict-free DMMA fragments)
-#define TRD_SYR_DBL (4 * TRD_SYR_LD * HH_NB)
+#define TRD_SYR_KH 32     // the trailing update stages its operands in two k-halves
+#define TRD_SYR_DBL (4 * TRD_SYR_LD * TRD_SYR_KH)
 
 // One user of the Householder / divide-and-conquer path
 struct HJob {
@@ -43,6 +44,11 @@ struct HJob {
     int64_t lam_off;      // into lam_pad
 };
 
+// element (r, c) of a tile-major np x np matrix with NT = np / 64 tiles per dimension
+__host__ __device__ __forceinline__ size_t hh_tidx(int r, int c, int NT) {
+    return (((size_t)(c >> 6) * NT + (r >> 6)) << 12) + ((c & 63) << 6) + (r & 63);
+}
+
 struct TrdParams {
     const HJob* jobs;
     int njobs;
@@ -50,6 +56,7 @@ struct TrdParams {
     double* A;
     double* d; double* e; double* tau;      // indexed by r_off
     int T, npmax, stages;
+    int own_max;          // 64-row blocks a CTA can own: ceil(npmax / 64 / T)
     double* acol;         // [teams][npmax]
     double* ypart;        // [teams][T][npmax]
     double* part;         // [teams][T][TRD_PART]
@@ -57,11 +64,13 @@ struct TrdParams {
     double* Vp; double* Wp;                 // [teams][npmax*HH_NB], leading dimension = the job's np
     unsigned* bar;        // [teams] monotonic arrival counters (zeroed before launch)
     int* slot;            // [teams] job broadcast
+    long long* prof;      // optional [16] cycle counters of CTA 0 (GSI_TRACE), else nullptr
 };
 
-static inline size_t trd_smem_bytes(int npmax, int stages) {
+static inline size_t trd_smem_bytes(int npmax, int stages, int T) {
     const size_t region = (size_t)std::max(stages * TRD_STAGE_DBL, TRD_SYR_DBL);
-    return (region + npmax + TRD_MAXR * 256 + 4 * 64 + 512 + 16) * sizeof(double) + 8 * sizeof(uint64_t) + 128;
+    const size_t own = (size_t)((npmax / 64 + T - 1) / T) * 64;
+    return (region + 2 * (size_t)npmax + own + 4 * 64 + 1152 + 16) * sizeof(double) + 16 * sizeof(uint64_t) + 128;
 }
 
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -105,8 +114,16 @@ struct TileWalk {
     __device__ __forceinline__ void next() { I += T; norm(); }
 };
 
+#define TRD_PROF(slot_)                                                             \
+    do {                                                                            \
+        if (prof_on) { const long long t_ = clock64(); prof_acc[slot_] += t_ - prof_t; prof_t = t_; } \
+    } while (0)
+
 __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
     extern __shared__ __align__(128) unsigned char trd_smem[];
+    const bool prof_on = P.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_t = prof_on ? clock64() : 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = P.T, team = blockIdx.x / T, c = blockIdx.x % T;
     const int npmax = P.npmax, stages = P.stages;
@@ -114,14 +131,17 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
     double* stage_base = (double*)trd_smem;
     const int region = max(stages * TRD_STAGE_DBL, TRD_SYR_DBL);
     double* ysm = stage_base + region;             // [npmax]
-    double* anext = ysm + npmax;                   // [TRD_MAXR*256]
-    double* Wtv = anext + TRD_MAXR * 256;          // [64]
+    double* xsm = ysm + npmax;                     // [npmax] acol of the step (bulk-copied once per step)
+    double* aown = xsm + npmax;                    // [own_max*64] acol of the rows this CTA owns
+    double* Wtv = aown + P.own_max * 64;           // [64]
     double* Vtv = Wtv + 64;
     double* Wrow = Vtv + 64;
     double* Vrow = Wrow + 64;
-    double* red = Vrow + 64;                       // [512]
-    double* sc = red + 512;                        // [16] scalars
-    uint64_t* full = (uint64_t*)(sc + 16);         // [8]
+    double* red = Vrow + 64;                       // [1152] two parities of (8 x 64 direct partials + 64 transposed sums)
+    double* sc = red + 1152;                       // [16] scalars
+    uint64_t* full = (uint64_t*)(sc + 16);         // [8] tile stages, [8] = the x vector
+    uint64_t* xbar = full + 8;
+    unsigned xphase = 0;
 
     double* acol = P.acol + (size_t)team * npmax;
     double* ypart = P.ypart + (size_t)team * T * npmax;
@@ -131,10 +151,12 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
     double* Wp = P.Wp + (size_t)team * npmax * HH_NB;
     unsigned* bar = P.bar + team;
     unsigned bar_target = 0;
-    unsigned seq = 0;                              // tiles streamed so far (mbarrier phase bookkeeping)
+    int c_st = 0, p_st = 0, pre_issued = 0;        // stage ring: next stage to consume / to fill; tiles requested ahead
+    unsigned c_ph = 0;                             // parity of the consumer's stage
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+        mbar_init(xbar, 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -150,43 +172,43 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
         double* dvec = P.d + jb.r_off;
         double* evec = P.e + jb.r_off;
         double* tvec = P.tau + jb.r_off;
-        const int R = (np + 256 * T - 1) / (256 * T);
-        double a_own[TRD_MAXR];
+        const int nown = (NT > c) ? (NT - c + T - 1) / T : 0;       // 64-row blocks c, c+T, ... owned by this CTA
         for (int i = tid; i < np; i += TRD_THREADS) ysm[i] = 0.0;
+        if (n < 2) team_barrier(bar, bar_target, T);                // keeps the slot broadcast race-free
 
-        auto issue_tile = [&](int I, int J, unsigned sq) {     // executed by warp 0
-            const int st = sq % stages;
-            double* tile = stage_base + (size_t)st * TRD_STAGE_DBL;
-            if (lane == 0) mbar_expect_tx(&full[st], (HH_TS * HH_TS + 2 * HH_TS) * 8);
-            __syncwarp();
-            const double* src = A + (size_t)(J * HH_TS) * ld + I * HH_TS;
-            bulk_g2s(tile + lane * HH_TS, src + (size_t)lane * ld, HH_TS * 8, &full[st]);
-            bulk_g2s(tile + (lane + 32) * HH_TS, src + (size_t)(lane + 32) * ld, HH_TS * 8, &full[st]);
-            if (lane == 0) bulk_g2s(tile + HH_TS * HH_TS, acol + I * HH_TS, HH_TS * 8, &full[st]);
-            if (lane == 1) bulk_g2s(tile + HH_TS * HH_TS + HH_TS, acol + J * HH_TS, HH_TS * 8, &full[st]);
+        auto issue_tile = [&](int I, int J, int st) {          // one thread; ONE request per tile (the copy engine
+            double* tile = stage_base + (size_t)st * TRD_STAGE_DBL;    // serialises requests, ~150 ns each)
+            mbar_expect_tx(&full[st], HH_TS * HH_TS * 8);
+            bulk_g2s(tile, A + (((size_t)J * NT + I) << 12), HH_TS * HH_TS * 8, &full[st]);
         };
 
         for (int j0 = 0; j0 < n - 1; j0 += HH_NB) {
             const int pw = min(HH_NB, n - 1 - j0);
+            const int JP = j0 >> 6;                                 // the panel's diagonal block
+            // first owned slot at or below the panel's diagonal block, number of live owned rows
+            const int s0 = (JP > c) ? (JP - c + T - 1) / T : 0;
+            const int rows_live = max(0, nown - s0) * 64;
+            // threads per row: short dependent chains when the CTA owns few rows
+            const int G = (rows_live <= 64) ? 4 : (rows_live <= 128 ? 2 : 1);
+            const int sub = tid & (G - 1), rs0 = tid / G, rstep = TRD_THREADS / G;
             // ---- phase A0: the matrix is up to date, acol = A[:, j0]
             {
                 double nrm = 0.0;
-#pragma unroll
-                for (int s = 0; s < TRD_MAXR; ++s) {
-                    const int r = (c + s * T) * 256 + tid;
-                    if (s < R && r < np) {
-                        const double a = (r >= j0) ? __ldcg(A + (size_t)j0 * ld + r) : 0.0;
-                        a_own[s] = a;
-                        acol[r] = a;
-                        if (r >= j0 + 2) nrm = fma(a, a, nrm);
-                    }
+                for (int rs = tid; rs < rows_live; rs += TRD_THREADS) {
+                    const int slot = s0 + (rs >> 6), r = (c + slot * T) * 64 + (rs & 63);
+                    const double a = (r >= j0) ? __ldcg(A + hh_tidx(r, j0, NT)) : 0.0;
+                    aown[slot * 64 + (rs & 63)] = a;
+                    acol[r] = a;
+                    if (r >= j0 + 2) nrm = fma(a, a, nrm);
                 }
                 nrm = cta_sum_d(nrm, red);
                 if (tid == 0) part[c * TRD_PART] = nrm;
             }
             for (int jj = 0; jj < pw; ++jj) {
                 const int j = j0 + jj;
+                TRD_PROF(0);
                 team_barrier(bar, bar_target, T);                                   // ---- barrier 1
+                TRD_PROF(1);
                 // ---- scalars of the reflector (identical arithmetic in every CTA)
                 if (warp == 0) {
                     double s = 0.0;
@@ -214,6 +236,7 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                     if (lane == 0) tot[idx - 2] = s;
                 }
                 __syncthreads();
+                TRD_PROF(2);
                 const double xfix = sc[3];
                 // ---- phase B: y = A x' over my tiles
                 const int J0 = (j + 1) >> 6;
@@ -223,62 +246,120 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                     TileWalk wi, wc;
                     wi.init(J0, NT, c, T);
                     wc = wi;
-                    int issued = 0;
-                    if (warp == 0) fence_proxy_async();
+                    int issued = pre_issued;                        // tiles already requested at the end of the last step
+                    for (int u = 0; u < pre_issued; ++u) wi.next();
+                    pre_issued = 0;
+                    if (mine > 0 && tid == 0) {                     // x' of this step: rows J0*64 .. np in ONE request
+                        const unsigned xb = (unsigned)(np - J0 * HH_TS) * 8;
+                        mbar_expect_tx(xbar, xb);
+                        bulk_g2s(xsm + J0 * HH_TS, acol + J0 * HH_TS, xb, xbar);
+                    }
                     for (; issued < min(stages, mine); ++issued) {
-                        if (warp == 0) issue_tile(wi.I, wi.J, seq + issued);
+                        if (tid == 0) issue_tile(wi.I, wi.J, p_st);
+                        p_st = (p_st + 1 == stages) ? 0 : p_st + 1;
                         wi.next();
                     }
-                    double xax = 0.0;
-                    const int i = tid & 63, q = tid >> 6;
-                    for (int k = 0; k < mine; ++k) {
-                        const unsigned sq = seq + k;
-                        const int st = sq % stages;
-                        mbar_wait(&full[st], (sq / stages) & 1);
-                        double* tile = stage_base + (size_t)st * TRD_STAGE_DBL;
-                        double* xI = tile + HH_TS * HH_TS;
-                        double* xJ = xI + HH_TS;
-                        const int I = wc.I, J = wc.J;
-                        if (tid < 128) {
-                            const int gi = (q ? J : I) * HH_TS + i;
-                            double* xp = q ? xJ : xI;
-                            if (gi <= j) xp[i] = 0.0;
-                            else if (gi == j + 1) xp[i] = xfix;
-                        }
-                        __syncthreads();
-                        {
-                            double acc = 0.0;
-#pragma unroll
-                            for (int cc = 0; cc < 16; ++cc) acc = fma(tile[(q * 16 + cc) * HH_TS + i], xJ[q * 16 + cc], acc);
-                            red[q * 64 + i] = acc;
-                        }
-                        if (I != J) {
-                            double acc = 0.0;
-#pragma unroll
-                            for (int kk = 0; kk < 16; ++kk) {
-                                const int r = q * 16 + ((kk + i) & 15);
-                                acc = fma(tile[i * HH_TS + r], xI[r], acc);
-                            }
-                            red[256 + q * 64 + i] = acc;
-                        }
-                        __syncthreads();
+                    if (mine > 0) {
+                        mbar_wait(xbar, xphase & 1);
+                        ++xphase;
+                        // x' = acol with the rows <= j zeroed and x'[j+1] = alpha - beta: only block J0 is touched
                         if (tid < 64) {
-                            const double y = (red[i] + red[64 + i]) + (red[128 + i] + red[192 + i]);
-                            ysm[I * HH_TS + i] += y;
-                            xax = fma(xI[i] * y, (I != J) ? 2.0 : 1.0, xax);
-                        } else if (tid < 128 && I != J) {
-                            const double y = (red[256 + i] + red[320 + i]) + (red[384 + i] + red[448 + i]);
-                            ysm[J * HH_TS + i] += y;
+                            const int gi = J0 * HH_TS + tid;
+                            if (gi <= j) xsm[gi] = 0.0;
+                            else if (gi == j + 1) xsm[gi] = xfix;
+                        }
+                        fence_proxy_async();                        // this generic write precedes the next step's bulk copy
+                        __syncthreads();
+                    }
+                    double xax = 0.0;
+                    for (int k = 0; k < mine; ++k) {
+                        mbar_wait(&full[c_st], c_ph);
+                        const double* tile = stage_base + (size_t)c_st * TRD_STAGE_DBL;
+                        const int st_now = c_st;
+                        if (++c_st == stages) { c_st = 0; c_ph ^= 1; }
+                        const int I = wc.I, J = wc.J;
+                        const double* xI = xsm + I * HH_TS;
+                        const double* xJ = xsm + J * HH_TS;
+                        double* rd = red + (k & 1) * 576;           // [8 warps][64 rows] direct partials + [64] transposed sums
+                        // warp w owns tile columns 8w..8w+7; lane owns rows 2 lane, 2 lane + 1 (16-byte loads)
+                        const double2* tp = (const double2*)tile + (8 * warp) * 32 + lane;
+                        double2 a[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) a[q] = tp[q * 32];
+                        double xj[8];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const double2 v = ((const double2*)xJ)[4 * warp + q];
+                            xj[2 * q] = v.x; xj[2 * q + 1] = v.y;
+                        }
+                        double2 de = make_double2(0.0, 0.0), dodd = make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int q = 0; q < 8; q += 2) {
+                            de.x = fma(a[q].x, xj[q], de.x); de.y = fma(a[q].y, xj[q], de.y);
+                            dodd.x = fma(a[q + 1].x, xj[q + 1], dodd.x); dodd.y = fma(a[q + 1].y, xj[q + 1], dodd.y);
+                        }
+                        ((double2*)rd)[warp * 32 + lane] = make_double2(de.x + dodd.x, de.y + dodd.y);
+                        if (I != J) {
+                            const double2 xi = ((const double2*)xI)[lane];
+                            double t[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) t[q] = fma(a[q].x, xi.x, a[q].y * xi.y);
+                            // transpose-reduce: 8 column sums over 32 lanes in 9 shuffles
+                            const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
+                            double u[4], v2[2], w1;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const double send = h4 ? t[q] : t[q + 4];
+                                const double keep = h4 ? t[q + 4] : t[q];
+                                u[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                const double send = h3 ? u[q] : u[q + 2];
+                                const double keep = h3 ? u[q + 2] : u[q];
+                                v2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                            }
+                            {
+                                const double send = h2 ? v2[0] : v2[1];
+                                const double keep = h2 ? v2[1] : v2[0];
+                                w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                            }
+                            w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+                            w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+                            if ((lane & 3) == 0) rd[512 + 8 * warp + ((lane >> 2) & 7)] = w1;
                         }
                         __syncthreads();
-                        if (issued < mine) {
-                            if (warp == 0) { fence_proxy_async(); issue_tile(wi.I, wi.J, seq + issued); }
+                        if (issued < mine) {                        // every warp has the tile in registers: refill the stage
+                            if (tid == 0) issue_tile(wi.I, wi.J, st_now);
+                            p_st = (p_st + 1 == stages) ? 0 : p_st + 1;
                             wi.next();
                             ++issued;
                         }
+                        if (tid < 64) {
+                            const double y = ((rd[tid] + rd[64 + tid]) + (rd[128 + tid] + rd[192 + tid])) +
+                                             ((rd[256 + tid] + rd[320 + tid]) + (rd[384 + tid] + rd[448 + tid]));
+                            ysm[I * HH_TS + tid] += y;
+                            xax = fma(xI[tid] * y, (I != J) ? 2.0 : 1.0, xax);
+                        } else if (tid < 128 && I != J) {
+                            ysm[J * HH_TS + tid - 64] += rd[512 + tid - 64];
+                        }
                         wc.next();
                     }
-                    seq += mine;
+                    __syncthreads();                                // the last tile's sums are in ysm
+                    // the matrix does not change inside a panel: request the first tiles of the next step now, so
+                    // that they stream in while the team synchronises
+                    if (jj + 1 < pw) {
+                        const int J0n = (j + 2) >> 6, mn = NT - J0n, totn = mn * (mn + 1) / 2;
+                        const int minen = (c < totn) ? (totn - c + T - 1) / T : 0;
+                        TileWalk wn;
+                        wn.init(J0n, NT, c, T);
+                        for (; pre_issued < min(stages, minen); ++pre_issued) {
+                            if (tid == 0) issue_tile(wn.I, wn.J, p_st);
+                            p_st = (p_st + 1 == stages) ? 0 : p_st + 1;
+                            wn.next();
+                        }
+                    }
+                    TRD_PROF(3);
                     for (int r = J0 * HH_TS + tid; r < np; r += TRD_THREADS) {
                         ypart[(size_t)c * npmax + r] = ysm[r];
                         ysm[r] = 0.0;
@@ -286,7 +367,9 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                     xax = cta_sum_d(xax, red);
                     if (tid == 0) part[c * TRD_PART + 1] = xax;
                 }
+                TRD_PROF(4);
                 team_barrier(bar, bar_target, T);                                   // ---- barrier 2
+                TRD_PROF(5);
                 // ---- phase C
                 const double beta = sc[0], tj = sc[1], scale = sc[2];
                 if (tid < jj) {
@@ -322,92 +405,131 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                 __syncthreads();
                 const double alpha2 = sc[6], wj1 = sc[7];
                 const bool more = jj + 1 < pw;
+                TRD_PROF(6);
                 double nrm = 0.0;
-#pragma unroll
-                for (int s = 0; s < TRD_MAXR; ++s) {
-                    const int r = (c + s * T) * 256 + tid;
-                    if (s < R && r < np) {
-                        if (r <= j) { A[(size_t)j * ld + r] = 0.0; anext[s * 256 + tid] = 0.0; }
-                        else {
-                            double av = 0.0;
-                            for (int cc = 0; cc < T; ++cc) av += __ldcg(ypart + (size_t)cc * npmax + r);
-                            av *= scale;
-                            const double vr = (r == j + 1) ? 1.0 : scale * a_own[s];
-                            double pdot = 0.0, adot = 0.0;
-                            for (int cc = 0; cc < jj; ++cc) {
-                                const double vv = __ldcg(Vp + (size_t)cc * ld + r), ww = __ldcg(Wp + (size_t)cc * ld + r);
-                                pdot = fma(vv, Wtv[cc], fma(ww, Vtv[cc], pdot));
-                                adot = fma(vv, Wrow[cc], fma(ww, Vrow[cc], adot));
-                            }
-                            const double wr = tj * (av - pdot) + alpha2 * vr;
-                            Vp[(size_t)jj * ld + r] = vr;
-                            Wp[(size_t)jj * ld + r] = wr;
-                            A[(size_t)j * ld + r] = vr;
-                            if (more) {
-                                const double an = __ldcg(A + (size_t)(j + 1) * ld + r) - adot - vr * wj1 - wr;
-                                a_own[s] = an;
-                                acol[r] = an;
-                                anext[s * 256 + tid] = an;
-                                if (r >= j + 3) nrm = fma(an, an, nrm);
-                            }
+                for (int base = 0; base < rows_live; base += rstep) {          // CTA-uniform trip count (shuffles inside)
+                    const int rs = base + rs0;
+                    const bool valid = rs < rows_live;
+                    const int slot = s0 + (rs >> 6), ii = rs & 63, r = (c + slot * T) * 64 + ii;
+                    const bool act = valid && r > j;
+                    // rows of the panel's diagonal block above the reflector
+                    if (valid && !act && sub == 0 && r >= j0) A[hh_tidx(r, j, NT)] = 0.0;
+                    double av = 0.0, pdot = 0.0, adot = 0.0;
+                    if (act) {
+#pragma unroll 4
+                        for (int cc = sub; cc < T; cc += G) av += __ldcg(ypart + (size_t)cc * npmax + r);
+#pragma unroll 4
+                        for (int cc = sub; cc < jj; cc += G) {
+                            const double vv = __ldcg(Vp + (size_t)cc * ld + r), ww = __ldcg(Wp + (size_t)cc * ld + r);
+                            pdot = fma(vv, Wtv[cc], fma(ww, Vtv[cc], pdot));
+                            adot = fma(vv, Wrow[cc], fma(ww, Vrow[cc], adot));
+                        }
+                    }
+                    for (int o = 1; o < G; o <<= 1) {              // lanes of a row are adjacent
+                        av += __shfl_xor_sync(0xffffffffu, av, o);
+                        pdot += __shfl_xor_sync(0xffffffffu, pdot, o);
+                        adot += __shfl_xor_sync(0xffffffffu, adot, o);
+                    }
+                    if (act && sub == 0) {
+                        av *= scale;
+                        const double vr = (r == j + 1) ? 1.0 : scale * aown[slot * 64 + ii];
+                        const double wr = tj * (av - pdot) + alpha2 * vr;
+                        Vp[(size_t)jj * ld + r] = vr;
+                        Wp[(size_t)jj * ld + r] = wr;
+                        A[hh_tidx(r, j, NT)] = vr;
+                        if (more) {
+                            const double an = __ldcg(A + hh_tidx(r, j + 1, NT)) - adot - vr * wj1 - wr;
+                            aown[slot * 64 + ii] = an;
+                            acol[r] = an;
+                            if (r >= j + 3) nrm = fma(an, an, nrm);
                         }
                     }
                 }
+                TRD_PROF(7);
                 if (more) {
-                    nrm = cta_sum_d(nrm, red);          // (its __syncthreads also publish anext and the new panel column)
+                    nrm = cta_sum_d(nrm, red);          // (its __syncthreads also publish aown and the new panel column)
                     if (tid == 0) part[c * TRD_PART] = nrm;
-                    for (int qd = warp; qd < 2 * (jj + 1); qd += TRD_THREADS / 32) {
-                        const int which = qd > jj, cc = which ? qd - (jj + 1) : qd;
-                        const double* Pn = (which ? Vp : Wp) + (size_t)cc * ld;
-                        double acc = 0.0;
-                        for (int s = 0; s < R; ++s) {
-                            const int base = (c + s * T) * 256;
-                            for (int ii = lane; ii < 256; ii += 32) {
-                                const int r = base + ii;
-                                if (r < np && r >= j + 2) acc = fma(__ldcg(Pn + r), anext[s * 256 + ii], acc);
+                    // partial W^T acol, V^T acol over my live rows: a warp takes 4 columns at a time so that
+                    // their (L2-latency bound) loads overlap
+                    const int ncols = 2 * (jj + 1);
+                    for (int q0 = 4 * warp; q0 < ncols; q0 += 4 * (TRD_THREADS / 32)) {
+                        const double* Pn[4];
+                        double acc[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int qd = min(q0 + u, ncols - 1);
+                            const int which = qd > jj, cc = which ? qd - (jj + 1) : qd;
+                            Pn[u] = (which ? Vp : Wp) + (size_t)cc * ld;
+                            acc[u] = 0.0;
+                        }
+                        for (int rs = lane; rs < rows_live; rs += 32) {
+                            const int slot = s0 + (rs >> 6), r = (c + slot * T) * 64 + (rs & 63);
+                            if (r >= j + 2) {
+                                const double av = aown[slot * 64 + (rs & 63)];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) acc[u] = fma(__ldcg(Pn[u] + r), av, acc[u]);
                             }
                         }
-                        acc = warp_sum_d(acc);
-                        if (lane == 0) part[c * TRD_PART + 2 + which * HH_NB + cc] = acc;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const double v = warp_sum_d(acc[u]);
+                            const int qd = q0 + u;
+                            if (lane == 0 && qd < ncols) {
+                                const int which = qd > jj, cc = which ? qd - (jj + 1) : qd;
+                                part[c * TRD_PART + 2 + which * HH_NB + cc] = v;
+                            }
+                        }
                     }
                 }
             }
             // ---- trailing update  A22 -= V W^T + W V^T  on the tiles at or below (jn, jn)
+            TRD_PROF(8);
             team_barrier(bar, bar_target, T);
+            TRD_PROF(9);
             {
                 const int jn = j0 + pw, kpad = (pw + 3) & ~3;
                 double* S = stage_base;
                 TileWalk w;
                 for (w.init(jn >> 6, NT, c, T); w.valid(); w.next()) {
                     const int I = w.I, J = w.J;
-                    for (int idx = tid; idx < 4 * 64 * kpad; idx += TRD_THREADS) {
-                        const int which = idx / (64 * kpad), rem = idx - which * 64 * kpad, k = rem >> 6, r = rem & 63;
-                        const double* src = ((which & 1) ? Wp : Vp) + (size_t)k * ld + ((which >> 1) ? J : I) * HH_TS + r;
-                        S[which * (TRD_SYR_LD * HH_NB) + k * TRD_SYR_LD + r] = (k < pw) ? __ldcg(src) : 0.0;
-                    }
-                    __syncthreads();
-                    const double* VIs = S, *WIs = S + TRD_SYR_LD * HH_NB, *VJs = S + 2 * TRD_SYR_LD * HH_NB, *WJs = S + 3 * TRD_SYR_LD * HH_NB;
                     double acc[8][2];
 #pragma unroll
                     for (int rb = 0; rb < 8; ++rb) { acc[rb][0] = 0.0; acc[rb][1] = 0.0; }
                     const int fk = lane & 3, fr = lane >> 2;
-                    for (int k0 = 0; k0 < kpad; k0 += 4) {
-                        const double aW = WJs[(k0 + fk) * TRD_SYR_LD + 8 * warp + fr];
-                        const double aV = VJs[(k0 + fk) * TRD_SYR_LD + 8 * warp + fr];
+                    for (int kh = 0; kh < kpad; kh += TRD_SYR_KH) {
+                        const int kc = min(TRD_SYR_KH, kpad - kh);
 #pragma unroll
-                        for (int rb = 0; rb < 8; ++rb) {
-                            const double bV = VIs[(k0 + fk) * TRD_SYR_LD + 8 * rb + fr];
-                            const double bW = WIs[(k0 + fk) * TRD_SYR_LD + 8 * rb + fr];
-                            dmma(acc[rb][0], acc[rb][1], aW, bV);
-                            dmma(acc[rb][0], acc[rb][1], aV, bW);
+                        for (int which = 0; which < 4; ++which) {
+                            const double* srcp = ((which & 1) ? Wp : Vp) + (size_t)kh * ld + ((which >> 1) ? J : I) * HH_TS;
+                            double* dstp = S + which * (TRD_SYR_LD * TRD_SYR_KH);
+                            for (int e = tid; e < 64 * kc; e += TRD_THREADS) {
+                                const int k = e >> 6, r = e & 63;
+                                dstp[k * TRD_SYR_LD + r] = (kh + k < pw) ? __ldcg(srcp + (size_t)k * ld + r) : 0.0;
+                            }
                         }
+                        __syncthreads();
+                        const double* VIs = S, *WIs = S + TRD_SYR_LD * TRD_SYR_KH, *VJs = S + 2 * TRD_SYR_LD * TRD_SYR_KH,
+                                     *WJs = S + 3 * TRD_SYR_LD * TRD_SYR_KH;
+                        for (int k0 = 0; k0 < kc; k0 += 4) {
+                            const double aW = WJs[(k0 + fk) * TRD_SYR_LD + 8 * warp + fr];
+                            const double aV = VJs[(k0 + fk) * TRD_SYR_LD + 8 * warp + fr];
+#pragma unroll
+                            for (int rb = 0; rb < 8; ++rb) {
+                                const double bV = VIs[(k0 + fk) * TRD_SYR_LD + 8 * rb + fr];
+                                const double bW = WIs[(k0 + fk) * TRD_SYR_LD + 8 * rb + fr];
+                                dmma(acc[rb][0], acc[rb][1], aW, bV);
+                                dmma(acc[rb][0], acc[rb][1], aV, bW);
+                            }
+                        }
+                        __syncthreads();
                     }
-                    const int gc = J * HH_TS + 8 * warp + fr;
+                    const int lc = 8 * warp + fr, gc = J * HH_TS + lc;
                     if (gc >= jn) {
+                        double* tile = A + (((size_t)J * NT + I) << 12) + lc * HH_TS;
 #pragma unroll
                         for (int rb = 0; rb < 8; ++rb) {
-                            const int gr = I * HH_TS + 8 * rb + 2 * fk;
-                            double2* p = (double2*)(A + (size_t)gc * ld + gr);
+                            const int lr = 8 * rb + 2 * fk, gr = I * HH_TS + lr;
+                            double2* p = (double2*)(tile + lr);
                             double2 v = __ldcg(p);
                             if (gr >= jn) v.x -= acc[rb][0];
                             if (gr + 1 >= jn) v.y -= acc[rb][1];
@@ -416,13 +538,15 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                     }
                     __syncthreads();
                 }
+                fence_proxy_async();                   // S staging (generic proxy) precedes the next bulk copies
             }
+            TRD_PROF(10);
             team_barrier(bar, bar_target, T);
+            TRD_PROF(11);
         }
-        if (c == 0 && tid == 0) {
-            dvec[n - 1] = __ldcg(A + (size_t)(n - 1) * ld + (n - 1));
-            if (n >= 2) { /* e[n-1], tau[n-1] unused */ }
-        }
+        if (c == 0 && tid == 0) dvec[n - 1] = __ldcg(A + hh_tidx(n - 1, n - 1, NT));
         // the next job's first barrier separates this job's scratch use from the next one's
     }
+    if (prof_on)
+        for (int i = 0; i < 12; ++i) P.prof[i] = prof_acc[i];
 }
