@@ -73,7 +73,7 @@ struct HhDev {           // device views of one chunk
     int64_t* roff_arr; int64_t* voff_arr; int64_t* loff_arr;
 };
 
-#define HH_CTL_INTS 1024       // [0] trd queue, [1] bt queue, [16 .. 16+148) slots, [256 .. 256+148) barrier counters
+#define HH_CTL_INTS 4096       // [0..8) trd level queues, [8] bt queue, [64 + 256 l ..) slots, [2048 + 256 l ..) barriers, [3840..) trace
 
 static int hh_alloc(gsi_ctx* ctx, const HhPlan& pl, const Job* jobs, HhDev& D) {
     Workspace& ws = WS(ctx);
@@ -125,71 +125,99 @@ static int hh_alloc(gsi_ctx* ctx, const HhPlan& pl, const Job* jobs, HhDev& D) {
     return GSI_OK;
 }
 
-// team size of the tridiagonalisation for a class of `count` users whose largest padded size is np
-static int hh_team_size(gsi_ctx* ctx, int np, int count, int forced) {
-    const int sms = ctx->sm_count;
-    if (forced > 0) return std::min(sms, forced);
-    if (np > 4096) return sms;
-    int t = (np > 2048) ? 8 : (np > 1024 ? 2 : 1);
-    while (2 * t <= sms / std::max(count, 1)) t *= 2;      // few users: give each of them more SMs
-    return std::min(sms, t);
-}
+// size class of a user on the tridiagonalisation levels.  Every CTA of a team pays the per-column
+// synchronisation latency, so teams are kept as small as the tail allows: the biggest users start first
+// and everything smaller fills the other SMs behind them.
+static int hh_level_of(int np) { return np > 4096 ? 0 : (np > 2048 ? 1 : (np > 1024 ? 2 : 3)); }
 
 static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_team) {
     Workspace& ws = WS(ctx);
     cudaStream_t st = ctx->stream;
     const int nj = pl.nj;
     int rc;
-    // ---------------- tridiagonalisation: classes of similar size share a launch
+    // ---------------- tridiagonalisation: ONE persistent launch, levels of nested teams (kern_trd.cuh)
     {
+        const int sms = ctx->sm_count;
+        int level_T[4] = {37, 9, 3, 1};
+        if (const char* lt = getenv("GSI_TRD_TEAMS")) sscanf(lt, "%d,%d,%d,%d", &level_T[0], &level_T[1], &level_T[2], &level_T[3]);
+        TrdParams P;
+        memset(&P, 0, sizeof P);
+        P.jobs = D.jobs; P.A = D.A; P.d = D.d; P.e = D.e; P.tau = D.tau;
+        P.nlevels = 0;
+        size_t smem = 0;
         int b = 0;
-        while (b < nj) {
-            const int npb = pl.jobs[b].np;
+        while (b < nj) {                                           // jobs are sorted by n descending
+            const int lv = hh_level_of(pl.jobs[b].np);
             int e = b;
-            auto cls = [](int np) { return np > 4096 ? 3 : (np > 2048 ? 2 : (np > 1024 ? 1 : 0)); };
-            while (e < nj && cls(pl.jobs[e].np) == cls(npb)) ++e;
-            const int T = hh_team_size(ctx, npb, e - b, forced_team);
-            const int teams = std::max(1, std::min(ctx->sm_count / T, e - b));
-            int stages = 4;
-            while (stages > 1 && trd_smem_bytes(npb, stages, T) > 227 * 1024) --stages;
-            const size_t smem = trd_smem_bytes(npb, stages, T);
-            if (smem > 227 * 1024) return gsi_fail(ctx, GSI_ERR_INVALID, "user with n = %d does not fit the tridiagonalisation kernel", pl.jobs[b].n);
-            if ((rc = ws.trd_acol.ensure(ctx, (size_t)teams * npb * 8)) != GSI_OK) return rc;
-            if ((rc = ws.trd_ypart.ensure(ctx, (size_t)teams * T * npb * 8)) != GSI_OK) return rc;
-            if ((rc = ws.trd_part.ensure(ctx, (size_t)teams * T * TRD_PART * 8 + (size_t)teams * 2 * HH_NB * 8)) != GSI_OK) return rc;
-            if ((rc = ws.trd_panels.ensure(ctx, (size_t)2 * teams * npb * HH_NB * 8)) != GSI_OK) return rc;
-            TrdParams P;
-            P.jobs = D.jobs + b; P.njobs = e - b; P.queue = D.ctl; P.A = D.A; P.d = D.d; P.e = D.e; P.tau = D.tau;
-            P.T = T; P.npmax = npb; P.stages = stages; P.own_max = (npb / 64 + T - 1) / T;
-            P.acol = ws.trd_acol.as<double>(); P.ypart = ws.trd_ypart.as<double>(); P.part = ws.trd_part.as<double>();
-            P.tot = P.part + (size_t)teams * T * TRD_PART;
-            P.Vp = ws.trd_panels.as<double>(); P.Wp = P.Vp + (size_t)teams * npb * HH_NB;
-            P.bar = (unsigned*)(D.ctl + 256); P.slot = D.ctl + 16;
-            P.prof = ctx->trace ? (long long*)(D.ctl + 512) : nullptr;
-            GSI_CUDA(ctx, cudaMemsetAsync(D.ctl, 0, HH_CTL_INTS * 4, st));
-            GSI_CUDA(ctx, cudaFuncSetAttribute(trd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            GsiSpan sp(ctx, GSI_T_TRD, 1);
-            void* args[] = {&P};
-            cudaEvent_t ta = nullptr, tb = nullptr;
-            if (ctx->trace) { cudaEventCreate(&ta); cudaEventCreate(&tb); cudaEventRecord(ta, st); }
-            GSI_CUDA(ctx, cudaLaunchCooperativeKernel((void*)trd_kernel, dim3(teams * T), dim3(TRD_THREADS), args, smem, st));
-            sp.end();
-            if (ctx->trace) {
-                cudaEventRecord(tb, st); cudaEventSynchronize(tb);
-                float ms = 0.f; cudaEventElapsedTime(&ms, ta, tb);
-                double n3 = 0; for (int j = b; j < e; ++j) n3 += (double)pl.jobs[j].n * pl.jobs[j].n * pl.jobs[j].n;
-                fprintf(stderr, "[gsi trace] trd: %d users n=%d..%d T=%d teams=%d stages=%d  %.2f ms  (sum n^3 = %.3g, symv bytes %.3g -> %.1f GB/s)\n",
-                        e - b, pl.jobs[b].n, pl.jobs[e - 1].n, T, teams, stages, ms, n3, n3 * 8 / 6, n3 * 8 / 6 / (ms * 1e-3) / 1e9);
-                long long pr[12];
-                cudaMemcpy(pr, D.ctl + 512, sizeof pr, cudaMemcpyDeviceToHost);
-                static const char* nm[12] = {"dots", "bar1", "scal", "symv", "ywr", "bar2", "preC", "rows", "dots+A0", "bar3", "syr2k", "bar4"};
-                long long tot = 0; for (int i = 0; i < 12; ++i) tot += pr[i];
-                fprintf(stderr, "[gsi trace]   CTA0 cycles %%:");
-                for (int i = 0; i < 12; ++i) fprintf(stderr, " %s %.1f", nm[i], 100.0 * pr[i] / std::max<long long>(tot, 1));
-                fprintf(stderr, "  (total %.1f ms @1.965GHz)\n", tot / 1.965e6);
-                cudaEventDestroy(ta); cudaEventDestroy(tb);
-            }
+            while (e < nj && hh_level_of(pl.jobs[e].np) == lv) ++e;
+            TrdLevel& L = P.lv[P.nlevels++];
+            L.T = forced_team > 0 ? std::min(sms, forced_team) : level_T[lv];
+            L.job0 = b; L.njobs = e - b; L.npmax = pl.jobs[b].np;
+            L.own = (L.npmax / 64 + L.T - 1) / L.T;
+            L.stages = TRD_MAX_STAGES;
+            while (L.stages > 1 && trd_smem_bytes(L.npmax, L.stages, L.own) > 227 * 1024) --L.stages;
+            if (trd_smem_bytes(L.npmax, L.stages, L.own) > 227 * 1024)
+                return gsi_fail(ctx, GSI_ERR_INVALID, "user with n = %d does not fit the tridiagonalisation kernel", pl.jobs[b].n);
+            smem = std::max(smem, trd_smem_bytes(L.npmax, L.stages, L.own));
             b = e;
+        }
+        // teams per level (the kernel derives the same nesting), scratch
+        size_t o_acol = 0, o_ypart = 0, o_part = 0, o_pan = 0;
+        int size_prev = sms, teams = 1;
+        bool nested = true;
+        std::vector<size_t> off_acol(P.nlevels), off_ypart(P.nlevels), off_part(P.nlevels), off_pan(P.nlevels);
+        std::vector<int> nteams(P.nlevels);
+        for (int l = 0; l < P.nlevels; ++l) {
+            TrdLevel& L = P.lv[l];
+            if (L.T == 1) teams = sms;
+            else if (nested) { const int nsub = size_prev / L.T; teams *= nsub; size_prev = L.T; }
+            nteams[l] = teams;
+            if (teams > 240) return gsi_fail(ctx, GSI_ERR_INVALID, "internal: too many teams");
+            off_acol[l] = o_acol; off_ypart[l] = o_ypart; off_part[l] = o_part; off_pan[l] = o_pan;
+            o_acol += (size_t)teams * L.npmax;
+            o_ypart += (size_t)teams * L.T * L.npmax;
+            o_part += (size_t)teams * L.T * TRD_PART + (size_t)teams * 2 * HH_NB;
+            o_pan += (size_t)2 * teams * L.npmax * HH_NB;
+        }
+        if ((rc = ws.trd_acol.ensure(ctx, o_acol * 8)) != GSI_OK) return rc;
+        if ((rc = ws.trd_ypart.ensure(ctx, o_ypart * 8)) != GSI_OK) return rc;
+        if ((rc = ws.trd_part.ensure(ctx, o_part * 8)) != GSI_OK) return rc;
+        if ((rc = ws.trd_panels.ensure(ctx, o_pan * 8)) != GSI_OK) return rc;
+        for (int l = 0; l < P.nlevels; ++l) {
+            TrdLevel& L = P.lv[l];
+            L.acol = ws.trd_acol.as<double>() + off_acol[l];
+            L.ypart = ws.trd_ypart.as<double>() + off_ypart[l];
+            L.part = ws.trd_part.as<double>() + off_part[l];
+            L.tot = L.part + (size_t)nteams[l] * L.T * TRD_PART;
+            L.Vp = ws.trd_panels.as<double>() + off_pan[l];
+            L.Wp = L.Vp + (size_t)nteams[l] * L.npmax * HH_NB;
+            L.queue = D.ctl + l; L.slot = D.ctl + 64 + 256 * l; L.bar = (unsigned*)(D.ctl + 2048 + 256 * l);
+        }
+        P.prof = ctx->trace ? (long long*)(D.ctl + 3840) : nullptr;
+        GSI_CUDA(ctx, cudaMemsetAsync(D.ctl, 0, HH_CTL_INTS * 4, st));
+        GSI_CUDA(ctx, cudaFuncSetAttribute(trd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GsiSpan sp(ctx, GSI_T_TRD, 1);
+        void* args[] = {&P};
+        cudaEvent_t ta = nullptr, tb = nullptr;
+        if (ctx->trace) { cudaEventCreate(&ta); cudaEventCreate(&tb); cudaEventRecord(ta, st); }
+        GSI_CUDA(ctx, cudaLaunchCooperativeKernel((void*)trd_kernel, dim3(sms), dim3(TRD_THREADS), args, smem, st));
+        sp.end();
+        if (ctx->trace) {
+            cudaEventRecord(tb, st); cudaEventSynchronize(tb);
+            float ms = 0.f; cudaEventElapsedTime(&ms, ta, tb);
+            double n3 = 0; for (int j = 0; j < nj; ++j) n3 += (double)pl.jobs[j].n * pl.jobs[j].n * pl.jobs[j].n;
+            fprintf(stderr, "[gsi trace] trd: %d users n=%d..%d  %.2f ms  (sum n^3 = %.3g, symv bytes %.3g -> %.1f GB/s); levels:",
+                    nj, pl.jobs[0].n, pl.jobs[nj - 1].n, ms, n3, n3 * 8 / 6, n3 * 8 / 6 / (ms * 1e-3) / 1e9);
+            for (int l = 0; l < P.nlevels; ++l)
+                fprintf(stderr, " [T=%d x%d teams, %d users, np<=%d, %d stages]", P.lv[l].T, nteams[l], P.lv[l].njobs, P.lv[l].npmax, P.lv[l].stages);
+            long long pr[12];
+            cudaMemcpy(pr, D.ctl + 3840, sizeof pr, cudaMemcpyDeviceToHost);
+            static const char* nm[12] = {"dots", "bar1", "scal", "symv", "ywr", "bar2", "preC", "rows", "dots+A0", "bar3", "syr2k", "bar4"};
+            long long tot = 0; for (int i = 0; i < 12; ++i) tot += pr[i];
+            fprintf(stderr, "\n[gsi trace]   CTA0 cycles %%:");
+            for (int i = 0; i < 12; ++i) fprintf(stderr, " %s %.1f", nm[i], 100.0 * pr[i] / std::max<long long>(tot, 1));
+            fprintf(stderr, "  (total %.1f ms @1.965GHz)\n", tot / 1.965e6);
+            cudaEventDestroy(ta); cudaEventDestroy(tb);
         }
     }
     // ---------------- divide & conquer
@@ -231,13 +259,13 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
     // ---------------- back-transformation
     BtParams B;
     B.jobs = D.jobs; B.njobs = nj; B.A = D.A; B.tau = D.tau; B.S = D.S; B.Qa = D.Qa; B.Qb = D.Qb; B.kuser = D.kuser;
-    B.items = D.bt_items; B.nitems = (int)pl.bt_items.size(); B.queue = D.ctl + 1;
+    B.items = D.bt_items; B.nitems = (int)pl.bt_items.size(); B.queue = D.ctl + 8;
     {
         GsiSpan sp(ctx, GSI_T_BT, 2);
         GSI_CUDA(ctx, cudaFuncSetAttribute(bt_formt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_formt_smem_bytes()));
         GSI_CUDA(ctx, cudaFuncSetAttribute(bt_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_smem_bytes()));
         bt_formt_kernel<<<dim3((pl.nmax - 1 + BT_NB - 1) / BT_NB, nj), 256, bt_formt_smem_bytes(), st>>>(B);
-        GSI_CUDA(ctx, cudaMemsetAsync(D.ctl + 1, 0, 4, st));
+        GSI_CUDA(ctx, cudaMemsetAsync(D.ctl + 8, 0, 4, st));
         bt_apply_kernel<<<ctx->sm_count, 256, bt_smem_bytes(), st>>>(B);
         sp.end();
         GSI_CUDA(ctx, cudaGetLastError());
@@ -248,7 +276,7 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
 static BtParams hh_bt_params(const HhPlan& pl, const HhDev& D) {
     BtParams B;
     B.jobs = D.jobs; B.njobs = pl.nj; B.A = D.A; B.tau = D.tau; B.S = D.S; B.Qa = D.Qa; B.Qb = D.Qb; B.kuser = D.kuser;
-    B.items = D.bt_items; B.nitems = (int)pl.bt_items.size(); B.queue = D.ctl + 1;
+    B.items = D.bt_items; B.nitems = (int)pl.bt_items.size(); B.queue = D.ctl + 8;
     return B;
 }
 

@@ -31,6 +31,8 @@
 #define TRD_SYR_LD 68     // k-stride of the syr2k operand panels in shared memory (conflict-free DMMA fragments)
 #define TRD_SYR_KH 32     // the trailing update stages its operands in two k-halves
 #define TRD_SYR_DBL (4 * TRD_SYR_LD * TRD_SYR_KH)
+#define TRD_FIXED_DBL (16 + 4 * 64 + 1152 + 16)     // mbarriers, Wtv/Vtv/Wrow/Vrow, reduction scratch, scalars
+#define TRD_MAX_STAGES 6
 
 // One user of the Householder / divide-and-conquer path
 struct HJob {
@@ -49,14 +51,14 @@ __host__ __device__ __forceinline__ size_t hh_tidx(int r, int c, int NT) {
     return (((size_t)(c >> 6) * NT + (r >> 6)) << 12) + ((c & 63) << 6) + (r & 63);
 }
 
-struct TrdParams {
-    const HJob* jobs;
-    int njobs;
-    int* queue;           // job counter (zeroed before launch)
-    double* A;
-    double* d; double* e; double* tau;      // indexed by r_off
-    int T, npmax, stages;
-    int own_max;          // 64-row blocks a CTA can own: ceil(npmax / 64 / T)
+// One launch walks a few LEVELS: level l works on the users of one size class with teams of T_l CTAs,
+// T_0 > T_1 > ... (the last level usually has T = 1).  The teams of level l+1 are subdivisions of the
+// teams of level l, so a team that finds its level's queue empty splits and moves on at once -- the
+// big users start first on big teams and the small ones fill every SM behind them (no tail per class).
+#define TRD_MAX_LEVELS 6
+struct TrdLevel {
+    int T, job0, njobs, npmax;              // team size, job range [job0, job0 + njobs), largest padded size
+    int stages, own;                        // tile stages that fit beside this level's vectors; 64-row blocks a CTA can own
     double* acol;         // [teams][npmax]
     double* ypart;        // [teams][T][npmax]
     double* part;         // [teams][T][TRD_PART]
@@ -64,13 +66,22 @@ struct TrdParams {
     double* Vp; double* Wp;                 // [teams][npmax*HH_NB], leading dimension = the job's np
     unsigned* bar;        // [teams] monotonic arrival counters (zeroed before launch)
     int* slot;            // [teams] job broadcast
+    int* queue;           // job counter of the level (zeroed before launch)
+};
+struct TrdParams {
+    const HJob* jobs;
+    double* A;
+    double* d; double* e; double* tau;      // indexed by r_off
+    int nlevels;
+    TrdLevel lv[TRD_MAX_LEVELS];
     long long* prof;      // optional [16] cycle counters of CTA 0 (GSI_TRACE), else nullptr
 };
 
-static inline size_t trd_smem_bytes(int npmax, int stages, int T) {
+// shared memory of a level: fixed part, own rows, y and x' vectors, tile stages (the trailing update's
+// operand staging overlays the stages)
+static inline size_t trd_smem_bytes(int npmax, int stages, int own) {
     const size_t region = (size_t)std::max(stages * TRD_STAGE_DBL, TRD_SYR_DBL);
-    const size_t own = (size_t)((npmax / 64 + T - 1) / T) * 64;
-    return (region + 2 * (size_t)npmax + own + 4 * 64 + 1152 + 16) * sizeof(double) + 16 * sizeof(uint64_t) + 128;
+    return (TRD_FIXED_DBL + (size_t)own * 64 + 2 * (size_t)npmax + region) * sizeof(double) + 128;
 }
 
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -125,48 +136,59 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
     long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long prof_t = prof_on ? clock64() : 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int T = P.T, team = blockIdx.x / T, c = blockIdx.x % T;
-    const int npmax = P.npmax, stages = P.stages;
-
-    double* stage_base = (double*)trd_smem;
-    const int region = max(stages * TRD_STAGE_DBL, TRD_SYR_DBL);
-    double* ysm = stage_base + region;             // [npmax]
-    double* xsm = ysm + npmax;                     // [npmax] acol of the step (bulk-copied once per step)
-    double* aown = xsm + npmax;                    // [own_max*64] acol of the rows this CTA owns
-    double* Wtv = aown + P.own_max * 64;           // [64]
+    // fixed part of the carve; the per-level part follows (sizes differ per level)
+    double* sm = (double*)trd_smem;
+    uint64_t* full = (uint64_t*)sm;                // [8] tile stages, [8] = the x vector
+    uint64_t* xbar = full + 8;
+    double* Wtv = sm + 16;                         // [64]
     double* Vtv = Wtv + 64;
     double* Wrow = Vtv + 64;
     double* Vrow = Wrow + 64;
     double* red = Vrow + 64;                       // [1152] two parities of (8 x 64 direct partials + 64 transposed sums)
     double* sc = red + 1152;                       // [16] scalars
-    uint64_t* full = (uint64_t*)(sc + 16);         // [8] tile stages, [8] = the x vector
-    uint64_t* xbar = full + 8;
-    unsigned xphase = 0;
-
-    double* acol = P.acol + (size_t)team * npmax;
-    double* ypart = P.ypart + (size_t)team * T * npmax;
-    double* part = P.part + (size_t)team * T * TRD_PART;
-    double* tot = P.tot + (size_t)team * 2 * HH_NB;
-    double* Vp = P.Vp + (size_t)team * npmax * HH_NB;
-    double* Wp = P.Wp + (size_t)team * npmax * HH_NB;
-    unsigned* bar = P.bar + team;
-    unsigned bar_target = 0;
+    double* lvl_base = sc + 16;
+    unsigned xphase = 0, phbits = 0;               // parity to wait for next, per mbarrier
     int c_st = 0, p_st = 0, pre_issued = 0;        // stage ring: next stage to consume / to fill; tiles requested ahead
-    unsigned c_ph = 0;                             // parity of the consumer's stage
 
     if (tid == 0) {
-        for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < TRD_MAX_STAGES; ++s) mbar_init(&full[s], 1);
         mbar_init(xbar, 1);
         mbar_fence_init();
     }
     __syncthreads();
 
+    int rank = blockIdx.x, team = 0, size_prev = gridDim.x;
+    bool nested = true;                            // still inside the nested team structure
+    for (int lvi = 0; lvi < P.nlevels; ++lvi) {
+    const TrdLevel& LV = P.lv[lvi];
+    const int T = LV.T;
+    if (T == 1) { team = blockIdx.x; rank = 0; }   // every CTA is its own team
+    else {
+        if (!nested) continue;
+        const int nsub = size_prev / T, sub = rank / T;
+        if (sub >= nsub) { nested = false; continue; }     // left over by the subdivision: joins again at T = 1
+        team = team * nsub + sub; rank = rank % T; size_prev = T;
+    }
+    const int c = rank, lnp = LV.npmax, stages = LV.stages;
+    double* aown = lvl_base;                       // [own*64] acol of the rows this CTA owns
+    double* ysm = aown + LV.own * 64;              // [lnp]
+    double* xsm = ysm + lnp;                       // [lnp] acol of the step (bulk-copied once per step)
+    double* stage_base = xsm + lnp;                // 128-byte aligned: every size above is a multiple of 16 doubles
+    c_st = 0; p_st = 0;                            // every stage is drained between levels
+    double* acol = LV.acol + (size_t)team * lnp;
+    double* ypart = LV.ypart + (size_t)team * T * lnp;
+    double* part = LV.part + (size_t)team * T * TRD_PART;
+    double* tot = LV.tot + (size_t)team * 2 * HH_NB;
+    double* Vp = LV.Vp + (size_t)team * lnp * HH_NB;
+    double* Wp = LV.Wp + (size_t)team * lnp * HH_NB;
+    unsigned* bar = LV.bar + team;
+    unsigned bar_target = 0;
     for (;;) {
-        if (c == 0 && tid == 0) P.slot[team] = atomicAdd(P.queue, 1);
+        if (c == 0 && tid == 0) LV.slot[team] = atomicAdd(LV.queue, 1);
         team_barrier(bar, bar_target, T);
-        const int job = __ldcg(P.slot + team);
-        if (job >= P.njobs) break;
-        const HJob jb = P.jobs[job];
+        const int job = __ldcg(LV.slot + team);
+        if (job >= LV.njobs) break;
+        const HJob jb = P.jobs[LV.job0 + job];
         const int n = jb.n, np = jb.np, ld = jb.np, NT = jb.np >> 6;
         double* A = P.A + jb.m_off;
         double* dvec = P.d + jb.r_off;
@@ -228,12 +250,21 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                     }
                 }
                 // ---- totals of the panel dot products, spread over the team
-                for (int el = c + T * warp; el < 2 * jj; el += T * (TRD_THREADS / 32)) {
-                    const int idx = (el < jj) ? 2 + el : 2 + HH_NB + (el - jj);
-                    double s = 0.0;
-                    for (int cc = lane; cc < T; cc += 32) s += __ldcg(part + cc * TRD_PART + idx);
-                    s = warp_sum_d(s);
-                    if (lane == 0) tot[idx - 2] = s;
+                if (T <= 32) {                      // thread per element, T loads each
+                    for (int el = c + T * tid; el < 2 * jj; el += T * TRD_THREADS) {
+                        const int idx = (el < jj) ? 2 + el : 2 + HH_NB + (el - jj);
+                        double s = 0.0;
+                        for (int cc = 0; cc < T; ++cc) s += __ldcg(part + cc * TRD_PART + idx);
+                        tot[idx - 2] = s;
+                    }
+                } else {                            // warp per element, lanes over the team
+                    for (int el = c + T * warp; el < 2 * jj; el += T * (TRD_THREADS / 32)) {
+                        const int idx = (el < jj) ? 2 + el : 2 + HH_NB + (el - jj);
+                        double s = 0.0;
+                        for (int cc = lane; cc < T; cc += 32) s += __ldcg(part + cc * TRD_PART + idx);
+                        s = warp_sum_d(s);
+                        if (lane == 0) tot[idx - 2] = s;
+                    }
                 }
                 __syncthreads();
                 TRD_PROF(2);
@@ -273,10 +304,11 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                     }
                     double xax = 0.0;
                     for (int k = 0; k < mine; ++k) {
-                        mbar_wait(&full[c_st], c_ph);
+                        mbar_wait(&full[c_st], (phbits >> c_st) & 1u);
+                        phbits ^= 1u << c_st;
                         const double* tile = stage_base + (size_t)c_st * TRD_STAGE_DBL;
                         const int st_now = c_st;
-                        if (++c_st == stages) { c_st = 0; c_ph ^= 1; }
+                        if (++c_st == stages) c_st = 0;
                         const int I = wc.I, J = wc.J;
                         const double* xI = xsm + I * HH_TS;
                         const double* xJ = xsm + J * HH_TS;
@@ -361,7 +393,7 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                     }
                     TRD_PROF(3);
                     for (int r = J0 * HH_TS + tid; r < np; r += TRD_THREADS) {
-                        ypart[(size_t)c * npmax + r] = ysm[r];
+                        ypart[(size_t)c * lnp + r] = ysm[r];
                         ysm[r] = 0.0;
                     }
                     xax = cta_sum_d(xax, red);
@@ -382,7 +414,7 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                     double s = 0.0, y = 0.0;
                     for (int cc = lane; cc < T; cc += 32) {
                         s += __ldcg(part + cc * TRD_PART + 1);
-                        y += __ldcg(ypart + (size_t)cc * npmax + j + 1);
+                        y += __ldcg(ypart + (size_t)cc * lnp + j + 1);
                     }
                     s = warp_sum_d(s); y = warp_sum_d(y);
                     if (lane == 0) { sc[4] = s; sc[5] = y; }
@@ -417,7 +449,7 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                     double av = 0.0, pdot = 0.0, adot = 0.0;
                     if (act) {
 #pragma unroll 4
-                        for (int cc = sub; cc < T; cc += G) av += __ldcg(ypart + (size_t)cc * npmax + r);
+                        for (int cc = sub; cc < T; cc += G) av += __ldcg(ypart + (size_t)cc * lnp + r);
 #pragma unroll 4
                         for (int cc = sub; cc < jj; cc += G) {
                             const double vv = __ldcg(Vp + (size_t)cc * ld + r), ww = __ldcg(Wp + (size_t)cc * ld + r);
@@ -547,6 +579,7 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
         if (c == 0 && tid == 0) dvec[n - 1] = __ldcg(A + hh_tidx(n - 1, n - 1, NT));
         // the next job's first barrier separates this job's scratch use from the next one's
     }
+    }   // levels
     if (prof_on)
         for (int i = 0; i < 12; ++i) P.prof[i] = prof_acc[i];
 }
