@@ -125,6 +125,21 @@ static int hh_alloc(gsi_ctx* ctx, const HhPlan& pl, const Job* jobs, HhDev& D) {
     return GSI_OK;
 }
 
+// GSI_TRACE: synchronising stopwatch around a group of launches (diagnostics only)
+struct HhTrace {
+    gsi_ctx* ctx; const char* name; cudaEvent_t a = nullptr, b = nullptr;
+    HhTrace(gsi_ctx* c, const char* n) : ctx(c), name(n) {
+        if (ctx->trace) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, ctx->stream); }
+    }
+    ~HhTrace() {
+        if (!a) return;
+        cudaEventRecord(b, ctx->stream); cudaEventSynchronize(b);
+        float ms = 0.f; cudaEventElapsedTime(&ms, a, b);
+        fprintf(stderr, "[gsi trace] %s %.3f ms\n", name, ms);
+        cudaEventDestroy(a); cudaEventDestroy(b);
+    }
+};
+
 // size class of a user on the tridiagonalisation levels.  Every CTA of a team pays the per-column
 // synchronisation latency, so teams are kept as small as the tail allows: the biggest users start first
 // and everything smaller fills the other SMs behind them.
@@ -139,7 +154,9 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
     {
         const int sms = ctx->sm_count;
         int level_T[4] = {37, 9, 3, 1};
+        int level_nb[4] = {64, 64, 32, 16};
         if (const char* lt = getenv("GSI_TRD_TEAMS")) sscanf(lt, "%d,%d,%d,%d", &level_T[0], &level_T[1], &level_T[2], &level_T[3]);
+        if (const char* lt = getenv("GSI_TRD_NB")) sscanf(lt, "%d,%d,%d,%d", &level_nb[0], &level_nb[1], &level_nb[2], &level_nb[3]);
         TrdParams P;
         memset(&P, 0, sizeof P);
         P.jobs = D.jobs; P.A = D.A; P.d = D.d; P.e = D.e; P.tau = D.tau;
@@ -153,6 +170,7 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
             TrdLevel& L = P.lv[P.nlevels++];
             L.T = forced_team > 0 ? std::min(sms, forced_team) : level_T[lv];
             L.job0 = b; L.njobs = e - b; L.npmax = pl.jobs[b].np;
+            L.nb = std::min(HH_NB, std::max(4, level_nb[lv] & ~3));
             L.own = (L.npmax / 64 + L.T - 1) / L.T;
             L.stages = TRD_MAX_STAGES;
             while (L.stages > 1 && trd_smem_bytes(L.npmax, L.stages, L.own) > 227 * 1024) --L.stages;
@@ -229,6 +247,7 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
     {
         GsiSpan sp(ctx, GSI_T_DC, 1);
         const int nl = (int)pl.leaves.size();
+        HhTrace tr(ctx, "dc_leaf");
         dc_leaf_kernel<<<(nl + 3) / 4, 128, 0, st>>>(D.jobs, D.leaves, nl, D.d, D.e, D.lamA, D.Qa);
         sp.end();
         GSI_CUDA(ctx, cudaGetLastError());
@@ -240,18 +259,24 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
         const int mmax = pl.lvl_mmax[l];
         {
             GsiSpan sp(ctx, GSI_T_DC, 6);
-            dc_deflate_kernel<<<P.nnodes, 256, 0, st>>>(P);
-            dc_secular_kernel<<<dim3((mmax + 127) / 128, P.nnodes), 128, 0, st>>>(P);
-            dc_rank_kernel<<<P.nnodes, 256, 0, st>>>(P);
-            dc_zhat_kernel<<<dim3((mmax + 7) / 8, P.nnodes), 256, 0, st>>>(P);
-            dc_vectors_kernel<<<dim3((mmax + 7) / 8, P.nnodes), 256, 0, st>>>(P);
+            if (ctx->trace) fprintf(stderr, "[gsi trace] dc level %d: %d nodes, mmax %d\n", l, P.nnodes, mmax);
+            { HhTrace tr(ctx, "  deflate"); dc_deflate_kernel<<<P.nnodes, 256, 0, st>>>(P); }
+            {
+                HhTrace tr(ctx, "  secular");       // lanes per root grow with the merge size (few, big merges near the top)
+                if (mmax <= 256) dc_secular_kernel<1><<<dim3((mmax + 127) / 128, P.nnodes), 128, 0, st>>>(P);
+                else if (mmax <= 1024) dc_secular_kernel<8><<<dim3((mmax + 15) / 16, P.nnodes), 128, 0, st>>>(P);
+                else dc_secular_kernel<32><<<dim3((mmax + 3) / 4, P.nnodes), 128, 0, st>>>(P);
+            }
+            { HhTrace tr(ctx, "  rank"); dc_rank_kernel<<<P.nnodes, 256, 0, st>>>(P); }
+            { HhTrace tr(ctx, "  zhat"); dc_zhat_kernel<<<dim3((mmax + 7) / 8, P.nnodes), 256, 0, st>>>(P); }
+            { HhTrace tr(ctx, "  vectors"); dc_vectors_kernel<<<dim3((mmax + 7) / 8, P.nnodes), 256, 0, st>>>(P); }
             dc_plan_kernel<<<1, 1024, 0, st>>>(P, D.tile_off);
             sp.end();
         }
         {
             GsiSpan sp(ctx, GSI_T_DC_GEMM, 2);
-            dc_gemm_kernel<<<2 * ctx->sm_count, 256, gemm_smem, st>>>(P, D.tile_off);
-            dc_copy_kernel<<<dim3((mmax + 7) / 8, P.nnodes), 256, 0, st>>>(P);
+            { HhTrace tr(ctx, "  gemm"); dc_gemm_kernel<<<2 * ctx->sm_count, 256, gemm_smem, st>>>(P, D.tile_off); }
+            { HhTrace tr(ctx, "  copy"); dc_copy_kernel<<<dim3((mmax + 7) / 8, P.nnodes), 256, 0, st>>>(P); }
             sp.end();
         }
         GSI_CUDA(ctx, cudaGetLastError());
@@ -264,9 +289,9 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
         GsiSpan sp(ctx, GSI_T_BT, 2);
         GSI_CUDA(ctx, cudaFuncSetAttribute(bt_formt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_formt_smem_bytes()));
         GSI_CUDA(ctx, cudaFuncSetAttribute(bt_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_smem_bytes()));
-        bt_formt_kernel<<<dim3((pl.nmax - 1 + BT_NB - 1) / BT_NB, nj), 256, bt_formt_smem_bytes(), st>>>(B);
+        { HhTrace tr(ctx, "bt_formt"); bt_formt_kernel<<<dim3((pl.nmax - 1 + BT_NB - 1) / BT_NB, nj), 256, bt_formt_smem_bytes(), st>>>(B); }
         GSI_CUDA(ctx, cudaMemsetAsync(D.ctl + 8, 0, 4, st));
-        bt_apply_kernel<<<ctx->sm_count, 256, bt_smem_bytes(), st>>>(B);
+        { HhTrace tr(ctx, "bt_apply"); bt_apply_kernel<<<ctx->sm_count, 256, bt_smem_bytes(), st>>>(B); }
         sp.end();
         GSI_CUDA(ctx, cudaGetLastError());
     }
@@ -289,18 +314,30 @@ static int run_hh_chunk(gsi_ctx* ctx, const Job* jobs, int nj, const int32_t* d_
     HhDev D;
     int rc;
     if ((rc = hh_alloc(ctx, pl, jobs, D)) != GSI_OK) return rc;
-    {   // Laplacian stage (shared with the block-Jacobi path): sym(lower(L)) without the +1 shift
-        LChunk C;
-        memset(&C, 0, sizeof C);
-        C.nu = nj; C.n = D.n_arr; C.ld = D.ld_arr; C.g_off = D.moff_arr; C.item_off = D.ioff_arr; C.row_off = D.roff_arr;
-        C.G = D.A; C.deg = D.deg; C.scale = D.scale; C.sigmax = D.sigmax; C.tiled = 1;
-        const int nmax = pl.nmax, tiles = (nmax + 31) / 32;
-        GsiSpan sp(ctx, GSI_T_LAP, 5);
-        lap_gather_kernel<<<dim3(tiles * tiles, 1, nj), dim3(32, 8), 0, st>>>(C, ctx->d_w, ctx->w_rows, d_items, tiles);
-        lap_degree_kernel<<<dim3((nmax + 127) / 128, 1, nj), 128, 0, st>>>(C);
-        lap_transform_kernel<<<dim3((nmax + 127) / 128, (nmax + 7) / 8, nj), 128, 0, st>>>(C);
-        lap_sigmin_kernel<<<dim3((nmax + 127) / 128, 1, nj), 128, 0, st>>>(C, out.d_sig_min);
-        lap_symmetrize_kernel<<<dim3(tiles * tiles, 1, nj), dim3(32, 8), 0, st>>>(C, tiles, 0.0);
+    {   // Laplacian stage (shared with the block-Jacobi path): sym(lower(L)) without the +1 shift.  Jobs are
+        // sorted by n descending; launch per group of similar size so that the grids match the matrices.
+        int ngroups = 0;
+        for (int b1 = 0; b1 < nj; ++ngroups) { const int nm = pl.jobs[b1].n; while (b1 < nj && 2 * pl.jobs[b1].n > nm) ++b1; }
+        GsiSpan sp(ctx, GSI_T_LAP, 5 * ngroups);
+        HhTrace tr(ctx, "lap");
+        int b0 = 0;
+        while (b0 < nj) {
+            const int nmax = pl.jobs[b0].n;
+            int e0 = b0;
+            while (e0 < nj && 2 * pl.jobs[e0].n > nmax) ++e0;
+            const int cnt = e0 - b0, tiles = (nmax + 31) / 32;
+            LChunk C;
+            memset(&C, 0, sizeof C);
+            C.nu = cnt; C.n = D.n_arr + b0; C.ld = D.ld_arr + b0; C.g_off = D.moff_arr + b0; C.item_off = D.ioff_arr + b0;
+            C.row_off = D.roff_arr + b0;
+            C.G = D.A; C.deg = D.deg; C.scale = D.scale; C.sigmax = D.sigmax + b0; C.tiled = 1;
+            lap_gather_kernel<<<dim3(tiles * tiles, 1, cnt), dim3(32, 8), 0, st>>>(C, ctx->d_w, ctx->w_rows, d_items, tiles);
+            lap_degree_kernel<<<dim3((nmax + 127) / 128, 1, cnt), 128, 0, st>>>(C);
+            lap_transform_kernel<<<dim3((nmax + 127) / 128, (nmax + 7) / 8, cnt), 128, 0, st>>>(C);
+            lap_sigmin_kernel<<<dim3((nmax + 127) / 128, 1, cnt), 128, 0, st>>>(C, out.d_sig_min);
+            lap_symmetrize_kernel<<<dim3(tiles * tiles, 1, cnt), dim3(32, 8), 0, st>>>(C, tiles, 0.0);
+            b0 = e0;
+        }
         sp.end();
         GSI_CUDA(ctx, cudaGetLastError());
     }
@@ -308,10 +345,17 @@ static int run_hh_chunk(gsi_ctx* ctx, const Job* jobs, int nj, const int32_t* d_
     {
         GsiSpan sp(ctx, GSI_T_BT, 2);
         BtParams B = hh_bt_params(pl, D);
-        emit_sign_kernel<<<dim3((pl.nmax + 7) / 8, nj), 256, 0, st>>>(B, D.sgn);
-        const int tiles = (pl.nmax + 31) / 32;
-        emit_vec_kernel<<<dim3(tiles * tiles, 1, nj), dim3(32, 8), 0, st>>>(B, D.sgn, D.lamA, D.lamB, ws.vec_pad.as<double>(),
-                                                                          ws.lam_pad.as<double>(), tiles);
+        HhTrace tr(ctx, "emit");
+        for (int b0 = 0; b0 < nj;) {                  // groups of similar size: grids that match the matrices
+            const int nmax = pl.jobs[b0].n;
+            int e0 = b0;
+            while (e0 < nj && 2 * pl.jobs[e0].n > nmax) ++e0;
+            const int tiles = (nmax + 31) / 32;
+            emit_sign_kernel<<<dim3((nmax + 7) / 8, e0 - b0), 256, 0, st>>>(B, D.sgn, b0);
+            emit_vec_kernel<<<dim3(tiles * tiles, 1, e0 - b0), dim3(32, 8), 0, st>>>(B, D.sgn, D.lamA, D.lamB, ws.vec_pad.as<double>(),
+                                                                               ws.lam_pad.as<double>(), tiles, b0);
+            b0 = e0;
+        }
         sp.end();
         GSI_CUDA(ctx, cudaGetLastError());
     }

@@ -117,16 +117,24 @@ __global__ void __launch_bounds__(256) bt_formt_kernel(BtParams P) {
     }
 }
 
-// smem: 2 stages x (V chunk 64x64 + Z chunk 64x32) + X (64 x 32)
+// smem: 2 stages x (V chunk 64x64 + Z chunk 64x32), X (64 x 32) and its 4 k-slice partials
 #define BT_STAGE_DBL (BT_NB * BT_LD + BT_CB * BT_LD)
-static inline size_t bt_smem_bytes() { return (size_t)(2 * BT_STAGE_DBL + BT_CB * BT_LD) * sizeof(double); }
+static inline size_t bt_smem_bytes() { return (size_t)(2 * BT_STAGE_DBL + 5 * BT_CB * BT_LD) * sizeof(double); }
 
+// Register blocking (the m8n8k4 fragments are small, so shared-memory loads per DMMA decide the rate):
+//   phase 1  X = V^T Z over a 64-row chunk: warp (ks, vh) takes the 16 rows ks of the chunk and the 32
+//            reflector columns vh -> 4 x 4 tiles, 8 fragment loads per 16 DMMA; the 4 row slices are
+//            summed through shared memory once per panel
+//   phase 2  Z -= VT X: the whole X sits in registers as A fragments (64 doubles per lane), a warp owns
+//            8 rows of every chunk -> 1 fragment load per 4 DMMA
 __global__ void __launch_bounds__(256, 1) bt_apply_kernel(BtParams P) {
     extern __shared__ __align__(16) double bt_smem[];
     __shared__ int item_s;
     double* Xs = bt_smem + 2 * BT_STAGE_DBL;       // [zcol][k] , k = reflector index within the panel
+    double* Xpart = Xs + BT_CB * BT_LD;            // [4][zcol][k]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fk = lane & 3, fr = lane >> 2;
+    const int ks = warp & 3, vh = warp >> 2;
     for (;;) {
         __syncthreads();
         if (tid == 0) item_s = atomicAdd(P.queue, 1);
@@ -163,9 +171,11 @@ __global__ void __launch_bounds__(256, 1) bt_apply_kernel(BtParams P) {
                     cp_async16(Zs + c * BT_LD + r2, Z + (size_t)c * ld + r0 + r2);
                 }
             };
-            double acc[4][2];
+            double acc[4][4][2];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) { acc[a][0] = 0.0; acc[a][1] = 0.0; }
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int z = 0; z < 4; ++z) { acc[a][z][0] = 0.0; acc[a][z][1] = 0.0; }
             __syncthreads();
             load1(0, 0);
             cp_async_commit();
@@ -176,26 +186,43 @@ __global__ void __launch_bounds__(256, 1) bt_apply_kernel(BtParams P) {
                 __syncthreads();
                 const double* Vs = bt_smem + (size_t)(ch & 1) * BT_STAGE_DBL;
                 const double* Zs = Vs + BT_NB * BT_LD;
-                // D[vcol][zcol] += V[k][vcol] * Z[k][zcol];  warp -> vcol block, 4 zcol blocks
-#pragma unroll 4
-                for (int k4 = 0; k4 < 64; k4 += 4) {
-                    const double a = Vs[(8 * warp + fr) * BT_LD + k4 + fk];
+                // D[vcol][zcol] += V[k][vcol] * Z[k][zcol] over my 16 rows of the chunk
 #pragma unroll
-                    for (int zb = 0; zb < 4; ++zb) {
-                        const double bq = Zs[(8 * zb + fr) * BT_LD + k4 + fk];
-                        dmma(acc[zb][0], acc[zb][1], a, bq);
-                    }
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    const int kr = 16 * ks + 4 * s4 + fk;
+                    double af[4], bf[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) af[a] = Vs[(32 * vh + 8 * a + fr) * BT_LD + kr];
+#pragma unroll
+                    for (int z = 0; z < 4; ++z) bf[z] = Zs[(8 * z + fr) * BT_LD + kr];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int z = 0; z < 4; ++z) dmma(acc[a][z][0], acc[a][z][1], af[a], bf[z]);
                 }
                 __syncthreads();
             }
-            // X -> smem as Xs[zcol][vcol]: lane holds D[vcol = 8 warp + fr][zcol = 8 zb + 2 fk + {0,1}]
+            // partial X -> smem [ks][zcol][vcol]: lane holds D[vcol = 32 vh + 8 a + fr][zcol = 8 z + 2 fk + {0,1}]
 #pragma unroll
-            for (int zb = 0; zb < 4; ++zb) {
-                Xs[(8 * zb + 2 * fk) * BT_LD + 8 * warp + fr] = acc[zb][0];
-                Xs[(8 * zb + 2 * fk + 1) * BT_LD + 8 * warp + fr] = acc[zb][1];
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int z = 0; z < 4; ++z) {
+                    double* xp = Xpart + ks * (BT_CB * BT_LD) + (8 * z + 2 * fk) * BT_LD + 32 * vh + 8 * a + fr;
+                    xp[0] = acc[a][z][0];
+                    xp[BT_LD] = acc[a][z][1];
+                }
+            __syncthreads();
+            for (int e = tid; e < BT_CB * BT_NB; e += 256) {
+                const int zc = e >> 6, v = e & 63, o = zc * BT_LD + v;
+                Xs[o] = (Xpart[o] + Xpart[BT_CB * BT_LD + o]) + (Xpart[2 * BT_CB * BT_LD + o] + Xpart[3 * BT_CB * BT_LD + o]);
             }
             __syncthreads();
-            // ---------------- phase 2: Z -= VT X, 64-row chunks; warp -> 8-row block, 4 zcol blocks
+            // ---------------- phase 2: Z -= VT X, 64-row chunks; X as A fragments in registers
+            double xa[4][16];
+#pragma unroll
+            for (int z = 0; z < 4; ++z)
+#pragma unroll
+                for (int k4 = 0; k4 < 16; ++k4) xa[z][k4] = Xs[(8 * z + fr) * BT_LD + 4 * k4 + fk];       // X[k][zcol]
             auto load2 = [&](int ch, int stg) {
                 double* Ts = bt_smem + (size_t)stg * BT_STAGE_DBL;
                 const int r0 = j0 + ch * 64;
@@ -211,31 +238,27 @@ __global__ void __launch_bounds__(256, 1) bt_apply_kernel(BtParams P) {
                 if (ch + 1 < nch) load2(ch + 1, (ch + 1) & 1);
                 cp_async_commit();
                 const int r0 = j0 + ch * 64;
-                // D[zcol][row]: init with Z, subtract the product
                 double d[4][2];
                 double2* zp[4];
 #pragma unroll
-                for (int zb = 0; zb < 4; ++zb) {
-                    zp[zb] = (double2*)(Z + (size_t)(8 * zb + fr) * ld + r0 + 8 * warp + 2 * fk);
-                    d[zb][0] = 0.0; d[zb][1] = 0.0;
+                for (int z = 0; z < 4; ++z) {
+                    zp[z] = (double2*)(Z + (size_t)(8 * z + fr) * ld + r0 + 8 * warp + 2 * fk);
+                    d[z][0] = 0.0; d[z][1] = 0.0;
                 }
                 cp_async_wait<1>();
                 __syncthreads();
                 const double* Ts = bt_smem + (size_t)(ch & 1) * BT_STAGE_DBL;
-#pragma unroll 4
-                for (int k4 = 0; k4 < 64; k4 += 4) {
-                    const double bq = Ts[(k4 + fk) * BT_LD + 8 * warp + fr];        // VT[row][k]
 #pragma unroll
-                    for (int zb = 0; zb < 4; ++zb) {
-                        const double a = Xs[(8 * zb + fr) * BT_LD + k4 + fk];       // X[k][zcol]
-                        dmma(d[zb][0], d[zb][1], a, bq);
-                    }
+                for (int k4 = 0; k4 < 16; ++k4) {
+                    const double bq = Ts[(4 * k4 + fk) * BT_LD + 8 * warp + fr];        // VT[row][k]
+#pragma unroll
+                    for (int z = 0; z < 4; ++z) dmma(d[z][0], d[z][1], xa[z][k4], bq);
                 }
 #pragma unroll
-                for (int zb = 0; zb < 4; ++zb) {
-                    double2 z = *zp[zb];
-                    z.x -= d[zb][0]; z.y -= d[zb][1];
-                    *zp[zb] = z;
+                for (int z = 0; z < 4; ++z) {
+                    double2 zz = *zp[z];
+                    zz.x -= d[z][0]; zz.y -= d[z][1];
+                    *zp[z] = zz;
                 }
                 __syncthreads();
             }
@@ -246,10 +269,10 @@ __global__ void __launch_bounds__(256, 1) bt_apply_kernel(BtParams P) {
 
 // grid (ceil(npmax/8), njobs), block 256: warp per kept column -> sign (largest |component| positive,
 // first on ties), stored as +-1 in sgn[r_off + col]
-__global__ void __launch_bounds__(256) emit_sign_kernel(BtParams P, double* __restrict__ sgn) {
-    const HJob jb = P.jobs[blockIdx.y];
+__global__ void __launch_bounds__(256) emit_sign_kernel(BtParams P, double* __restrict__ sgn, int job0) {
+    const HJob jb = P.jobs[job0 + blockIdx.y];
     const int col = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    const int lim = P.kuser[blockIdx.y];
+    const int lim = P.kuser[job0 + blockIdx.y];
     if (col >= lim || col >= jb.n) return;
     const double* z = ((jb.levels & 1) ? P.Qb : P.Qa) + jb.m_off + (size_t)col * jb.np;
     double best = -1.0;
@@ -270,10 +293,10 @@ __global__ void __launch_bounds__(256) emit_sign_kernel(BtParams P, double* __re
 // grid (tiles_i * tiles_r, 1, njobs), block (32, 8): vec[i*k + r] = sgn[r] * Z[i, r]; lam[r]
 __global__ void emit_vec_kernel(BtParams P, const double* __restrict__ sgn, const double* __restrict__ lamA,
                                 const double* __restrict__ lamB, double* __restrict__ vec_pad,
-                                double* __restrict__ lam_pad, int tiles_r) {
+                                double* __restrict__ lam_pad, int tiles_r, int job0) {
     __shared__ double tile[32][33];
-    const HJob jb = P.jobs[blockIdx.z];
-    const int n = jb.n, k = P.kuser[blockIdx.z];
+    const HJob jb = P.jobs[job0 + blockIdx.z];
+    const int n = jb.n, k = P.kuser[job0 + blockIdx.z];
     const int ti = blockIdx.x / tiles_r, tr = blockIdx.x % tiles_r;
     if (ti * 32 >= n || tr * 32 >= k) return;
     const double* Z = ((jb.levels & 1) ? P.Qb : P.Qa) + jb.m_off;

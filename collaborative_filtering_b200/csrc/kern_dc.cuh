@@ -252,30 +252,34 @@ __global__ void __launch_bounds__(256) dc_deflate_kernel(DcParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// secular equation: grid (ceil(mmax/128), nnodes), block 128, thread per root
+// secular equation: grid (ceil(mmax * LPR / 128), nnodes), block 128.  LPR lanes (1, 8 or 32, adjacent)
+// share a root and split the poles, so that the few big merges near the top of the tree still fill
+// the machine; every sum is reduced in a fixed order.
 // ---------------------------------------------------------------------------------------------
+template <int LPR>
 __global__ void __launch_bounds__(128) dc_secular_kernel(DcParams P) {
+    constexpr int RPC = 128 / LPR;                           // roots per CTA
     const DcNode nd = P.nodes[P.node0 + blockIdx.y];
     const DcState st = P.state[P.node0 + blockIdx.y];
     const int k = st.k;
-    if ((int)blockIdx.x * 128 >= k) return;
+    if ((int)blockIdx.x * RPC >= k) return;
     const HJob jb = P.jobs[nd.job];
     const size_t vb = (size_t)jb.r_off + nd.off;
     const double* dk = P.dk + vb;
     const double* zk = P.zk + vb;
-    const int tid = threadIdx.x, j = blockIdx.x * 128 + tid;
+    const int tid = threadIdx.x, sub = tid % LPR, j = blockIdx.x * RPC + tid / LPR;
     const bool active = j < k;
     const double rho = st.rho, rhoinv = 1.0 / rho;
     __shared__ double sd[128], sz2[128];
     if (k == 1) {
-        if (j == 0) { P.orig[vb] = 0; P.tau[vb] = rho * zk[0] * zk[0]; P.lamk[vb] = dk[0] + rho * zk[0] * zk[0]; }
+        if (j == 0 && sub == 0) { P.orig[vb] = 0; P.tau[vb] = rho * zk[0] * zk[0]; P.lamk[vb] = dk[0] + rho * zk[0] * zk[0]; }
         return;
     }
     const bool last = (j == k - 1);
     const int jc = active ? j : k - 1;
     const double dj = dk[jc];
     // upper end of the root's interval: next pole, or d_k + rho * ||z||^2 (z has unit norm) for the last root
-    const double gap = last || !active ? rho : dk[jc + 1] - dj;
+    const double gap = (last || !active) ? rho : dk[jc + 1] - dj;
 
     // evaluates psi (poles <= jc), phi (poles > jc) and derivatives at lam = origin + tau
     auto evaluate = [&](double origin, double tau, double& psi, double& phi, double& dpsi, double& dphi) {
@@ -285,12 +289,19 @@ __global__ void __launch_bounds__(128) dc_secular_kernel(DcParams P) {
             if (c0 + tid < k) { sd[tid] = dk[c0 + tid]; const double z = zk[c0 + tid]; sz2[tid] = z * z; }
             __syncthreads();
             const int cnt = min(128, k - c0);
-            for (int i = 0; i < cnt; ++i) {
-                const double delta = (sd[i] - origin) - tau;
-                const double t = sz2[i] / delta;
-                const double t2 = t / delta;
+            for (int i = sub; i < cnt; i += LPR) {
+                const double inv = 1.0 / ((sd[i] - origin) - tau);
+                const double t = sz2[i] * inv;
+                const double t2 = t * inv;
                 if (c0 + i <= jc) { psi += t; dpsi += t2; } else { phi += t; dphi += t2; }
             }
+        }
+#pragma unroll
+        for (int o = 1; o < LPR; o <<= 1) {
+            psi += __shfl_xor_sync(0xffffffffu, psi, o);
+            phi += __shfl_xor_sync(0xffffffffu, phi, o);
+            dpsi += __shfl_xor_sync(0xffffffffu, dpsi, o);
+            dphi += __shfl_xor_sync(0xffffffffu, dphi, o);
         }
     };
 
@@ -338,7 +349,7 @@ __global__ void __launch_bounds__(128) dc_secular_kernel(DcParams P) {
         if ((hi - lo) <= 4.0 * DC_EPS * fmax(fabs(lo), fabs(hi))) { done = true; continue; }
         tau = cand;
     }
-    if (active) { P.orig[vb + j] = og; P.tau[vb + j] = tau; P.lamk[vb + j] = origin + tau; }
+    if (active && sub == 0) { P.orig[vb + j] = og; P.tau[vb + j] = tau; P.lamk[vb + j] = origin + tau; }
 }
 
 // ---------------------------------------------------------------------------------------------

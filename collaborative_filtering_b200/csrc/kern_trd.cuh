@@ -59,6 +59,7 @@ __host__ __device__ __forceinline__ size_t hh_tidx(int r, int c, int NT) {
 struct TrdLevel {
     int T, job0, njobs, npmax;              // team size, job range [job0, job0 + njobs), largest padded size
     int stages, own;                        // tile stages that fit beside this level's vectors; 64-row blocks a CTA can own
+    int nb, pad_;                           // panel width of the level (<= HH_NB): small users pay less per column with narrow panels
     double* acol;         // [teams][npmax]
     double* ypart;        // [teams][T][npmax]
     double* part;         // [teams][T][TRD_PART]
@@ -204,8 +205,8 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
             bulk_g2s(tile, A + (((size_t)J * NT + I) << 12), HH_TS * HH_TS * 8, &full[st]);
         };
 
-        for (int j0 = 0; j0 < n - 1; j0 += HH_NB) {
-            const int pw = min(HH_NB, n - 1 - j0);
+        for (int j0 = 0; j0 < n - 1; j0 += LV.nb) {
+            const int pw = min(LV.nb, n - 1 - j0);
             const int JP = j0 >> 6;                                 // the panel's diagonal block
             // first owned slot at or below the panel's diagonal block, number of live owned rows
             const int s0 = (JP > c) ? (JP - c + T - 1) / T : 0;
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                     const int slot = s0 + (rs >> 6), ii = rs & 63, r = (c + slot * T) * 64 + ii;
                     const bool act = valid && r > j;
                     // rows of the panel's diagonal block above the reflector
-                    if (valid && !act && sub == 0 && r >= j0) A[hh_tidx(r, j, NT)] = 0.0;
+                    if (valid && !act && sub == 0) A[hh_tidx(r, j, NT)] = 0.0;      // (live rows start at the diagonal block)
                     double av = 0.0, pdot = 0.0, adot = 0.0;
                     if (act) {
 #pragma unroll 4
