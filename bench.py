@@ -304,34 +304,49 @@ def run_gpu(args, rank, world, local_rank):
             return v["ms"] * (v["launches"] / v["samples"]) if v["samples"] else 0.0
         small = deg[deg <= 160].astype(np.float64)
         large = deg[deg > 160].astype(np.float64)
-        groups = {
-            "bj_gram+bj_inner+bj_update (block Jacobi, n>160)": (["bj_gram", "bj_inner", "bj_update"], 9.0 * (large ** 3).sum()),
-            "trd+dc+dc_gemm+bt (Householder tridiagonalisation + divide&conquer + back-transform, n>160)":
-                (["trd", "dc", "dc_gemm", "bt"], 9.0 * (large ** 3).sum()),
-            "eig_cta (fused gather+Laplacian+Jacobi, n<=160)": (["eig_cta"], 9.0 * (small ** 3).sum()),
-        }
+        n3_large = float((large ** 3).sum())
         kernels = {k: {"ms_per_step": est_ms(k) / args.steps, "launches_per_step": timing[k]["launches"] / args.steps,
                        "avg_launch_us": (1e3 * timing[k]["ms"] / timing[k]["samples"]) if timing[k]["samples"] else None}
                    for k in timing if timing[k]["launches"]}
-        top = max(groups, key=lambda g: sum(est_ms(k) for k in groups[g][0]))
-        names, flop = groups[top]
-        top_ms = sum(est_ms(k) for k in names) / args.steps
-        achieved = flop / (top_ms * 1e-3) / 1e12 if top_ms > 0 else 0.0
-        lap_bytes = float((8.0 * large ** 2 + 12.0 * large).sum())          # 8n^2 (fp64 table) + ids + sig_min
-        lap_ms = est_ms("lap") / args.steps
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
+        # ---- dominant kernel: trd_kernel, ONE persistent launch per step over every user with n > 160.
+        # Algorithmic bytes per user: the symmetric half of the trailing matrix is streamed
+        # once per column, 8 (n-j)^2 / 2 bytes -> (4/3) n^3, plus read+write of it once per 64-column panel for the
+        # rank-128 trailing update -> n^3 / 24:   B_trd(n) = 1.375 n^3 bytes.
+        use_bj = timing["bj_update"]["launches"] > 0
+        trd_ms = est_ms("trd") / max(1, timing["trd"]["launches"])             # average launch duration, live CUDA events
+        trd_bytes = 1.375 * n3_large * args.steps / max(1, timing["trd"]["launches"])   # per launch
+        trd_gbs = trd_bytes / (trd_ms * 1e-3) / 1e9 if trd_ms > 0 else 0.0
+        # ---- the whole eigensolve group against the FP64 peak: 9 n^3 flop per user
+        grp = ["bj_gram", "bj_inner", "bj_update"] if use_bj else ["trd", "dc", "dc_gemm", "bt"]
+        grp_ms = sum(est_ms(k) for k in grp) / args.steps
+        eig_tf = 9.0 * n3_large / (grp_ms * 1e-3) / 1e12 if grp_ms > 0 else 0.0
+        lap_bytes = float((8.0 * large ** 2 + 12.0 * large).sum())          # 8n^2 (fp64 table) + ids + sig_min
+        lap_ms = est_ms("lap") / args.steps
         roofline = {
-            "kernel": top, "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
-            "peak_source": "FP64 FMA peak measured live by gsi_measure_fp64_tflops (MEASURED_PEAKS.json has no FP64 figure); DMMA probe %.1f TF/s" % dmma_peak,
-            "algorithmic_flop_per_launch_group": flop,
-            "executed_vs_algorithmic": "9 n^3 per user is credited (SURVEY.md 8d); the Householder + D&C path executes ~4-5 n^3 "
-                                       "(4/3 n^3 tridiagonalisation, ~1-2 n^3 merges, 2 n^2 k back-transform), block Jacobi ~60 n^3",
+            "kernel": "trd_kernel (blocked Householder tridiagonalisation, persistent team kernel, n > 160)",
+            "bound": "hbm", "achieved": trd_gbs, "peak": hbm_peak, "unit": "GB/s",
+            "frac": trd_gbs / hbm_peak if hbm_peak else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture of this same
+            # workload (profiles/r01b_prof_trd_raw.csv): 1.764 TB + 67.2 GB per launch
+            "traffic": 1.831e12 if (args.shape == "ml-10m" and not use_bj) else None,
+            "peak_source": hbm_src,
+            "algorithmic_bytes_per_launch": trd_bytes, "avg_launch_ms": trd_ms,
+            "algorithmic_bytes_per_unit": "1.375 n^3 per user (4/3 n^3 half-matrix symv stream + n^3/24 trailing update)",
+            "share_of_step": (est_ms("trd") / args.steps) / (ms_total / args.steps) if ms_total > 0 else None,
+            "eigensolve_fp64": {
+                "kernels": "+".join(grp), "bound": "fp64", "achieved": eig_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": eig_tf / fp64_peak if fp64_peak else None, "algorithmic_flop_per_step": 9.0 * n3_large,
+                "peak_source": "FP64 FMA peak measured live by gsi_measure_fp64_tflops (MEASURED_PEAKS.json has no FP64 figure); "
+                               "DMMA m8n8k4 probe %.1f TF/s" % dmma_peak,
+                "executed_vs_algorithmic": "9 n^3 per user is credited (SURVEY.md 8d); Householder + D&C executes ~4-5 n^3 "
+                                           "(4/3 n^3 tridiagonalisation, ~1-2 n^3 merges, 2 n^2 k back-transform)"},
             "secondary": {"kernel": "lap_* (gather+Laplacian+sig_min, n>160)", "bound": "hbm",
                           "achieved": (lap_bytes / (lap_ms * 1e-3) / 1e9) if lap_ms > 0 else None, "peak": hbm_peak,
                           "unit": "GB/s", "frac": (lap_bytes / (lap_ms * 1e-3) / 1e9 / hbm_peak) if lap_ms > 0 else None,
-                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
+                          "peak_source": hbm_src},
         }
         launches = int(sum(v["launches"] for v in timing.values()) // args.steps)
         # ---- CPU baseline on this box's host cores (bounded sample) ----
