@@ -73,7 +73,7 @@ struct HhDev {           // device views of one chunk
     int64_t* roff_arr; int64_t* voff_arr; int64_t* loff_arr;
 };
 
-#define HH_CTL_INTS 4096       // [0..8) trd level queues, [8] bt queue, [64 + 256 l ..) slots, [2048 + 256 l ..) barriers, [3840..) trace
+#define HH_CTL_INTS 4608       // [0..8) trd level queues, [8] bt queue, [64 + 256 l ..) slots, [2048 + 256 l ..) barriers, [3840..) trace
 
 static int hh_alloc(gsi_ctx* ctx, const HhPlan& pl, const Job* jobs, HhDev& D) {
     Workspace& ws = WS(ctx);
@@ -235,6 +235,13 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
             fprintf(stderr, "\n[gsi trace]   CTA0 cycles %%:");
             for (int i = 0; i < 12; ++i) fprintf(stderr, " %s %.1f", nm[i], 100.0 * pr[i] / std::max<long long>(tot, 1));
             fprintf(stderr, "  (total %.1f ms @1.965GHz)\n", tot / 1.965e6);
+            std::vector<long long> fin(16 + sms);
+            cudaMemcpy(fin.data(), D.ctl + 3840, fin.size() * 8, cudaMemcpyDeviceToHost);
+            std::vector<double> ft;
+            for (int i = 0; i < sms; ++i) ft.push_back((fin[16 + i] - fin[15]) * 1e-6);
+            std::sort(ft.begin(), ft.end());
+            fprintf(stderr, "[gsi trace]   CTA finish times (ms): min %.1f  p25 %.1f  median %.1f  p75 %.1f  p90 %.1f  max %.1f\n",
+                    ft[0], ft[sms / 4], ft[sms / 2], ft[3 * sms / 4], ft[(9 * sms) / 10], ft[sms - 1]);
             cudaEventDestroy(ta); cudaEventDestroy(tb);
         }
     }

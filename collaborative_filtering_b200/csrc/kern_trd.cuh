@@ -29,8 +29,8 @@
 #define TRD_PART 136      // doubles per CTA: [0] norm^2, [1] x'Ax', [2..66) W^T acol, [66..130) V^T acol
 #define TRD_STAGE_DBL (HH_TS * HH_TS)
 #define TRD_SYR_LD 68     // k-stride of the syr2k operand panels in shared memory (conflict-free DMMA fragments)
-#define TRD_SYR_KH 32     // the trailing update stages its operands in two k-halves
-#define TRD_SYR_DBL (4 * TRD_SYR_LD * TRD_SYR_KH)
+#define TRD_SYR_KH 16     // the trailing update streams its operands in k-chunks of 16, double buffered (cp.async)
+#define TRD_SYR_DBL (2 * 4 * TRD_SYR_LD * TRD_SYR_KH)
 #define TRD_FIXED_DBL (16 + 4 * 64 + 1152 + 16)     // mbarriers, Wtv/Vtv/Wrow/Vrow, reduction scratch, scalars
 #define TRD_MAX_STAGES 6
 
@@ -134,6 +134,7 @@ struct TileWalk {
 __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
     extern __shared__ __align__(128) unsigned char trd_smem[];
     const bool prof_on = P.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    if (prof_on) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); P.prof[15] = (long long)t; }
     long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long prof_t = prof_on ? clock64() : 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -304,6 +305,38 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                         __syncthreads();
                     }
                     double xax = 0.0;
+                    // A_IJ^T x_I: the column sums are kept per lane across the tiles of one tile column J of the walk and
+                    // reduced over the warp only when J changes (the walk is column-major)
+                    double tacc[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) tacc[q] = 0.0;
+                    int Jacc = -1;
+                    auto flush_tacc = [&](double* rdq) {            // 8 column sums over 32 lanes in 9 shuffles -> rdq[8 warp + q]
+                        const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
+                        double u[4], v2[2], w1;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const double send = h4 ? tacc[q] : tacc[q + 4];
+                            const double keep = h4 ? tacc[q + 4] : tacc[q];
+                            u[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const double send = h3 ? u[q] : u[q + 2];
+                            const double keep = h3 ? u[q + 2] : u[q];
+                            v2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                        }
+                        {
+                            const double send = h2 ? v2[0] : v2[1];
+                            const double keep = h2 ? v2[1] : v2[0];
+                            w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                        }
+                        w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+                        w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+                        if ((lane & 3) == 0) rdq[8 * warp + ((lane >> 2) & 7)] = w1;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) tacc[q] = 0.0;
+                    };
                     for (int k = 0; k < mine; ++k) {
                         mbar_wait(&full[c_st], (phbits >> c_st) & 1u);
                         phbits ^= 1u << c_st;
@@ -332,34 +365,14 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                             dodd.x = fma(a[q + 1].x, xj[q + 1], dodd.x); dodd.y = fma(a[q + 1].y, xj[q + 1], dodd.y);
                         }
                         ((double2*)rd)[warp * 32 + lane] = make_double2(de.x + dodd.x, de.y + dodd.y);
+                        const bool newJ = (Jacc >= 0) && (J != Jacc);   // CTA-uniform
+                        const int Jflush = Jacc;
+                        if (newJ) flush_tacc(rd + 512);
+                        Jacc = J;
                         if (I != J) {
                             const double2 xi = ((const double2*)xI)[lane];
-                            double t[8];
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) t[q] = fma(a[q].x, xi.x, a[q].y * xi.y);
-                            // transpose-reduce: 8 column sums over 32 lanes in 9 shuffles
-                            const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
-                            double u[4], v2[2], w1;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const double send = h4 ? t[q] : t[q + 4];
-                                const double keep = h4 ? t[q + 4] : t[q];
-                                u[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                            }
-#pragma unroll
-                            for (int q = 0; q < 2; ++q) {
-                                const double send = h3 ? u[q] : u[q + 2];
-                                const double keep = h3 ? u[q + 2] : u[q];
-                                v2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                            }
-                            {
-                                const double send = h2 ? v2[0] : v2[1];
-                                const double keep = h2 ? v2[1] : v2[0];
-                                w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                            }
-                            w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
-                            w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
-                            if ((lane & 3) == 0) rd[512 + 8 * warp + ((lane >> 2) & 7)] = w1;
+                            for (int q = 0; q < 8; ++q) tacc[q] = fma(a[q].x, xi.x, fma(a[q].y, xi.y, tacc[q]));
                         }
                         __syncthreads();
                         if (issued < mine) {                        // every warp has the tile in registers: refill the stage
@@ -373,12 +386,18 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                                              ((rd[256 + tid] + rd[320 + tid]) + (rd[384 + tid] + rd[448 + tid]));
                             ysm[I * HH_TS + tid] += y;
                             xax = fma(xI[tid] * y, (I != J) ? 2.0 : 1.0, xax);
-                        } else if (tid < 128 && I != J) {
-                            ysm[J * HH_TS + tid - 64] += rd[512 + tid - 64];
+                        } else if (tid < 128 && newJ) {
+                            ysm[Jflush * HH_TS + tid - 64] += rd[512 + tid - 64];
                         }
                         wc.next();
                     }
-                    __syncthreads();                                // the last tile's sums are in ysm
+                    __syncthreads();                                // the last tile's direct sums are in ysm
+                    if (Jacc >= 0) {                                // the last tile column's transposed sums
+                        flush_tacc(red + 512);
+                        __syncthreads();
+                        if (tid < 64) ysm[Jacc * HH_TS + tid] += red[512 + tid];
+                        __syncthreads();
+                    }
                     // the matrix does not change inside a panel: request the first tiles of the next step now, so
                     // that they stream in while the team synchronises
                     if (jj + 1 < pw) {
@@ -520,29 +539,50 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
             team_barrier(bar, bar_target, T);
             TRD_PROF(9);
             {
-                const int jn = j0 + pw, kpad = (pw + 3) & ~3;
-                double* S = stage_base;
-                TileWalk w;
-                for (w.init(jn >> 6, NT, c, T); w.valid(); w.next()) {
+                const int jn = j0 + pw, kpad = (pw + 3) & ~3, nq = (kpad + TRD_SYR_KH - 1) / TRD_SYR_KH;
+                // operand chunk q of tile (I, J): rows of V_I, W_I, V_J, W_J x 16 panel columns -> S[buf][which][k][68]
+                auto stage_unit = [&](int I, int J, int q, int buf) {
+                    double* dst = stage_base + buf * (4 * TRD_SYR_LD * TRD_SYR_KH);
+                    const int kh = q * TRD_SYR_KH;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const int e = tid + t * TRD_THREADS;            // 4 blocks x 16 k x 32 16-byte chunks
+                        const int which = e >> 9, k = (e >> 5) & 15, r2 = (e & 31) * 2;
+                        const double* src = ((which & 1) ? Wp : Vp) + (size_t)(kh + k) * ld + ((which >> 1) ? J : I) * HH_TS + r2;
+                        cp_async16_zfill(dst + which * (TRD_SYR_LD * TRD_SYR_KH) + k * TRD_SYR_LD + r2, src, kh + k < pw);
+                    }
+                };
+                TileWalk w, wn;
+                w.init(jn >> 6, NT, c, T);
+                wn = w;
+                int buf = 0;
+                if (w.valid()) stage_unit(w.I, w.J, 0, 0);
+                cp_async_commit();
+                const int fk = lane & 3, fr = lane >> 2;
+                for (; w.valid(); w.next()) {
                     const int I = w.I, J = w.J;
+                    wn.next();
+                    const int lc = 8 * warp + fr, gc = J * HH_TS + lc;
+                    double* ctile = A + (((size_t)J * NT + I) << 12) + lc * HH_TS;
+                    double2 cv[8];                                  // the C values of this lane, requested early
+                    if (gc >= jn) {
+#pragma unroll
+                        for (int rb = 0; rb < 8; ++rb) cv[rb] = __ldcg((const double2*)(ctile + 8 * rb + 2 * fk));
+                    }
                     double acc[8][2];
 #pragma unroll
                     for (int rb = 0; rb < 8; ++rb) { acc[rb][0] = 0.0; acc[rb][1] = 0.0; }
-                    const int fk = lane & 3, fr = lane >> 2;
-                    for (int kh = 0; kh < kpad; kh += TRD_SYR_KH) {
-                        const int kc = min(TRD_SYR_KH, kpad - kh);
-#pragma unroll
-                        for (int which = 0; which < 4; ++which) {
-                            const double* srcp = ((which & 1) ? Wp : Vp) + (size_t)kh * ld + ((which >> 1) ? J : I) * HH_TS;
-                            double* dstp = S + which * (TRD_SYR_LD * TRD_SYR_KH);
-                            for (int e = tid; e < 64 * kc; e += TRD_THREADS) {
-                                const int k = e >> 6, r = e & 63;
-                                dstp[k * TRD_SYR_LD + r] = (kh + k < pw) ? __ldcg(srcp + (size_t)k * ld + r) : 0.0;
-                            }
-                        }
+                    for (int q = 0; q < nq; ++q) {
+                        // request the next chunk (of this tile or of my next tile) into the other buffer
+                        if (q + 1 < nq) stage_unit(I, J, q + 1, buf ^ 1);
+                        else if (wn.valid()) stage_unit(wn.I, wn.J, 0, buf ^ 1);
+                        cp_async_commit();
+                        cp_async_wait<1>();
                         __syncthreads();
+                        const double* S = stage_base + buf * (4 * TRD_SYR_LD * TRD_SYR_KH);
                         const double* VIs = S, *WIs = S + TRD_SYR_LD * TRD_SYR_KH, *VJs = S + 2 * TRD_SYR_LD * TRD_SYR_KH,
                                      *WJs = S + 3 * TRD_SYR_LD * TRD_SYR_KH;
+                        const int kc = min(TRD_SYR_KH, kpad - q * TRD_SYR_KH);
                         for (int k0 = 0; k0 < kc; k0 += 4) {
                             const double aW = WJs[(k0 + fk) * TRD_SYR_LD + 8 * warp + fr];
                             const double aV = VJs[(k0 + fk) * TRD_SYR_LD + 8 * warp + fr];
@@ -555,22 +595,20 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                             }
                         }
                         __syncthreads();
+                        buf ^= 1;
                     }
-                    const int lc = 8 * warp + fr, gc = J * HH_TS + lc;
                     if (gc >= jn) {
-                        double* tile = A + (((size_t)J * NT + I) << 12) + lc * HH_TS;
 #pragma unroll
                         for (int rb = 0; rb < 8; ++rb) {
                             const int lr = 8 * rb + 2 * fk, gr = I * HH_TS + lr;
-                            double2* p = (double2*)(tile + lr);
-                            double2 v = __ldcg(p);
+                            double2 v = cv[rb];
                             if (gr >= jn) v.x -= acc[rb][0];
                             if (gr + 1 >= jn) v.y -= acc[rb][1];
-                            *p = v;
+                            *(double2*)(ctile + lr) = v;
                         }
                     }
-                    __syncthreads();
                 }
+                cp_async_wait<0>();
                 fence_proxy_async();                   // S staging (generic proxy) precedes the next bulk copies
             }
             TRD_PROF(10);
@@ -583,4 +621,9 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
     }   // levels
     if (prof_on)
         for (int i = 0; i < 12; ++i) P.prof[i] = prof_acc[i];
+    if (P.prof != nullptr && threadIdx.x == 0) {           // finish time of every CTA (trace only)
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.prof[16 + blockIdx.x] = (long long)t;
+    }
 }
