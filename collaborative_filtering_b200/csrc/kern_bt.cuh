@@ -225,11 +225,17 @@ __global__ void __launch_bounds__(256, 1) bt_apply_kernel(BtParams P) {
                 for (int k4 = 0; k4 < 16; ++k4) xa[z][k4] = Xs[(8 * z + fr) * BT_LD + 4 * k4 + fk];       // X[k][zcol]
             auto load2 = [&](int ch, int stg) {
                 double* Ts = bt_smem + (size_t)stg * BT_STAGE_DBL;
+                double* Zs = Ts + BT_NB * BT_LD;
                 const int r0 = j0 + ch * 64;
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                     const int e = tid + t * 256, c = e >> 5, r2 = (e & 31) * 2;
                     cp_async16_zfill(Ts + c * BT_LD + r2, VT + (size_t)c * ld + r0 + r2, c < b);
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {           // the Z chunk rides along: no exposed global latency in the update
+                    const int e = tid + t * 256, c = e >> 5, r2 = (e & 31) * 2;
+                    cp_async16(Zs + c * BT_LD + r2, Z + (size_t)c * ld + r0 + r2);
                 }
             };
             load2(0, 0);
@@ -248,6 +254,7 @@ __global__ void __launch_bounds__(256, 1) bt_apply_kernel(BtParams P) {
                 cp_async_wait<1>();
                 __syncthreads();
                 const double* Ts = bt_smem + (size_t)(ch & 1) * BT_STAGE_DBL;
+                const double* Zs = Ts + BT_NB * BT_LD;
 #pragma unroll
                 for (int k4 = 0; k4 < 16; ++k4) {
                     const double bq = Ts[(4 * k4 + fk) * BT_LD + 8 * warp + fr];        // VT[row][k]
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__(256, 1) bt_apply_kernel(BtParams P) {
                 }
 #pragma unroll
                 for (int z = 0; z < 4; ++z) {
-                    double2 zz = *zp[z];
+                    double2 zz = *(const double2*)(Zs + (8 * z + fr) * BT_LD + 8 * warp + 2 * fk);
                     zz.x -= d[z][0]; zz.y -= d[z][1];
                     *zp[z] = zz;
                 }
