@@ -302,8 +302,8 @@ def run_gpu(args, rank, world, local_rank):
         def est_ms(name):
             v = timing[name]
             return v["ms"] * (v["launches"] / v["samples"]) if v["samples"] else 0.0
-        small = deg[deg <= 160].astype(np.float64)
-        large = deg[deg > 160].astype(np.float64)
+        small = deg[deg <= ctx.small_max].astype(np.float64)
+        large = deg[deg > ctx.small_max].astype(np.float64)
         n3_large = float((large ** 3).sum())
         kernels = {k: {"ms_per_step": est_ms(k) / args.steps, "launches_per_step": timing[k]["launches"] / args.steps,
                        "avg_launch_us": (1e3 * timing[k]["ms"] / timing[k]["samples"]) if timing[k]["samples"] else None}
@@ -326,7 +326,7 @@ def run_gpu(args, rank, world, local_rank):
         lap_bytes = float((8.0 * large ** 2 + 12.0 * large).sum())          # 8n^2 (fp64 table) + ids + sig_min
         lap_ms = est_ms("lap") / args.steps
         roofline = {
-            "kernel": "trd_kernel (blocked Householder tridiagonalisation, persistent team kernel, n > 160)",
+            "kernel": "trd_kernel (blocked Householder tridiagonalisation, persistent team kernel, n > %d)" % ctx.small_max,
             "bound": "hbm", "achieved": trd_gbs, "peak": hbm_peak, "unit": "GB/s",
             "frac": trd_gbs / hbm_peak if hbm_peak else None,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture of this same
@@ -343,7 +343,7 @@ def run_gpu(args, rank, world, local_rank):
                                "DMMA m8n8k4 probe %.1f TF/s" % dmma_peak,
                 "executed_vs_algorithmic": "9 n^3 per user is credited (SURVEY.md 8d); Householder + D&C executes ~4-5 n^3 "
                                            "(4/3 n^3 tridiagonalisation, ~1-2 n^3 merges, 2 n^2 k back-transform)"},
-            "secondary": {"kernel": "lap_* (gather+Laplacian+sig_min, n>160)", "bound": "hbm",
+            "secondary": {"kernel": "lap_* (gather+Laplacian+sig_min, n>%d)" % ctx.small_max, "bound": "hbm",
                           "achieved": (lap_bytes / (lap_ms * 1e-3) / 1e9) if lap_ms > 0 else None, "peak": hbm_peak,
                           "unit": "GB/s", "frac": (lap_bytes / (lap_ms * 1e-3) / 1e9 / hbm_peak) if lap_ms > 0 else None,
                           "peak_source": hbm_src},

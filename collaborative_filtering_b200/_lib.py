@@ -39,6 +39,7 @@ SYMBOLS = {
     "gsi_version": (ctypes.c_char_p, []),
     "gsi_set_workspace_limit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
     "gsi_sync": (ctypes.c_int, [ctypes.c_void_p]),
+    "gsi_small_max": (ctypes.c_int, [ctypes.c_void_p]),
     "gsi_set_weights_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "gsi_set_weights_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "gsi_set_weights_edges": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,

@@ -97,6 +97,11 @@ class Context:
     def set_workspace_limit(self, nbytes: int):
         self._check(self._lib.gsi_set_workspace_limit(self._h, nbytes))
 
+    @property
+    def small_max(self) -> int:
+        """Largest n handled by the CTA-resident Jacobi kernel (gsi_small_max)."""
+        return int(self._lib.gsi_small_max(self._h))
+
     def sync(self):
         self._check(self._lib.gsi_sync(self._h))
 

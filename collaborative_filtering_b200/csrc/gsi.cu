@@ -146,6 +146,7 @@ extern "C" int gsi_create(gsi_ctx** out, int device, void* stream) {
     ctx->bj_m = (bm && atoi(bm) == 32) ? 32 : 64;
     const char* lp = getenv("GSI_LARGE");          // "bj": one-sided block Jacobi (kept for comparison); default Householder + D&C
     ctx->large_bj = lp && strcmp(lp, "bj") == 0;
+    if (const char* sm = getenv("GSI_SMALL_MAX")) ctx->small_max = std::min(GSI_S_MAX_N, std::max(32, atoi(sm)));
     const char* tr = getenv("GSI_TRACE");
     ctx->trace = tr && atoi(tr) != 0;
     GSI_CUDA(ctx, cudaFuncSetAttribute(bj_inner_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 65 * 8));
@@ -187,6 +188,7 @@ extern "C" int gsi_set_workspace_limit(gsi_ctx* ctx, int64_t bytes) {
     ctx->ws_limit = bytes;
     return GSI_OK;
 }
+extern "C" int gsi_small_max(const gsi_ctx* ctx) { return ctx ? ctx->small_max : GSI_SMALL_DEFAULT; }
 extern "C" int gsi_sync(gsi_ctx* ctx) {
     if (!ctx) return GSI_ERR_INVALID;
     GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -253,7 +255,7 @@ extern "C" int gsi_get_weights(gsi_ctx* ctx, double** d_w, int* rows) {
 
 // ---- planner ----------------------------------------------------------------------------------
 struct Job { int64_t user; int n; int64_t item_off; };
-struct Chunk { bool large; int begin, end; };   // [begin, end) into the sorted job list
+struct Chunk { bool large; int begin, end; bool bj = false; };   // [begin, end) into the sorted job list; bj: block-Jacobi path
 
 static inline int64_t pad_slots(int n) { return (int64_t)n * std::max(n, 2); }
 static inline int ld_of(int n) { return (n + 7) & ~7; }
@@ -269,7 +271,7 @@ static int plan(gsi_ctx* ctx, int64_t nu, const int64_t* off, std::vector<Job>& 
         const int64_t n = off[u + 1] - off[u];
         if (n < 1) return gsi_fail(ctx, GSI_ERR_INVALID, "user %lld has %lld rated movies (need >= 1)", (long long)u, (long long)n);
         if (n > 46000) return gsi_fail(ctx, GSI_ERR_INVALID, "user %lld: n = %lld too large", (long long)u, (long long)n);
-        (n <= GSI_S_MAX_N ? small : large).push_back({u, (int)n, off[u]});
+        (n <= ctx->small_max ? small : large).push_back({u, (int)n, off[u]});
     }
     auto desc = [](const Job& a, const Job& b) { return a.n != b.n ? a.n > b.n : a.user < b.user; };
     std::sort(small.begin(), small.end(), desc);
@@ -277,6 +279,14 @@ static int plan(gsi_ctx* ctx, int64_t nu, const int64_t* off, std::vector<Job>& 
     // large first (longest jobs first), then small
     const int64_t budget = ctx->ws_limit / (int64_t)sizeof(double);
     int b = 0;
+    // users too large for the shared-memory vectors of the tridiagonalisation kernel (n > GSI_HH_MAX_N, e.g. the
+    // heaviest Netflix users) stay on the block-Jacobi path
+    int n_bj_first = (int)large.size();                                         // large[0 .. n_bj_first) -> block Jacobi
+    if (!ctx->large_bj) {
+        n_bj_first = 0;
+        while (n_bj_first < (int)large.size() && large[n_bj_first].n > GSI_HH_MAX_N) ++n_bj_first;   // sorted descending
+    }
+    b = n_bj_first;
     while (b < (int)large.size() && !ctx->large_bj) {
         // Householder path: any mix of sizes, bounded by the workspace (4 np^2 doubles per user)
         int64_t used = 0;
@@ -286,23 +296,24 @@ static int plan(gsi_ctx* ctx, int64_t nu, const int64_t* off, std::vector<Job>& 
             if (e > b && used + need > budget) break;
             used += need; ++e;
         }
-        chunks.push_back({true, b, e});
+        chunks.push_back({true, b, e, false});
         b = e;
     }
-    while (b < (int)large.size()) {
+    b = 0;
+    while (b < n_bj_first) {
         const int nmax = large[b].n;
         const int B = ctx->bj_m / 2, MM = ctx->bj_m * ctx->bj_m;
         const int nb = nb_of(nmax, B), ncols = nb * B;
         int64_t used = 0;
         int e = b;
-        while (e < (int)large.size() && e - b < 60000) {
+        while (e < n_bj_first && e - b < 60000) {
             const int n = large[e].n;
             if (e > b && (double)n < 0.7 * nmax) break;
             const int64_t need = (int64_t)ld_of(n) * ncols + pad_slots(n) + (int64_t)(nb / 2) * MM * (1 + (ld_of(nmax) + GSI_BJ_ROWS - 1) / GSI_BJ_ROWS);
             if (e > b && used + need > budget) break;
             used += need; ++e;
         }
-        chunks.push_back({true, b, e});
+        chunks.push_back({true, b, e, true});
         b = e;
     }
     b = 0;
@@ -314,7 +325,7 @@ static int plan(gsi_ctx* ctx, int64_t nu, const int64_t* off, std::vector<Job>& 
             if (e > b && used + need > budget) break;
             used += need; ++e;
         }
-        chunks.push_back({false, b, e});
+        chunks.push_back({false, b, e, false});
         b = e;
     }
     return GSI_OK;
@@ -564,7 +575,7 @@ extern "C" int gsi_precompute_device(gsi_ctx* ctx, int64_t nu, const int64_t* h_
     if ((rc = plan(ctx, nu, h_offsets, small, large, chunks)) != GSI_OK) return rc;
     RunOut out{d_lam, lam_cap, d_vec, vec_cap, ws.totals.as<int64_t>(), d_k, d_lam_off, d_vec_off, d_sig_min};
     for (const Chunk& c : chunks) {
-        rc = c.large ? (ctx->large_bj ? run_large_chunk : run_hh_chunk)(ctx, large.data() + c.begin, c.end - c.begin, d_items, out)
+        rc = c.large ? (c.bj ? run_large_chunk : run_hh_chunk)(ctx, large.data() + c.begin, c.end - c.begin, d_items, out)
                      : run_small_chunk(ctx, small.data() + c.begin, c.end - c.begin, d_items, out);
         if (rc != GSI_OK) return rc;
     }
@@ -616,7 +627,7 @@ extern "C" int gsi_precompute_stream(gsi_ctx* ctx, int64_t nu, const int64_t* of
         GSI_CUDA(ctx, cudaMemsetAsync(ws.totals.p, 0, 64, ctx->stream));
         RunOut out{ws.stage_lam.as<double>(), lcap, ws.stage_vec.as<double>(), vcap, ws.totals.as<int64_t>(),
                    ws.outk.as<int32_t>(), ws.outlam.as<int64_t>(), ws.outvec.as<int64_t>(), ws.sig.as<double>()};
-        rc = c.large ? (ctx->large_bj ? run_large_chunk : run_hh_chunk)(ctx, jobs, nj, ws.items.as<int32_t>(), out)
+        rc = c.large ? (c.bj ? run_large_chunk : run_hh_chunk)(ctx, jobs, nj, ws.items.as<int32_t>(), out)
                      : run_small_chunk(ctx, jobs, nj, ws.items.as<int32_t>(), out);
         if (rc != GSI_OK) return rc;
         int64_t* h_tot = (int64_t*)(ws.h_small.as<char>() + 16);

@@ -19,8 +19,13 @@
 // CTA-resident solver covers n <= 32 * GSI_S_MAX_EPT
 #define GSI_S_MAX_EPT 5
 #define GSI_S_MAX_N (32 * GSI_S_MAX_EPT)
+// measured crossover (scripts/sweep_degree.py, profiles/r01b_degree_sweep.md): the Householder + D&C path is faster
+// than the CTA-resident Jacobi kernel from n ~ 80 on (2.1x at n = 128)
+#define GSI_SMALL_DEFAULT 80
 
 // block Jacobi (large path): panels of M columns = two blocks of M/2; M is 64 (default) or 32
+// largest n on the Householder path: its tridiagonalisation kernel keeps two np-long vectors in shared memory
+#define GSI_HH_MAX_N 9216
 #define GSI_BJ_ROWS 512  // rows of a panel handled by one CTA of the Gram / update kernels
 
 struct gsi_ctx {
@@ -31,6 +36,7 @@ struct gsi_ctx {
     int sm_count = 148;
     int64_t ws_limit = (int64_t)8 << 30;
     int bj_m = 64;
+    int small_max = GSI_SMALL_DEFAULT;   // users with n <= small_max take the CTA-resident Jacobi kernel (GSI_SMALL_MAX, 32..160)
     bool trace = false;        // GSI_TRACE=1: per-launch timing lines on stderr (synchronising; diagnostics only)
     bool large_bj = false;     // GSI_LARGE=bj: block-Jacobi large path instead of Householder + D&C
     // weights

@@ -270,20 +270,20 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
             { HhTrace tr(ctx, "  deflate"); dc_deflate_kernel<<<P.nnodes, 256, 0, st>>>(P); }
             {
                 HhTrace tr(ctx, "  secular");       // lanes per root grow with the merge size (few, big merges near the top)
-                if (mmax <= 256) dc_secular_kernel<1><<<dim3((mmax + 127) / 128, P.nnodes), 128, 0, st>>>(P);
-                else if (mmax <= 1024) dc_secular_kernel<8><<<dim3((mmax + 15) / 16, P.nnodes), 128, 0, st>>>(P);
-                else dc_secular_kernel<32><<<dim3((mmax + 3) / 4, P.nnodes), 128, 0, st>>>(P);
+                if (mmax <= 256) dc_secular_kernel<1><<<dim3(P.nnodes, (mmax + 127) / 128), 128, 0, st>>>(P);
+                else if (mmax <= 1024) dc_secular_kernel<8><<<dim3(P.nnodes, (mmax + 15) / 16), 128, 0, st>>>(P);
+                else dc_secular_kernel<32><<<dim3(P.nnodes, (mmax + 3) / 4), 128, 0, st>>>(P);
             }
             { HhTrace tr(ctx, "  rank"); dc_rank_kernel<<<P.nnodes, 256, 0, st>>>(P); }
-            { HhTrace tr(ctx, "  zhat"); dc_zhat_kernel<<<dim3((mmax + 7) / 8, P.nnodes), 256, 0, st>>>(P); }
-            { HhTrace tr(ctx, "  vectors"); dc_vectors_kernel<<<dim3((mmax + 7) / 8, P.nnodes), 256, 0, st>>>(P); }
+            { HhTrace tr(ctx, "  zhat"); dc_zhat_kernel<<<dim3(P.nnodes, (mmax + 7) / 8), 256, 0, st>>>(P); }
+            { HhTrace tr(ctx, "  vectors"); dc_vectors_kernel<<<dim3(P.nnodes, (mmax + 7) / 8), 256, 0, st>>>(P); }
             dc_plan_kernel<<<1, 1024, 0, st>>>(P, D.tile_off);
             sp.end();
         }
         {
             GsiSpan sp(ctx, GSI_T_DC_GEMM, 2);
             { HhTrace tr(ctx, "  gemm"); dc_gemm_kernel<<<2 * ctx->sm_count, 256, gemm_smem, st>>>(P, D.tile_off); }
-            { HhTrace tr(ctx, "  copy"); dc_copy_kernel<<<dim3((mmax + 7) / 8, P.nnodes), 256, 0, st>>>(P); }
+            { HhTrace tr(ctx, "  copy"); dc_copy_kernel<<<dim3(P.nnodes, (mmax + 7) / 8), 256, 0, st>>>(P); }
             sp.end();
         }
         GSI_CUDA(ctx, cudaGetLastError());

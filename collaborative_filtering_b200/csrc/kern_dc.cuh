@@ -252,22 +252,22 @@ __global__ void __launch_bounds__(256) dc_deflate_kernel(DcParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// secular equation: grid (ceil(mmax * LPR / 128), nnodes), block 128.  LPR lanes (1, 8 or 32, adjacent)
+// secular equation: grid (nnodes, ceil(mmax * LPR / 128)), block 128.  LPR lanes (1, 8 or 32, adjacent)
 // share a root and split the poles, so that the few big merges near the top of the tree still fill
 // the machine; every sum is reduced in a fixed order.
 // ---------------------------------------------------------------------------------------------
 template <int LPR>
 __global__ void __launch_bounds__(128) dc_secular_kernel(DcParams P) {
     constexpr int RPC = 128 / LPR;                           // roots per CTA
-    const DcNode nd = P.nodes[P.node0 + blockIdx.y];
-    const DcState st = P.state[P.node0 + blockIdx.y];
+    const DcNode nd = P.nodes[P.node0 + blockIdx.x];
+    const DcState st = P.state[P.node0 + blockIdx.x];
     const int k = st.k;
-    if ((int)blockIdx.x * RPC >= k) return;
+    if ((int)blockIdx.y * RPC >= k) return;
     const HJob jb = P.jobs[nd.job];
     const size_t vb = (size_t)jb.r_off + nd.off;
     const double* dk = P.dk + vb;
     const double* zk = P.zk + vb;
-    const int tid = threadIdx.x, sub = tid % LPR, j = blockIdx.x * RPC + tid / LPR;
+    const int tid = threadIdx.x, sub = tid % LPR, j = blockIdx.y * RPC + tid / LPR;
     const bool active = j < k;
     const double rho = st.rho, rhoinv = 1.0 / rho;
     __shared__ double sd[128], sz2[128];
@@ -403,13 +403,13 @@ __global__ void __launch_bounds__(256) dc_rank_kernel(DcParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Loewner z-hat: grid (ceil(mmax/8), nnodes), block 256: warp per pole i
+// Loewner z-hat: grid (nnodes, ceil(mmax/8)), block 256: warp per pole i
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dc_zhat_kernel(DcParams P) {
-    const DcNode nd = P.nodes[P.node0 + blockIdx.y];
-    const DcState st = P.state[P.node0 + blockIdx.y];
+    const DcNode nd = P.nodes[P.node0 + blockIdx.x];
+    const DcState st = P.state[P.node0 + blockIdx.x];
     const int k = st.k;
-    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int i = blockIdx.y * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= k) return;
     const HJob jb = P.jobs[nd.job];
     const size_t vb = (size_t)jb.r_off + nd.off;
@@ -428,13 +428,13 @@ __global__ void __launch_bounds__(256) dc_zhat_kernel(DcParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// S[g(i), j] = zhat_i / (d_i - lam_j) / norm: grid (ceil(mmax/8), nnodes), block 256: warp per root j
+// S[g(i), j] = zhat_i / (d_i - lam_j) / norm: grid (nnodes, ceil(mmax/8)), block 256: warp per root j
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dc_vectors_kernel(DcParams P) {
-    const DcNode nd = P.nodes[P.node0 + blockIdx.y];
-    const DcState st = P.state[P.node0 + blockIdx.y];
+    const DcNode nd = P.nodes[P.node0 + blockIdx.x];
+    const DcState st = P.state[P.node0 + blockIdx.x];
     const int k = st.k;
-    const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int j = blockIdx.y * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (j >= st.kneed) return;
     const HJob jb = P.jobs[nd.job];
     const size_t vb = (size_t)jb.r_off + nd.off;
@@ -455,13 +455,13 @@ __global__ void __launch_bounds__(256) dc_vectors_kernel(DcParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// deflated columns: grid (ceil(mmax/8), nnodes), block 256: warp per deflated column
+// deflated columns: grid (nnodes, ceil(mmax/8)), block 256: warp per deflated column
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dc_copy_kernel(DcParams P) {
-    const DcNode nd = P.nodes[P.node0 + blockIdx.y];
-    const DcState st = P.state[P.node0 + blockIdx.y];
+    const DcNode nd = P.nodes[P.node0 + blockIdx.x];
+    const DcState st = P.state[P.node0 + blockIdx.x];
     const int m = nd.n1 + nd.n2, ndf = m - st.k;
-    const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int t = blockIdx.y * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (t >= ndf) return;
     const HJob jb = P.jobs[nd.job];
     const size_t vb = (size_t)jb.r_off + nd.off;

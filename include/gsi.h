@@ -46,6 +46,9 @@ const char* gsi_last_error(const gsi_ctx* ctx);
 const char* gsi_version(void);
 /* Device workspace budget in bytes for one chunk of users (default 8 GiB). */
 int gsi_set_workspace_limit(gsi_ctx* ctx, int64_t bytes);
+/* Largest n that takes the CTA-resident (shared-memory Jacobi) kernel; larger users take the Householder /
+ * divide-and-conquer path.  Default 80 (measured crossover), GSI_SMALL_MAX=32..160 overrides it. */
+int gsi_small_max(const gsi_ctx* ctx);
 /* Synchronise the context's stream. */
 int gsi_sync(gsi_ctx* ctx);
 
