@@ -181,6 +181,40 @@ def run_reference(args, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------
+# auxiliary: predictions/s of the local_calc_precomp stage on a bounded sample (second half of
+# BASELINE.json's metric string).  ML-100K shape, item graph built by the knn2 stage itself (cosine
+# weights), users with n <= 256, one prediction per (user, rated movie) pair.
+# ---------------------------------------------------------------------------------------------
+def predict_sample(local_rank, nmax=256):
+    from collaborative_filtering_b200.api import Context
+    r = D.make_ratings("ml-100k")
+    c2 = Context(local_rank)
+    try:
+        c2.knn_build(r.offsets, r.items, r.ratings, r.n_items + 1, install_weights=True)
+        deg = np.diff(r.offsets)
+        sel = np.nonzero(deg <= nmax)[0]
+        _, s_off, s_items, s_rat = D.subset(r, sel)
+        recs = c2.precompute(s_off, s_items)
+        c2.predict(recs, s_rat.astype(np.float64))                       # warm-up
+        c2.timing_enable(True)
+        c2.timing_reset()
+        t0 = time.perf_counter()
+        out = c2.predict(recs, s_rat.astype(np.float64))
+        wall = time.perf_counter() - t0
+        tm = c2.timing()["predict"]
+        npairs = int(s_off[-1])
+        ok = out["status"] == 0
+        return {"value": npairs / (tm["ms"] * 1e-3), "unit": "predictions/s", "e2e_value": npairs / wall,
+                "pairs": npairs, "well_posed_fraction": float(ok.mean()), "kernel_ms": tm["ms"], "launches": tm["launches"],
+                "rmse_well_posed": float(np.sqrt(np.mean(out["err"][ok]))) if ok.any() else None,
+                "sample": "ml-100k shape, knn2-built item graph, %d users with n <= %d, every (user, rated movie) pair; "
+                          "value = kernel time (CUDA events), e2e_value = gsi_predict_host wall time with host buffers"
+                          % (len(sel), nmax)}
+    finally:
+        c2.close()
+
+
+# ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 
@@ -355,6 +389,9 @@ def run_gpu(args, rank, world, local_rank):
             w_host = d_w.cpu().numpy()
             rate, desc, cores = cpu_reference_rate(w_host, offsets, items, budget_s=args.cpu_budget)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        predict_aux = None
+        if not args.no_predict:
+            predict_aux = predict_sample(local_rank)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -370,6 +407,7 @@ def run_gpu(args, rank, world, local_rank):
             "roofline": roofline,
             "kernels": kernels,
             "cpu_baseline": cpu,
+            "predict": predict_aux,
         }
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -387,6 +425,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-predict", action="store_true", help="skip the auxiliary predictions/s sample")
     ap.add_argument("--workspace-gb", type=int, default=64)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(256) predict_kernel(PredParams P) {
     double pred;
     if (kk == 0) { status = GSI_PRED_EMPTY; pred = __longlong_as_double(0x7ff8000000000000LL); }
     else if (c == 0) { pred = mean; }
-    else {
-        if (kk < c) status = GSI_PRED_UNDERDETERMINED;
+    else if (kk < c) { status = GSI_PRED_UNDERDETERMINED; pred = mean; }     // rank(M) <= kk < c: singular by construction,
+    else {                                                                   // the stated rule value without forming M
         // ---- Gram M = A^T A (lower), rhs = A^T y ----
         for (int e = tid; e < c * c; e += T) M[e] = 0.0;
         for (int a = tid; a < c; a += T) rhs[a] = 0.0;
