@@ -368,14 +368,29 @@ static int upload_meta(gsi_ctx* ctx, MetaBuilder& mb, char** d_base) {
     return GSI_OK;
 }
 
-static int finish_chunk(gsi_ctx* ctx, OutJobs J, const RunOut& out, int64_t max_nk) {
+static int finish_chunk(gsi_ctx* ctx, OutJobs J, const RunOut& out, int64_t max_nk, const int32_t* h_n = nullptr) {
     Workspace& ws = WS(ctx);
     GsiSpan sp(ctx, GSI_T_COMPACT, 2);
     out_scan_kernel<<<1, 1024, 0, ctx->stream>>>(J, out.d_totals, out.lam_cap, out.vec_cap, out.d_k, out.d_lam_off, out.d_vec_off);
     GSI_CUDA(ctx, cudaGetLastError());
-    const unsigned slices = (unsigned)std::max<int64_t>(1, (max_nk + GSI_COMPACT_SLICE - 1) / GSI_COMPACT_SLICE);
-    out_compact_kernel<<<dim3(J.nj, slices), 256, 0, ctx->stream>>>(J, ws.vec_pad.as<double>(), ws.lam_pad.as<double>(), out.d_vec, out.d_lam, out.lam_cap, out.vec_cap);
-    GSI_CUDA(ctx, cudaGetLastError());
+    // jobs are sorted by n descending: one launch per group of similar size (h_n), so that the slice grid matches
+    int b = 0;
+    while (b < J.nj) {
+        int e = J.nj;
+        int64_t nk = max_nk;
+        if (h_n) {
+            e = b;
+            while (e < J.nj && 2 * h_n[e] > h_n[b]) ++e;
+            nk = (int64_t)h_n[b] * std::max(h_n[b], 2);
+        }
+        OutJobs G = J;
+        G.nj = e - b; G.n = J.n + b; G.k = J.k + b; G.user = J.user + b; G.vec_pad = J.vec_pad + b; G.lam_pad = J.lam_pad + b;
+        G.vec_dst = J.vec_dst + b; G.lam_dst = J.lam_dst + b;
+        const unsigned slices = (unsigned)std::max<int64_t>(1, (nk + GSI_COMPACT_SLICE - 1) / GSI_COMPACT_SLICE);
+        out_compact_kernel<<<dim3(G.nj, slices), 256, 0, ctx->stream>>>(G, ws.vec_pad.as<double>(), ws.lam_pad.as<double>(), out.d_vec, out.d_lam, out.lam_cap, out.vec_cap);
+        GSI_CUDA(ctx, cudaGetLastError());
+        b = e;
+    }
     sp.end();
     return GSI_OK;
 }

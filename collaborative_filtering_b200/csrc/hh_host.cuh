@@ -153,7 +153,7 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
     // ---------------- tridiagonalisation: ONE persistent launch, levels of nested teams (kern_trd.cuh)
     {
         const int sms = ctx->sm_count;
-        int level_T[4] = {37, 9, 3, 1};
+        int level_T[4] = {37, 6, 2, 1};
         int level_nb[4] = {64, 64, 32, 16};
         if (const char* lt = getenv("GSI_TRD_TEAMS")) sscanf(lt, "%d,%d,%d,%d", &level_T[0], &level_T[1], &level_T[2], &level_T[3]);
         if (const char* lt = getenv("GSI_TRD_NB")) sscanf(lt, "%d,%d,%d,%d", &level_nb[0], &level_nb[1], &level_nb[2], &level_nb[3]);
@@ -369,7 +369,9 @@ static int run_hh_chunk(gsi_ctx* ctx, const Job* jobs, int nj, const int32_t* d_
     OutJobs J;
     J.nj = nj; J.n = D.n_arr; J.k = D.kuser; J.user = D.user; J.vec_pad = D.voff_arr; J.lam_pad = D.loff_arr;
     J.vec_dst = D.vec_dst; J.lam_dst = D.lam_dst;
-    return finish_chunk(ctx, J, out, pl.max_nk);
+    std::vector<int32_t> h_n(nj);
+    for (int j = 0; j < nj; ++j) h_n[j] = pl.jobs[j].n;
+    return finish_chunk(ctx, J, out, pl.max_nk, h_n.data());
 }
 
 // ---- stage-wise test hook ---------------------------------------------------------------------------

@@ -117,9 +117,11 @@ __global__ void __launch_bounds__(256) bt_formt_kernel(BtParams P) {
     }
 }
 
-// smem: 2 stages x (V chunk 64x64 + Z chunk 64x32), X (64 x 32) and its 4 k-slice partials
+// smem: 3 stages x (V chunk 64x64 + Z chunk 64x32) and X (64 x 32); the 4 k-slice partials of X overlay the
+// (drained) stages between the two phases
 #define BT_STAGE_DBL (BT_NB * BT_LD + BT_CB * BT_LD)
-static inline size_t bt_smem_bytes() { return (size_t)(2 * BT_STAGE_DBL + 5 * BT_CB * BT_LD) * sizeof(double); }
+#define BT_STAGES 3
+static inline size_t bt_smem_bytes() { return (size_t)(BT_STAGES * BT_STAGE_DBL + BT_CB * BT_LD) * sizeof(double); }
 
 // Register blocking (the m8n8k4 fragments are small, so shared-memory loads per DMMA decide the rate):
 //   phase 1  X = V^T Z over a 64-row chunk: warp (ks, vh) takes the 16 rows ks of the chunk and the 32
@@ -130,8 +132,8 @@ static inline size_t bt_smem_bytes() { return (size_t)(2 * BT_STAGE_DBL + 5 * BT
 __global__ void __launch_bounds__(256, 1) bt_apply_kernel(BtParams P) {
     extern __shared__ __align__(16) double bt_smem[];
     __shared__ int item_s;
-    double* Xs = bt_smem + 2 * BT_STAGE_DBL;       // [zcol][k] , k = reflector index within the panel
-    double* Xpart = Xs + BT_CB * BT_LD;            // [4][zcol][k]
+    double* Xs = bt_smem + BT_STAGES * BT_STAGE_DBL;   // [zcol][k] , k = reflector index within the panel
+    double* Xpart = bt_smem;                           // [4][zcol][k], overlays the stages (4 * 32 * 68 <= 2 stages)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fk = lane & 3, fr = lane >> 2;
     const int ks = warp & 3, vh = warp >> 2;
@@ -179,12 +181,14 @@ __global__ void __launch_bounds__(256, 1) bt_apply_kernel(BtParams P) {
             __syncthreads();
             load1(0, 0);
             cp_async_commit();
+            if (nch > 1) load1(1, 1);
+            cp_async_commit();
             for (int ch = 0; ch < nch; ++ch) {
-                if (ch + 1 < nch) load1(ch + 1, (ch + 1) & 1);
-                cp_async_commit();
                 cp_async_wait<1>();
-                __syncthreads();
-                const double* Vs = bt_smem + (size_t)(ch & 1) * BT_STAGE_DBL;
+                __syncthreads();                        // chunk ch has landed; everyone is done with chunk ch - 1
+                if (ch + 2 < nch) load1(ch + 2, (ch + 2) % BT_STAGES);
+                cp_async_commit();
+                const double* Vs = bt_smem + (size_t)(ch % BT_STAGES) * BT_STAGE_DBL;
                 const double* Zs = Vs + BT_NB * BT_LD;
                 // D[vcol][zcol] += V[k][vcol] * Z[k][zcol] over my 16 rows of the chunk
 #pragma unroll
@@ -200,8 +204,9 @@ __global__ void __launch_bounds__(256, 1) bt_apply_kernel(BtParams P) {
 #pragma unroll
                         for (int z = 0; z < 4; ++z) dmma(acc[a][z][0], acc[a][z][1], af[a], bf[z]);
                 }
-                __syncthreads();
             }
+            cp_async_wait<0>();
+            __syncthreads();                            // the stages are drained: the partials may overlay them
             // partial X -> smem [ks][zcol][vcol]: lane holds D[vcol = 32 vh + 8 a + fr][zcol = 8 z + 2 fk + {0,1}]
 #pragma unroll
             for (int a = 0; a < 4; ++a)
@@ -240,20 +245,18 @@ __global__ void __launch_bounds__(256, 1) bt_apply_kernel(BtParams P) {
             };
             load2(0, 0);
             cp_async_commit();
+            if (nch > 1) load2(1, 1);
+            cp_async_commit();
             for (int ch = 0; ch < nch; ++ch) {
-                if (ch + 1 < nch) load2(ch + 1, (ch + 1) & 1);
+                cp_async_wait<1>();
+                __syncthreads();
+                if (ch + 2 < nch) load2(ch + 2, (ch + 2) % BT_STAGES);
                 cp_async_commit();
                 const int r0 = j0 + ch * 64;
                 double d[4][2];
-                double2* zp[4];
 #pragma unroll
-                for (int z = 0; z < 4; ++z) {
-                    zp[z] = (double2*)(Z + (size_t)(8 * z + fr) * ld + r0 + 8 * warp + 2 * fk);
-                    d[z][0] = 0.0; d[z][1] = 0.0;
-                }
-                cp_async_wait<1>();
-                __syncthreads();
-                const double* Ts = bt_smem + (size_t)(ch & 1) * BT_STAGE_DBL;
+                for (int z = 0; z < 4; ++z) { d[z][0] = 0.0; d[z][1] = 0.0; }
+                const double* Ts = bt_smem + (size_t)(ch % BT_STAGES) * BT_STAGE_DBL;
                 const double* Zs = Ts + BT_NB * BT_LD;
 #pragma unroll
                 for (int k4 = 0; k4 < 16; ++k4) {
@@ -265,9 +268,8 @@ __global__ void __launch_bounds__(256, 1) bt_apply_kernel(BtParams P) {
                 for (int z = 0; z < 4; ++z) {
                     double2 zz = *(const double2*)(Zs + (8 * z + fr) * BT_LD + 8 * warp + 2 * fk);
                     zz.x -= d[z][0]; zz.y -= d[z][1];
-                    *zp[z] = zz;
+                    *(double2*)(Z + (size_t)(8 * z + fr) * ld + r0 + 8 * warp + 2 * fk) = zz;
                 }
-                __syncthreads();
             }
             cp_async_wait<0>();
         }
