@@ -151,3 +151,67 @@ def test_large_path_vs_oracle(ctx):
     ctx.set_weights(w)
     recs = ctx.precompute(offsets, items)
     check_records(recs, w, tag="large")
+
+
+def _fresh_context(env):
+    """A context created under temporary environment settings (read by gsi_create)."""
+    from collaborative_filtering_b200.api import Context
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return Context(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_paths_agree_across_the_crossover(golden_dir):
+    """Users with 81 <= n <= 160 can take either eigensolver (GSI_SMALL_MAX moves the crossover): CTA-resident Jacobi
+    and Householder + divide & conquer must produce the same records (k exact, eigenvalues 1e-10, kept subspace 1e-8)."""
+    from collaborative_filtering_b200 import datasets as D
+    from tests.parity import check_records
+    r = D.make_ratings("ml-100k")
+    deg = np.diff(r.offsets)
+    sel = np.nonzero((deg > 80) & (deg <= 160))[0][:40]
+    assert len(sel) >= 20
+    _, off, items, _ = D.subset(r, sel)
+    w = D.make_weights(r.n_items)
+    recs = {}
+    for name, env in (("jacobi", {"GSI_SMALL_MAX": "160"}), ("householder", {"GSI_SMALL_MAX": "80"})):
+        c = _fresh_context(env)
+        try:
+            assert c.small_max == int(env["GSI_SMALL_MAX"])
+            c.set_weights(w)
+            recs[name] = c.precompute(off, items)
+        finally:
+            c.close()
+    a, b = recs["jacobi"], recs["householder"]
+    assert np.array_equal(a.sig_min, b.sig_min) and np.array_equal(a.k, b.k)
+    for u in range(len(sel)):
+        assert np.abs(a.lam_of(u) - b.lam_of(u)).max() <= 1e-10
+        pa, pb = a.vec_of(u) @ a.vec_of(u).T, b.vec_of(u) @ b.vec_of(u).T
+        assert np.abs(pa - pb).max() <= 1e-8
+    check_records(b, w, users=range(0, len(sel), 4), tag="householder 81..160")
+
+
+def test_small_workspace_splits_into_chunks(ctx):
+    """A 64 MiB workspace forces the Householder path through several chunks; the records must not depend on it."""
+    from collaborative_filtering_b200 import datasets as D
+    r = D.make_ratings("ml-100k")
+    deg = np.diff(r.offsets)
+    sel = np.nonzero((deg > 200) & (deg <= 420))[0][:24]
+    _, off, items, _ = D.subset(r, sel)
+    w = D.make_weights(r.n_items)
+    ctx.set_weights(w)
+    ctx.set_workspace_limit(8 << 30)
+    one = ctx.precompute(off, items)
+    ctx.set_workspace_limit(64 << 20)
+    many = ctx.precompute(off, items)
+    ctx.set_workspace_limit(8 << 30)
+    assert np.array_equal(one.k, many.k) and np.array_equal(one.sig_min, many.sig_min)
+    for u in range(len(sel)):
+        assert np.array_equal(one.lam_of(u), many.lam_of(u))          # fixed reduction orders: bit-identical
+        assert np.array_equal(one.vec_of(u), many.vec_of(u))
