@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../../include/gsi.h"
+#include "fast_fmt.hpp"
 
 namespace gsihost {
 
@@ -70,8 +71,8 @@ struct LineTok {
     bool next_double(double& v) {
         skip();
         if (p >= end) return false;
-        char* q; v = strtod(p, &q);
-        if (q == p) return false;
+        const char* q;
+        if (!parse_double(p, end, v, q)) return false;      // == strtod, fast path for short decimal tokens
         p = q; return true;
     }
 };
@@ -162,10 +163,23 @@ inline void load_movie_ratings(const std::string& prefix, std::map<unsigned, std
     }
 }
 
+// "<value> " exactly as the reference's `strm << value << " "` prints it (default ostream format == %g)
 inline void append_g(std::string& s, double v) {
     char buf[40];
-    int n = snprintf(buf, sizeof buf, "%g ", v);
+    int n = format_g6(buf, v);
+    buf[n++] = ' ';
     s.append(buf, n);
+}
+inline void append_int(std::string& s, long long v) {
+    char buf[24];
+    char* e = buf + sizeof buf;
+    char* p = e;
+    const bool neg = v < 0;
+    unsigned long long u = neg ? 0ULL - (unsigned long long)v : (unsigned long long)v;
+    do { *--p = (char)('0' + u % 10); u /= 10; } while (u);
+    if (neg) *--p = '-';
+    s.append(p, e - p);
+    s.push_back(' ');
 }
 
 inline int fail(gsi_ctx* ctx, const char* what) {

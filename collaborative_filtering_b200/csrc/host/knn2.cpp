@@ -44,12 +44,14 @@ int main(int, char**) {
     std::sort(edges.begin(), edges.end());
     FILE* f = fopen("out_fin_1_of_1", "w");
     if (!f) { perror("out_fin_1_of_1"); return 1; }
-    char buf[96];
+    std::string text;
     for (int64_t e = 0; e < ne; ++e) {                   // "src dst w\n" iff w > 0.01  :155-163
         if (!std::binary_search(edges.begin(), edges.end(), std::make_pair((unsigned)a[e], (unsigned)b[e]))) continue;
-        int n = snprintf(buf, sizeof buf, "%d %d %g\n", a[e], b[e], (double)w[e]);
-        fwrite(buf, 1, n, f);
+        append_int(text, a[e]); append_int(text, b[e]); append_g(text, (double)w[e]);
+        text.back() = '\n';                              // the weight ends the line
+        if (text.size() > (1u << 22)) { fwrite(text.data(), 1, text.size(), f); text.clear(); }
     }
+    fwrite(text.data(), 1, text.size(), f);
     fclose(f);
     return 0;
 }

@@ -147,18 +147,20 @@ int main(int argc, char** argv) {
     std::sort(rowsv.begin(), rowsv.end(), [](const Row& a, const Row& b) { return a.movie != b.movie ? a.movie < b.movie : a.user < b.user; });
     FILE* f = fopen("out_res_1_of_1", "w");
     if (!f) { perror("out_res_1_of_1"); return EXIT_FAILURE; }
-    char buf[128];
+    std::string res_text;
     double se = 0, se_ok = 0;
     size_t cnt = 0, ok = 0, illposed = 0, empty = 0;
     for (const Row& r : rowsv) {
-        int len = snprintf(buf, sizeof buf, "%u %u %g %d\n", r.movie, r.user, (double)r.mse, r.kk);
-        fwrite(buf, 1, len, f);
+        append_int(res_text, r.movie); append_int(res_text, r.user); append_g(res_text, (double)r.mse); append_int(res_text, r.kk);
+        res_text.back() = '\n';                          // "movie user' mse kk\n"  (:397-399)
+        if (res_text.size() > (1u << 22)) { fwrite(res_text.data(), 1, res_text.size(), f); res_text.clear(); }
         if (verbosity == 1 && r.mse != r.mse)
             printf("==== NaN: movieID: %u userID: %u connected: %d ====\n", r.movie, r.user, r.kk);
         if (r.status == GSI_PRED_EMPTY) { ++empty; continue; }
         se += r.mse; ++cnt;
         if (r.status == GSI_PRED_OK) { se_ok += r.mse; ++ok; } else ++illposed;
     }
+    fwrite(res_text.data(), 1, res_text.size(), f);
     fclose(f);
     const double secs = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
     printf("----------------------------------------------------------\n");

@@ -17,14 +17,10 @@ struct EigenSink {
 inline void format_record(const Csr& csr, const gsi_record_chunk* ch, int64_t j, std::string& s) {
     const int64_t u = ch->user_index[j];
     const int n = ch->n[j], k = ch->k[j];
-    char buf[64];
-    int len = snprintf(buf, sizeof buf, "%u %d %d ", csr.users[u], n, k);
-    s.append(buf, len);
+    s.reserve(s.size() + 16 * (size_t)n + 10 * (size_t)k + 9 * (size_t)n * k + 64);
+    append_int(s, csr.users[u]); append_int(s, n); append_int(s, k);
     const double* sig = ch->sig_min + csr.offsets[u];
-    for (int i = 0; i < n; ++i) {
-        len = snprintf(buf, sizeof buf, "%d %g ", csr.items[csr.offsets[u] + i], sig[i]);
-        s.append(buf, len);
-    }
+    for (int i = 0; i < n; ++i) { append_int(s, csr.items[csr.offsets[u] + i]); append_g(s, sig[i]); }
     s.push_back('\n');
     const double* lam = ch->lam + ch->lam_off[j];
     for (int i = 0; i < k; ++i) append_g(s, lam[i]);
