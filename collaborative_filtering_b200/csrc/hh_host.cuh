@@ -73,7 +73,7 @@ struct HhDev {           // device views of one chunk
     int64_t* roff_arr; int64_t* voff_arr; int64_t* loff_arr;
 };
 
-#define HH_CTL_INTS 4608       // [0..8) trd level queues, [8] bt queue, [64 + 256 l ..) slots, [2048 + 256 l ..) barriers, [3840..) trace
+#define HH_CTL_INTS 12288      // [0..8) trd level queues, [8] bt queue, [64 + 256 l ..) slots, [2048 + 256 l ..) barriers, [3840..) trace
 
 static int hh_alloc(gsi_ctx* ctx, const HhPlan& pl, const Job* jobs, HhDev& D) {
     Workspace& ws = WS(ctx);
@@ -173,7 +173,8 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
             L.nb = std::min(HH_NB, std::max(4, level_nb[lv] & ~3));
             L.own = (L.npmax / 64 + L.T - 1) / L.T;
             L.stages = TRD_MAX_STAGES;
-            while (L.stages > 1 && trd_smem_bytes(L.npmax, L.stages, L.own) > 227 * 1024) --L.stages;
+            if (const char* ms = getenv("GSI_TRD_STAGES")) L.stages = std::max(2, std::min(TRD_MAX_STAGES, atoi(ms)));   // probe
+            while (L.stages > 2 && trd_smem_bytes(L.npmax, L.stages, L.own) > 227 * 1024) --L.stages;   // (a refilled stage is consumed >= 2 tiles later)
             if (trd_smem_bytes(L.npmax, L.stages, L.own) > 227 * 1024)
                 return gsi_fail(ctx, GSI_ERR_INVALID, "user with n = %d does not fit the tridiagonalisation kernel", pl.jobs[b].n);
             smem = std::max(smem, trd_smem_bytes(L.npmax, L.stages, L.own));
@@ -242,6 +243,19 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
             std::sort(ft.begin(), ft.end());
             fprintf(stderr, "[gsi trace]   CTA finish times (ms): min %.1f  p25 %.1f  median %.1f  p75 %.1f  p90 %.1f  max %.1f\n",
                     ft[0], ft[sms / 4], ft[sms / 2], ft[3 * sms / 4], ft[(9 * sms) / 10], ft[sms - 1]);
+            std::vector<long long> lst((size_t)sms * TRD_MAX_LEVELS * 3);
+            cudaMemcpy(lst.data(), (long long*)(D.ctl + 3840) + TRD_PROF_LVSTAT, lst.size() * 8, cudaMemcpyDeviceToHost);
+            for (int l = 0; l < P.nlevels; ++l) {          // what a CTA streams while it is in the symv phase, per level
+                double cyc = 0, tiles = 0, tot = 0, tmax = 0; int nc = 0;
+                for (int b2 = 0; b2 < sms; ++b2) {
+                    const long long* o = &lst[((size_t)b2 * TRD_MAX_LEVELS + l) * 3];
+                    if (o[2] == 0) continue;
+                    cyc += (double)o[0]; tiles += (double)o[1]; tot += (double)o[2]; tmax = std::max(tmax, (double)o[2]); ++nc;
+                }
+                fprintf(stderr, "[gsi trace]   level %d (T=%d, %d stages): %d CTAs, %.0f tiles, symv %.1f %% of the level's CTA time, %.1f GB/s per CTA in symv, "
+                        "level time mean %.1f ms max %.1f ms\n", l, P.lv[l].T, P.lv[l].stages, nc, tiles, 100.0 * cyc / std::max(tot, 1.0),
+                        tiles * 32768.0 / std::max(cyc / 1.965e9, 1e-12) / 1e9, tot / std::max(nc, 1) / 1.965e6, tmax / 1.965e6);
+            }
             cudaEventDestroy(ta); cudaEventDestroy(tb);
         }
     }

@@ -31,7 +31,12 @@
 #define TRD_SYR_LD 68     // k-stride of the syr2k operand panels in shared memory (conflict-free DMMA fragments)
 #define TRD_SYR_KH 16     // the trailing update streams its operands in k-chunks of 16, double buffered (cp.async)
 #define TRD_SYR_DBL (2 * 4 * TRD_SYR_LD * TRD_SYR_KH)
-#define TRD_FIXED_DBL (16 + 4 * 64 + 1152 + 16)     // mbarriers, Wtv/Vtv/Wrow/Vrow, reduction scratch, scalars
+#define TRD_DSET_LD 66     // direct partials of a tile: [8 warps][64 rows], stride 66 (conflict-free 16-byte stores, 8-byte reduce loads)
+#define TRD_TSET_LD 68     // transposed partials of a tile column: [4 lane groups][64 columns], stride 68
+#define TRD_DSET_DBL (8 * TRD_DSET_LD)
+#define TRD_TSET_DBL (4 * TRD_TSET_LD)
+#define TRD_UNION_DBL (2 * TRD_DSET_DBL + 2 * TRD_TSET_DBL)   // symv: two parities of both partial sets; phase C: Wtv/Vtv/Wrow/Vrow + sum scratch
+#define TRD_FIXED_DBL (16 + 16 + 16 + TRD_UNION_DBL)          // mbarriers, scalars, tile descriptors of the stages (+ pad), the union above; multiple of 16
 #define TRD_MAX_STAGES 6
 
 // One user of the Householder / divide-and-conquer path
@@ -56,6 +61,7 @@ __host__ __device__ __forceinline__ size_t hh_tidx(int r, int c, int NT) {
 // teams of level l, so a team that finds its level's queue empty splits and moves on at once -- the
 // big users start first on big teams and the small ones fill every SM behind them (no tail per class).
 #define TRD_MAX_LEVELS 6
+#define TRD_PROF_LVSTAT 200   // trace buffer: [0..12) CTA 0 phase cycles, [15] start, [16..16+SMs) finish, then 3 values per (CTA, level)
 struct TrdLevel {
     int T, job0, njobs, npmax;              // team size, job range [job0, job0 + njobs), largest padded size
     int stages, own;                        // tile stages that fit beside this level's vectors; 64-row blocks a CTA can own
@@ -142,13 +148,17 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
     double* sm = (double*)trd_smem;
     uint64_t* full = (uint64_t*)sm;                // [8] tile stages, [8] = the x vector
     uint64_t* xbar = full + 8;
-    double* Wtv = sm + 16;                         // [64]
+    double* sc = sm + 16;                          // [16] scalars
+    int2* desc = (int2*)(sc + 16);                 // [8] (I, J) of the tile in each stage, written by the issuing thread
+    double* Wtv = sc + 32;                         // phase C view of the union: 4 x [64] ...
     double* Vtv = Wtv + 64;
     double* Wrow = Vtv + 64;
     double* Vrow = Wrow + 64;
-    double* red = Vrow + 64;                       // [1152] two parities of (8 x 64 direct partials + 64 transposed sums)
-    double* sc = red + 1152;                       // [16] scalars
-    double* lvl_base = sc + 16;
+    double* red = Vrow + 64;                       // ... and the scratch of cta_sum_d
+    double* dset = Wtv;                            // symv view: [2][8][66] direct partials, [2][4][68] transposed partials
+    double* tset = dset + 2 * TRD_DSET_DBL;
+    double* lvl_base = Wtv + TRD_UNION_DBL;
+    const uint32_t full_u32 = smem_u32(full), xbar_u32 = smem_u32(xbar);
     unsigned xphase = 0, phbits = 0;               // parity to wait for next, per mbarrier
     int c_st = 0, p_st = 0, pre_issued = 0;        // stage ring: next stage to consume / to fill; tiles requested ahead
 
@@ -185,6 +195,8 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
     double* Wp = LV.Wp + (size_t)team * lnp * HH_NB;
     unsigned* bar = LV.bar + team;
     unsigned bar_target = 0;
+    long long* lvstat = (long long*)(sc + 10);     // trace only: [0] symv cycles, [1] tiles, [2] level start
+    if (P.prof != nullptr && tid == 0) { lvstat[0] = 0; lvstat[1] = 0; lvstat[2] = clock64(); }
     for (;;) {
         if (c == 0 && tid == 0) LV.slot[team] = atomicAdd(LV.queue, 1);
         team_barrier(bar, bar_target, T);
@@ -202,9 +214,12 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
 
         auto issue_tile = [&](int I, int J, int st) {          // one thread; ONE request per tile (the copy engine
             double* tile = stage_base + (size_t)st * TRD_STAGE_DBL;    // serialises requests, ~150 ns each)
-            mbar_expect_tx(&full[st], HH_TS * HH_TS * 8);
-            bulk_g2s(tile, A + (((size_t)J * NT + I) << 12), HH_TS * HH_TS * 8, &full[st]);
+            desc[st] = make_int2(I, J);
+            mbar_expect_tx_u32(full_u32 + 8 * st, HH_TS * HH_TS * 8);
+            bulk_g2s_u32(smem_u32(tile), A + (((size_t)J * NT + I) << 12), HH_TS * HH_TS * 8, full_u32 + 8 * st);
         };
+        TileWalk wi;                                           // meaningful in thread 0 only
+        wi.init(0, NT, c, T);
 
         for (int j0 = 0; j0 < n - 1; j0 += LV.nb) {
             const int pw = min(LV.nb, n - 1 - j0);
@@ -276,24 +291,24 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                 {
                     const int m = NT - J0, total = m * (m + 1) / 2;
                     const int mine = (c < total) ? (total - c + T - 1) / T : 0;
-                    TileWalk wi, wc;
-                    wi.init(J0, NT, c, T);
-                    wc = wi;
+                    // The tile walk lives in the issuing thread only; everybody else reads (I, J) of a stage from `desc`.
                     int issued = pre_issued;                        // tiles already requested at the end of the last step
-                    for (int u = 0; u < pre_issued; ++u) wi.next();
+                    if (tid == 0) {
+                        if (pre_issued == 0) wi.init(J0, NT, c, T); // (else wi continues behind the tiles requested ahead)
+                        if (mine > 0) {                             // x' of this step: rows J0*64 .. np in ONE request
+                            const unsigned xb = (unsigned)(np - J0 * HH_TS) * 8;
+                            mbar_expect_tx_u32(xbar_u32, xb);
+                            bulk_g2s_u32(smem_u32(xsm + J0 * HH_TS), acol + J0 * HH_TS, xb, xbar_u32);
+                        }
+                        for (; issued < min(stages, mine); ++issued) {
+                            issue_tile(wi.I, wi.J, p_st);
+                            p_st = (p_st + 1 == stages) ? 0 : p_st + 1;
+                            wi.next();
+                        }
+                    }
                     pre_issued = 0;
-                    if (mine > 0 && tid == 0) {                     // x' of this step: rows J0*64 .. np in ONE request
-                        const unsigned xb = (unsigned)(np - J0 * HH_TS) * 8;
-                        mbar_expect_tx(xbar, xb);
-                        bulk_g2s(xsm + J0 * HH_TS, acol + J0 * HH_TS, xb, xbar);
-                    }
-                    for (; issued < min(stages, mine); ++issued) {
-                        if (tid == 0) issue_tile(wi.I, wi.J, p_st);
-                        p_st = (p_st + 1 == stages) ? 0 : p_st + 1;
-                        wi.next();
-                    }
                     if (mine > 0) {
-                        mbar_wait(xbar, xphase & 1);
+                        mbar_wait_u32(xbar_u32, xphase & 1);
                         ++xphase;
                         // x' = acol with the rows <= j zeroed and x'[j+1] = alpha - beta: only block J0 is touched
                         if (tid < 64) {
@@ -301,19 +316,26 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                             if (gi <= j) xsm[gi] = 0.0;
                             else if (gi == j + 1) xsm[gi] = xfix;
                         }
+                        // the first tile sums an all-zero "previous" direct set into block J0
+                        for (int i = tid; i < TRD_DSET_DBL; i += TRD_THREADS) dset[TRD_DSET_DBL + i] = 0.0;
                         fence_proxy_async();                        // this generic write precedes the next step's bulk copy
                         __syncthreads();
                     }
-                    double xax = 0.0;
-                    // A_IJ^T x_I: the column sums are kept per lane across the tiles of one tile column J of the walk and
-                    // reduced over the warp only when J changes (the walk is column-major)
+                    // Per tile: warp w owns the tile columns 8w..8w+7, a lane the rows 2 lane, 2 lane + 1 (16-byte loads).
+                    //   direct      A_IJ x_J: 8 warp partials per row -> dset[k & 1]; they are summed into y_I one tile LATER,
+                    //               by all threads, in the shadow of the next tile's loads (no warp is late at the barrier)
+                    //   transposed  A_IJ^T x_I: column sums stay in registers while J does not change (the walk is column-major);
+                    //               on a change, 3 shuffle stages leave 4 partials per column in tset, summed one tile later too
+                    // x'^T A x' is x'^T y of this CTA's partial y, taken once per column below.
+                    const int rrow = 8 * warp + (lane & 7);         // reduce role: lanes 0..7 of a warp own 8 entries of a 64-block (the others shadow them)
                     double tacc[8];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) tacc[q] = 0.0;
-                    int Jacc = -1;
-                    auto flush_tacc = [&](double* rdq) {            // 8 column sums over 32 lanes in 9 shuffles -> rdq[8 warp + q]
+                    int Jacc = -1, Iprev = J0, Jfl = -1;            // running column block; blocks whose partial sets wait
+                    unsigned fl_par = 0;
+                    auto flush_tacc = [&](double* ts) {             // 8 column sums over 32 lanes -> 4 partials per column
                         const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
-                        double u[4], v2[2], w1;
+                        double u[4], v2[2];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const double send = h4 ? tacc[q] : tacc[q + 4];
@@ -326,28 +348,36 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                             const double keep = h3 ? u[q + 2] : u[q];
                             v2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
                         }
-                        {
-                            const double send = h2 ? v2[0] : v2[1];
-                            const double keep = h2 ? v2[1] : v2[0];
-                            w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                        }
-                        w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
-                        w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
-                        if ((lane & 3) == 0) rdq[8 * warp + ((lane >> 2) & 7)] = w1;
+                        const double send = h2 ? v2[0] : v2[1];
+                        const double keep = h2 ? v2[1] : v2[0];
+                        ts[(lane & 3) * TRD_TSET_LD + 8 * warp + (lane >> 2)] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
 #pragma unroll
                         for (int q = 0; q < 8; ++q) tacc[q] = 0.0;
                     };
+                    // shuffle-free and branch-free on purpose: one basic block with the tile's FMAs, so the loads and the
+                    // add tree hide behind them (every lane computes and stores; lanes l, l + 8, l + 16, l + 24 are identical)
+                    auto sum_dset = [&](const double* ds, int blk) {        // y_blk += sum of the 8 warp partials
+                        const double* dp = ds + rrow;
+                        const double p0 = dp[0], p1 = dp[TRD_DSET_LD], p2 = dp[2 * TRD_DSET_LD], p3 = dp[3 * TRD_DSET_LD];
+                        const double p4 = dp[4 * TRD_DSET_LD], p5 = dp[5 * TRD_DSET_LD], p6 = dp[6 * TRD_DSET_LD], p7 = dp[7 * TRD_DSET_LD];
+                        double* yp = ysm + blk * HH_TS + rrow;
+                        const double yo = *yp;
+                        *yp = yo + (((p0 + p1) + (p2 + p3)) + ((p4 + p5) + (p6 + p7)));     // lanes l, l + 8, .. store the same value
+                    };
+                    auto sum_tset = [&](const double* ts, int blk) {        // y_blk += sum of the 4 lane-group partials
+                        const double* tp2 = ts + rrow;
+                        const double p0 = tp2[0], p1 = tp2[TRD_TSET_LD], p2 = tp2[2 * TRD_TSET_LD], p3 = tp2[3 * TRD_TSET_LD];
+                        double* yp = ysm + blk * HH_TS + rrow;
+                        *yp = *yp + ((p0 + p1) + (p2 + p3));
+                    };
+                    if (P.prof != nullptr && tid == 0) { lvstat[0] -= clock64(); lvstat[1] += mine; }
                     for (int k = 0; k < mine; ++k) {
-                        mbar_wait(&full[c_st], (phbits >> c_st) & 1u);
+                        const int2 dsc = desc[c_st];
+                        mbar_wait_u32(full_u32 + 8 * c_st, (phbits >> c_st) & 1u);
                         phbits ^= 1u << c_st;
                         const double* tile = stage_base + (size_t)c_st * TRD_STAGE_DBL;
-                        const int st_now = c_st;
                         if (++c_st == stages) c_st = 0;
-                        const int I = wc.I, J = wc.J;
-                        const double* xI = xsm + I * HH_TS;
-                        const double* xJ = xsm + J * HH_TS;
-                        double* rd = red + (k & 1) * 576;           // [8 warps][64 rows] direct partials + [64] transposed sums
-                        // warp w owns tile columns 8w..8w+7; lane owns rows 2 lane, 2 lane + 1 (16-byte loads)
+                        const int I = dsc.x, J = dsc.y;
                         const double2* tp = (const double2*)tile + (8 * warp) * 32 + lane;
                         double2 a[8];
 #pragma unroll
@@ -355,65 +385,67 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                         double xj[8];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const double2 v = ((const double2*)xJ)[4 * warp + q];
+                            const double2 v = ((const double2*)(xsm + J * HH_TS))[4 * warp + q];
                             xj[2 * q] = v.x; xj[2 * q + 1] = v.y;
                         }
+                        const double2 xi = ((const double2*)(xsm + I * HH_TS))[lane];
+                        // the partial sets of the previous tile (written before its barrier)
+                        sum_dset(dset + ((k + 1) & 1) * TRD_DSET_DBL, Iprev);
+                        if (Jfl >= 0) sum_tset(tset + (fl_par ^ 1) * TRD_TSET_DBL, Jfl);
+                        Jfl = -1;
                         double2 de = make_double2(0.0, 0.0), dodd = make_double2(0.0, 0.0);
 #pragma unroll
                         for (int q = 0; q < 8; q += 2) {
                             de.x = fma(a[q].x, xj[q], de.x); de.y = fma(a[q].y, xj[q], de.y);
                             dodd.x = fma(a[q + 1].x, xj[q + 1], dodd.x); dodd.y = fma(a[q + 1].y, xj[q + 1], dodd.y);
                         }
-                        ((double2*)rd)[warp * 32 + lane] = make_double2(de.x + dodd.x, de.y + dodd.y);
-                        const bool newJ = (Jacc >= 0) && (J != Jacc);   // CTA-uniform
-                        const int Jflush = Jacc;
-                        if (newJ) flush_tacc(rd + 512);
+                        *(double2*)(dset + (k & 1) * TRD_DSET_DBL + warp * TRD_DSET_LD + 2 * lane) = make_double2(de.x + dodd.x, de.y + dodd.y);
+                        if (Jacc >= 0 && J != Jacc) {               // CTA-uniform
+                            flush_tacc(tset + fl_par * TRD_TSET_DBL);
+                            fl_par ^= 1;
+                            Jfl = Jacc;
+                        }
                         Jacc = J;
                         if (I != J) {
-                            const double2 xi = ((const double2*)xI)[lane];
 #pragma unroll
                             for (int q = 0; q < 8; ++q) tacc[q] = fma(a[q].x, xi.x, fma(a[q].y, xi.y, tacc[q]));
                         }
+                        Iprev = I;
                         __syncthreads();
-                        if (issued < mine) {                        // every warp has the tile in registers: refill the stage
-                            if (tid == 0) issue_tile(wi.I, wi.J, st_now);
+                        if (tid == 0 && issued < mine) {            // every warp has the tile in registers: refill the stage
+                            issue_tile(wi.I, wi.J, p_st);
                             p_st = (p_st + 1 == stages) ? 0 : p_st + 1;
                             wi.next();
                             ++issued;
                         }
-                        if (tid < 64) {
-                            const double y = ((rd[tid] + rd[64 + tid]) + (rd[128 + tid] + rd[192 + tid])) +
-                                             ((rd[256 + tid] + rd[320 + tid]) + (rd[384 + tid] + rd[448 + tid]));
-                            ysm[I * HH_TS + tid] += y;
-                            xax = fma(xI[tid] * y, (I != J) ? 2.0 : 1.0, xax);
-                        } else if (tid < 128 && newJ) {
-                            ysm[Jflush * HH_TS + tid - 64] += rd[512 + tid - 64];
-                        }
-                        wc.next();
                     }
-                    __syncthreads();                                // the last tile's direct sums are in ysm
-                    if (Jacc >= 0) {                                // the last tile column's transposed sums
-                        flush_tacc(red + 512);
+                    if (mine > 0) {                                 // the sets still waiting, then the running column sums
+                        flush_tacc(tset + fl_par * TRD_TSET_DBL);   // (the last tile's barrier covers the reads of this parity)
                         __syncthreads();
-                        if (tid < 64) ysm[Jacc * HH_TS + tid] += red[512 + tid];
-                        __syncthreads();
+                        sum_dset(dset + ((mine + 1) & 1) * TRD_DSET_DBL, Iprev);
+                        if (Jfl >= 0) sum_tset(tset + (fl_par ^ 1) * TRD_TSET_DBL, Jfl);
+                        sum_tset(tset + fl_par * TRD_TSET_DBL, Jacc);
                     }
+                    __syncthreads();
+                    if (P.prof != nullptr && tid == 0) lvstat[0] += clock64();
                     // the matrix does not change inside a panel: request the first tiles of the next step now, so
                     // that they stream in while the team synchronises
-                    if (jj + 1 < pw) {
+                    if (jj + 1 < pw && tid == 0) {
                         const int J0n = (j + 2) >> 6, mn = NT - J0n, totn = mn * (mn + 1) / 2;
                         const int minen = (c < totn) ? (totn - c + T - 1) / T : 0;
-                        TileWalk wn;
-                        wn.init(J0n, NT, c, T);
+                        wi.init(J0n, NT, c, T);
                         for (; pre_issued < min(stages, minen); ++pre_issued) {
-                            if (tid == 0) issue_tile(wn.I, wn.J, p_st);
+                            issue_tile(wi.I, wi.J, p_st);
                             p_st = (p_st + 1 == stages) ? 0 : p_st + 1;
-                            wn.next();
+                            wi.next();
                         }
                     }
                     TRD_PROF(3);
+                    double xax = 0.0;
                     for (int r = J0 * HH_TS + tid; r < np; r += TRD_THREADS) {
-                        ypart[(size_t)c * lnp + r] = ysm[r];
+                        const double yv = ysm[r];
+                        ypart[(size_t)c * lnp + r] = yv;
+                        if (mine > 0) xax = fma(xsm[r], yv, xax);
                         ysm[r] = 0.0;
                     }
                     xax = cta_sum_d(xax, red);
@@ -617,6 +649,10 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
         }
         if (c == 0 && tid == 0) dvec[n - 1] = __ldcg(A + hh_tidx(n - 1, n - 1, NT));
         // the next job's first barrier separates this job's scratch use from the next one's
+    }
+    if (P.prof != nullptr && tid == 0) {                   // per-CTA, per-level stream statistics (trace only)
+        long long* o = P.prof + TRD_PROF_LVSTAT + ((size_t)blockIdx.x * TRD_MAX_LEVELS + lvi) * 3;
+        o[0] = lvstat[0]; o[1] = lvstat[1]; o[2] = clock64() - lvstat[2];
     }
     }   // levels
     if (prof_on)

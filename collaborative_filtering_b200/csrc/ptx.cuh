@@ -26,6 +26,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// the same on precomputed shared-window addresses (keeps the address conversion out of hot loops)
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s_u32(uint32_t dst_smem, const void* src_gmem, unsigned bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst_smem),
+                 "l"(src_gmem), "r"(bytes), "r"(bar)
+                 : "memory");
+}
 // generic-proxy accesses to shared memory ordered before later async-proxy (bulk copy) accesses
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 

@@ -31,6 +31,8 @@ ctx.set_weights(d_w)
 variant = os.environ.get("GSI_LARGE", "hh")
 for n in points:
     users = min(max(1, math.ceil(2 ** 26 / n ** 3)) * 148, 40000)
+    if os.environ.get("GSI_SWEEP_USERS"):          # probe: a fixed number of users per point (e.g. fewer than the SM count)
+        users = int(os.environ["GSI_SWEEP_USERS"])
     if variant == "bj" and n > 160:
         users = min(users, 148 if n <= 1024 else 8)
     rng = np.random.default_rng(31413 + n)
