@@ -500,10 +500,32 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                     if (valid && !act && sub == 0) A[hh_tidx(r, j, NT)] = 0.0;      // (live rows start at the diagonal block)
                     double av = 0.0, pdot = 0.0, adot = 0.0;
                     if (act) {
-#pragma unroll 4
-                        for (int cc = sub; cc < T; cc += G) av += __ldcg(ypart + (size_t)cc * lnp + r);
-#pragma unroll 4
-                        for (int cc = sub; cc < jj; cc += G) {
+                        // L2-latency bound: 8 (y partials) / 16 (panel entries) independent loads in flight per thread
+                        int cc = sub;
+                        for (; cc + 7 * G < T; cc += 8 * G) {
+                            double t8[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) t8[u] = __ldcg(ypart + (size_t)(cc + u * G) * lnp + r);
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) av += t8[u];
+                        }
+                        for (; cc < T; cc += G) av += __ldcg(ypart + (size_t)cc * lnp + r);
+                        cc = sub;
+                        for (; cc + 7 * G < jj; cc += 8 * G) {
+                            double v8[8], w8[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                v8[u] = __ldcg(Vp + (size_t)(cc + u * G) * ld + r);
+                                w8[u] = __ldcg(Wp + (size_t)(cc + u * G) * ld + r);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const int c2 = cc + u * G;
+                                pdot = fma(v8[u], Wtv[c2], fma(w8[u], Vtv[c2], pdot));
+                                adot = fma(v8[u], Wrow[c2], fma(w8[u], Vrow[c2], adot));
+                            }
+                        }
+                        for (; cc < jj; cc += G) {
                             const double vv = __ldcg(Vp + (size_t)cc * ld + r), ww = __ldcg(Wp + (size_t)cc * ld + r);
                             pdot = fma(vv, Wtv[cc], fma(ww, Vtv[cc], pdot));
                             adot = fma(vv, Wrow[cc], fma(ww, Vrow[cc], adot));
@@ -546,12 +568,29 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                             Pn[u] = (which ? Vp : Wp) + (size_t)cc * ld;
                             acc[u] = 0.0;
                         }
-                        for (int rs = lane; rs < rows_live; rs += 32) {
-                            const int slot = s0 + (rs >> 6), r = (c + slot * T) * 64 + (rs & 63);
-                            if (r >= j + 2) {
-                                const double av = aown[slot * 64 + (rs & 63)];
+                        // 4 row groups x 4 columns = 16 independent (predicated) loads in flight per lane; panel entries of
+                        // rows above the reflector are never written, so they are not read either
+                        for (int rs = lane; rs < rows_live; rs += 128) {
+                            double pv[4][4], avv[4];
+                            int rr[4];
+                            bool ok[4];
 #pragma unroll
-                                for (int u = 0; u < 4; ++u) acc[u] = fma(__ldcg(Pn[u] + r), av, acc[u]);
+                            for (int g = 0; g < 4; ++g) {
+                                const int rg = min(rs + 32 * g, rows_live - 1);
+                                const int slot = s0 + (rg >> 6);
+                                rr[g] = (c + slot * T) * 64 + (rg & 63);
+                                ok[g] = (rs + 32 * g < rows_live) && (rr[g] >= j + 2);
+                                avv[g] = aown[slot * 64 + (rg & 63)];
+                            }
+#pragma unroll
+                            for (int g = 0; g < 4; ++g)
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) pv[g][u] = ok[g] ? __ldcg(Pn[u] + rr[g]) : 0.0;
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const double a1 = ok[g] ? avv[g] : 0.0;
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) acc[u] = fma(pv[g][u], a1, acc[u]);
                             }
                         }
 #pragma unroll
