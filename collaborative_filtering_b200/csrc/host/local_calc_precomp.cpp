@@ -13,6 +13,7 @@
 #include <math.h>
 #include <time.h>
 
+#include <cstring>
 #include <random>
 
 #include "host_io.hpp"
@@ -39,8 +40,10 @@ int main(int argc, char** argv) {
     }
     // ---- out_eigen_ ----
     printf("Loading precomputed data.\nReading file: out_eigen_\n");
+    const char* bin_env = getenv("GSI_EIGEN_BINARY");     // binary side format written by precompute_local under the same switch
+    const bool binary = bin_env && atoi(bin_env) != 0;
     std::string text;
-    if (!read_file("out_eigen_", text)) { fprintf(stderr, "cannot read out_eigen_\n"); return EXIT_FAILURE; }
+    if (!read_file(binary ? "out_eigen_.bin" : "out_eigen_", text)) { fprintf(stderr, "cannot read %s\n", binary ? "out_eigen_.bin" : "out_eigen_"); return EXIT_FAILURE; }
     std::vector<unsigned> users;                          // user' per record, arrival order
     std::vector<int64_t> offsets(1, 0), lam_off, vec_off;
     std::vector<int32_t> items, kvec;
@@ -48,6 +51,33 @@ int main(int argc, char** argv) {
     std::unordered_map<unsigned, int64_t> rec_of;         // last record of a user wins (:470)
     int state = 0, n = 0, k = 0;
     bool bad = false;
+    if (binary) {                                         // precompute_common.hpp: "GSIEIG01" then records
+        const char* p = text.data();
+        const char* end = p + text.size();
+        bad = text.size() < 8 || memcmp(p, "GSIEIG01", 8) != 0;
+        p += 8;
+        while (!bad && p < end) {
+            int32_t head[4];
+            if (end - p < 16) { bad = true; break; }
+            memcpy(head, p, 16); p += 16;
+            n = head[1]; k = head[2];
+            const size_t ib = ((size_t)n + (n & 1)) * 4, need = ib + ((size_t)n + k + (size_t)n * k) * 8;
+            if (n < 0 || k < 0 || (size_t)(end - p) < need) { bad = true; break; }
+            users.push_back((unsigned)head[0]);
+            const size_t i0 = items.size(), s0 = sig_own.size();
+            items.resize(i0 + n); memcpy(items.data() + i0, p, (size_t)n * 4); p += ib;
+            sig_own.resize(s0 + n); memcpy(sig_own.data() + s0, p, (size_t)n * 8); p += (size_t)n * 8;
+            sig_run.insert(sig_run.end(), sig_own.begin() + s0, sig_own.end());             // never cleared in the reference (B1)
+            for (int i = 0; i < n; ++i) w_lim.push_back(fix_b1 ? sig_own[s0 + i] : sig_run[i]);
+            offsets.push_back((int64_t)items.size());
+            kvec.push_back(k);
+            lam_off.push_back((int64_t)lam.size());
+            lam.resize(lam.size() + k); memcpy(lam.data() + lam.size() - k, p, (size_t)k * 8); p += (size_t)k * 8;
+            vec_off.push_back((int64_t)vec.size());
+            vec.resize(vec.size() + (size_t)n * k); memcpy(vec.data() + vec.size() - (size_t)n * k, p, (size_t)n * k * 8); p += (size_t)n * k * 8;
+            rec_of[users.back()] = (int64_t)users.size() - 1;
+        }
+    } else
     for_each_line(text, [&](const char* b, const char* e) {
         if (bad) return;
         LineTok t(b, e);

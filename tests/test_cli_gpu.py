@@ -89,3 +89,59 @@ def test_pipeline_cli(tmp_path, golden_dir, case):
     out = _run("knn3", cwd)
     val = float(out.strip().split("Knn Average MSE:")[1])
     assert abs(val - meta["knn3_avg_mse"]) <= 2e-6 * max(1.0, meta["knn3_avg_mse"]) + 5e-6
+
+
+def _parse_eigen_bin(path):
+    """out_eigen_.bin (precompute_common.hpp): "GSIEIG01", then u32 user', i32 n, i32 k, i32 0, i32 movie[n] (+pad),
+    f64 sig_min[n], f64 lambda[k], f64 U[n*k]."""
+    buf = open(path, "rb").read()
+    assert buf[:8] == b"GSIEIG01"
+    p, recs = 8, {}
+    while p < len(buf):
+        uid, n, k, z = np.frombuffer(buf, dtype="<i4", count=4, offset=p)
+        assert z == 0
+        p += 16
+        items = np.frombuffer(buf, dtype="<i4", count=n, offset=p)
+        p += 4 * (n + (n & 1))
+        sig = np.frombuffer(buf, dtype="<f8", count=n, offset=p); p += 8 * n
+        lam = np.frombuffer(buf, dtype="<f8", count=k, offset=p); p += 8 * k
+        vec = np.frombuffer(buf, dtype="<f8", count=n * k, offset=p).reshape(n, k); p += 8 * n * k
+        recs[int(np.uint32(uid))] = {"items": items, "sigs_min": sig, "lam": lam, "vec": vec}
+    return recs
+
+
+def test_binary_out_eigen(tmp_path, golden_dir):
+    """SURVEY.md 8f.1 / README.md:29: GSI_EIGEN_BINARY=1 writes out_eigen_.bin (full doubles) instead of the text and
+    local_calc_precomp reads it back; the text path stays the default and agrees with it to its 6 digits."""
+    g = os.path.join(golden_dir, "tiny_int")
+    cwd = str(tmp_path)
+    shutil.copytree(os.path.join(g, "movielens"), os.path.join(cwd, "movielens"))
+    _run("knn", cwd)
+    _run("knn2", cwd)
+    _run("precompute_local", cwd)
+    text = O.parse_out_eigen(os.path.join(cwd, "out_eigen_"), bug_b1=False)
+    _run("local_calc_precomp", cwd, "--pct", "100", "--fix-b1")
+    res_text = open(os.path.join(cwd, "out_res_1_of_1")).read()
+    assert not os.path.exists(os.path.join(cwd, "out_eigen_.bin"))
+    env = {"GSI_EIGEN_BINARY": "1"}
+    _run("precompute_local_threads", cwd, "4", env=env)
+    assert os.path.getsize(os.path.join(cwd, "out_eigen_")) == 0          # no stale text next to the binary records
+    recs = _parse_eigen_bin(os.path.join(cwd, "out_eigen_.bin"))
+    assert sorted(recs) == sorted(text)
+    for u, t in text.items():
+        b = recs[u]
+        assert np.array_equal(b["items"], t["items"]) and b["lam"].shape == t["lam"].shape and b["vec"].shape == t["vec"].shape
+        assert np.allclose(b["sigs_min"], t["sigs_min"], rtol=1e-5, atol=0)       # the text keeps 6 significant digits
+        assert np.abs(b["lam"] - t["lam"]).max() <= 2e-6
+        n, k = b["vec"].shape
+        assert np.abs(b["vec"].T @ b["vec"] - np.eye(k)).max() <= 1e-9 or n < k     # full precision: orthonormal to fp64 level
+    _run("local_calc_precomp", cwd, "--pct", "100", "--fix-b1", env=env)
+    rows_b = [l.split() for l in open(os.path.join(cwd, "out_res_1_of_1"))]
+    rows_t = [l.split() for l in res_text.splitlines()]
+    assert [(r[0], r[1], r[3]) for r in rows_b] == [(r[0], r[1], r[3]) for r in rows_t]   # same pairs, same kk
+    eb = np.array([float(r[2]) for r in rows_b]); et = np.array([float(r[2]) for r in rows_t])
+    fin = np.isfinite(eb) & np.isfinite(et)
+    assert fin.sum() > 0 and np.median(np.abs(eb[fin] - et[fin])) <= 1e-3
+    # a later text run removes the binary file again
+    _run("precompute_local", cwd)
+    assert not os.path.exists(os.path.join(cwd, "out_eigen_.bin")) and os.path.getsize(os.path.join(cwd, "out_eigen_")) > 0
