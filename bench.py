@@ -204,7 +204,15 @@ def predict_sample(local_rank, nmax=256):
         tm = c2.timing()["predict"]
         npairs = int(s_off[-1])
         ok = out["status"] == 0
+        kk_ok, c_ok = out["kk"][ok].astype(np.float64), out["cols"][ok].astype(np.float64)
+        # algorithmic flops of the reference's per-pair solve: Gram + inverse + products
+        flop = float((2 * kk_ok * c_ok ** 2 + (2.0 / 3.0) * c_ok ** 3 + 2 * kk_ok * c_ok + 2 * c_ok ** 2).sum())
+        tf = flop / (tm["ms"] * 1e-3) / 1e12
+        peak = c2.measure_fp64_tflops(True)
         return {"value": npairs / (tm["ms"] * 1e-3), "unit": "predictions/s", "e2e_value": npairs / wall,
+                "roofline": {"kernel": "predict2_kernel (bordered Gram + blocked Cholesky, FP64 MMA)", "bound": "fp64 tensor",
+                             "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak if peak else None,
+                             "algorithmic_flop": flop, "peak_source": "DMMA m8n8k4 probe measured live (gsi_measure_fp64_tflops)"},
                 "pairs": npairs, "well_posed_fraction": float(ok.mean()), "kernel_ms": tm["ms"], "launches": tm["launches"],
                 "rmse_well_posed": float(np.sqrt(np.mean(out["err"][ok]))) if ok.any() else None,
                 "sample": "ml-100k shape, knn2-built item graph, %d users with n <= %d, every (user, rated movie) pair; "

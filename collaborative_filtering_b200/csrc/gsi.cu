@@ -736,14 +736,15 @@ extern "C" int gsi_predict_device(gsi_ctx* ctx, int64_t nu, const int64_t* h_off
         GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     // classes by the user's kept-eigenpair count (upper bound of the columns a pair can use)
-    static const int kClassC[] = {16, 32, 48, 64, 96, 128};
-    const int n_smem_classes = 6;
+    // (records with k <= 192 run on the tensor-core kernel with everything in shared memory, the rest on the scalar one)
+    static const int kClassC[] = {16, 32, 48, 64, 96, 128, 160, 192};
+    const int n_smem_classes = 8;
     std::vector<std::vector<PredTask>> cls(n_smem_classes + 1);
     for (int64_t u = 0; u < nu; ++u) {
         const int n = (int)(h_off[u + 1] - h_off[u]);
         const int k = h_k[u];
         int c = 0;
-        while (c < n_smem_classes && (k > kClassC[c] || predict_smem_bytes(kClassC[c], n, true) > 200 * 1024)) ++c;
+        while (c < n_smem_classes && (k > kClassC[c] || predict2_smem_bytes(kClassC[c], n, true) > 226 * 1024)) ++c;
         for (int i = 0; i < n; ++i) {
             const int64_t pair = h_off[u] + i;
             if (pair_mask && !pair_mask[pair]) continue;
@@ -779,14 +780,18 @@ extern "C" int gsi_predict_device(gsi_ctx* ctx, int64_t nu, const int64_t* h_off
         P.work = nullptr; P.work_stride = 0; P.nmax = nmax; P.m_in_smem = in_smem ? 1 : 0;
         if (in_smem) {
             P.cmax = kClassC[c];
-            const size_t smem = predict_smem_bytes(P.cmax, nmax, true);
-            GSI_CUDA(ctx, cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+            P.chunk_rows = P2_R;
+            const size_t smem = predict2_smem_bytes(P.cmax, nmax, true);
+            GSI_CUDA(ctx, cudaFuncSetAttribute(predict2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
             const int64_t wave = 1 << 20;
             for (int64_t b = 0; b < (int64_t)tasks.size(); b += wave) {
                 const int cnt = (int)std::min<int64_t>(wave, tasks.size() - b);
                 P.task_base = (int)b;
+                char label[96];
+                snprintf(label, sizeof label, "predict2 class c<=%d: %d pairs, nmax %d, %zu B smem", P.cmax, cnt, nmax, smem);
+                HhTrace tr(ctx, label);
                 GsiSpan sp(ctx, GSI_T_PREDICT, 1);
-                predict_kernel<<<cnt, 256, smem, ctx->stream>>>(P);
+                predict2_kernel<<<cnt, 256, smem, ctx->stream>>>(P);
                 sp.end();
                 GSI_CUDA(ctx, cudaGetLastError());
             }
@@ -795,16 +800,21 @@ extern "C" int gsi_predict_device(gsi_ctx* ctx, int64_t nu, const int64_t* h_off
             size_t b = 0;
             while (b < tasks.size()) {
                 const int kwave = tasks[b].k;                       // largest k of this wave (sorted)
-                const int64_t stride = (int64_t)kwave * kwave;
+                const int64_t stride = (int64_t)predict2_tiles_dbl(kwave);
                 int64_t wave = std::max<int64_t>(1, std::min<int64_t>(4 * ctx->sm_count, (ctx->ws_limit / 2) / (stride * 8)));
                 wave = std::min<int64_t>(wave, tasks.size() - b);
                 if ((rc = ws.pred_work.ensure(ctx, (size_t)wave * stride * 8)) != GSI_OK) return rc;
                 P.cmax = kwave; P.work = ws.pred_work.as<double>(); P.work_stride = stride; P.task_base = (int)b;
-                const size_t smem = predict_smem_bytes(P.cmax, nmax, false);
-                if (smem > 220 * 1024) return gsi_fail(ctx, GSI_ERR_INVALID, "predict: user too large for the staging buffers (n=%d, k=%d)", nmax, kwave);
-                GSI_CUDA(ctx, cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+                P.chunk_rows = 64;                                  // as many staged rows as fit beside the index arrays
+                while (P.chunk_rows > 8 && predict2_smem_bytes(P.cmax, nmax, false, P.chunk_rows) > 72 * 1024) P.chunk_rows /= 2;
+                const size_t smem = predict2_smem_bytes(P.cmax, nmax, false, P.chunk_rows);
+                if (smem > 226 * 1024) return gsi_fail(ctx, GSI_ERR_INVALID, "predict: user too large for the staging buffers (n=%d, k=%d)", nmax, kwave);
+                GSI_CUDA(ctx, cudaFuncSetAttribute(predict2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+                char label[96];
+                snprintf(label, sizeof label, "predict2 (M in L2) c<=%d: %d pairs, nmax %d, %zu B smem", P.cmax, (int)wave, nmax, smem);
+                HhTrace tr(ctx, label);
                 GsiSpan sp(ctx, GSI_T_PREDICT, 1);
-                predict_kernel<<<(int)wave, 256, smem, ctx->stream>>>(P);
+                predict2_kernel<<<(int)wave, 256, smem, ctx->stream>>>(P);
                 sp.end();
                 GSI_CUDA(ctx, cudaGetLastError());
                 b += wave;

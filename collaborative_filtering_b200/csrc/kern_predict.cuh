@@ -14,6 +14,7 @@
 #pragma once
 #include "gsi_internal.cuh"
 #include "kern_eig_cta.cuh"
+#include "ptx.cuh"
 
 #define GSI_PRED_CHUNK 16     // rows of A staged per Gram step
 
@@ -29,6 +30,7 @@ struct PredParams {
     float* err; int32_t* kk; double* pred; int32_t* status; int32_t* cols_used;
     double* work; int64_t work_stride;   // per-CTA global scratch for M when it does not fit smem
     int cmax, nmax, m_in_smem, task_base;
+    int chunk_rows;                 // rows of A staged per Gram step of predict2_kernel (multiple of 4)
 };
 
 // deterministic block-wide sum (fixed order: lanes by shuffle tree, warps ascending)
@@ -219,4 +221,273 @@ static inline size_t predict_smem_bytes(int cmax, int nmax, bool m_in_smem) {
     size_t d = (m_in_smem ? (size_t)cmax * cmax : 0) + (size_t)GSI_PRED_CHUNK * cmax + cmax + GSI_PRED_CHUNK;
     size_t i = (size_t)cmax + nmax + (nmax / 32 + 2);
     return d * sizeof(double) + i * sizeof(int) + 16;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Tensor-core predictor for records with k <= 192 (everything on chip).  Same selection rules and the same
+// pivot rule as predict_kernel above; what differs is how the normal equations are solved:
+//
+//   * A = U[K, cols] is staged 32 rows at a time and  M = A^T A  is accumulated with FP64 MMA (m8n8k4) into a
+//     tile-packed lower triangle of 8 x 8 tiles in shared memory (padded columns: zero, padded diagonal: 1);
+//   * the matrix is bordered by one more tile row that holds  rhs^T = (A^T (r_K - mean))^T  (it falls out of the
+//     same MMA pass: r_K - mean rides along as column `cpad` of the staging buffer) and  v^T = U[m, cols];
+//   * a right-looking blocked Cholesky (8 wide: diagonal tile by one warp in registers, panel by one thread
+//     per row, trailing update by MMA) runs over the bordered matrix.  The border rows turn into
+//     (L^-1 rhs)^T and (L^-1 v)^T and the corner tile receives  -(L^-1 v).(L^-1 rhs) = -v^T M^-1 rhs,
+//     i.e. the prediction minus the mean -- no triangular solves (local_calc_precomp.cpp:308-315).
+#define P2_R 32
+__host__ __device__ __forceinline__ int p2_ld(int cpad) { return ((cpad + 8 + 15) / 16) * 16 + 4; }    // == 4 mod 16: conflict-free fragments
+__host__ __device__ __forceinline__ int p2_tile(int ta, int tb) { return ((ta * (ta + 1) / 2) + tb) << 6; }
+static inline size_t predict2_tiles_dbl(int cmax) { const int nt = (cmax + 7) / 8; return (size_t)(nt + 1) * (nt + 2) / 2 * 64; }
+// M in shared memory when it fits; otherwise it lives in a per-CTA scratch in global memory (L2 resident) and only the
+// staging buffer is on chip
+static inline size_t predict2_smem_bytes(int cmax, int nmax, bool m_in_smem, int chunk_rows = P2_R) {
+    const int nt = (cmax + 7) / 8;
+    const size_t d = (m_in_smem ? predict2_tiles_dbl(cmax) : 0) + (size_t)chunk_rows * p2_ld(nt * 8);
+    const size_t i = (size_t)cmax + nmax + (nmax / 32 + 2);
+    return d * sizeof(double) + i * sizeof(int) + 16;
+}
+
+__global__ void __launch_bounds__(256) predict2_kernel(PredParams P) {
+    extern __shared__ double sm[];
+    const int tid = threadIdx.x, T = 256, lane = tid & 31, warp = tid >> 5, nwarps = 8;
+    const int task = blockIdx.x + P.task_base;
+    const int64_t pair = P.task_pair[task];
+    const int u = P.task_user[task];
+    const int64_t off = P.offsets[u];
+    const int n = (int)(P.offsets[u + 1] - off);
+    const int k = P.k[u];
+    const double* U = P.vec + P.vec_off[u];
+    const double* lam = P.lam + P.lam_off[u];
+    const int mrow = (int)(pair - off);
+    const unsigned m = (unsigned)P.items[pair];
+    const int cmax = P.cmax, ntmax = (cmax + 7) >> 3;
+    const int R = P.chunk_rows;
+    double* M = P.m_in_smem ? sm : P.work + (size_t)blockIdx.x * P.work_stride;     // (ntmax+1)(ntmax+2)/2 tiles of 64
+    double* As = sm + (P.m_in_smem ? (size_t)(ntmax + 1) * (ntmax + 2) / 2 * 64 : 0);   // [R][ld]
+    int* cols = (int*)(As + (size_t)R * p2_ld(ntmax * 8));           // [cmax]
+    int* rowsK = cols + cmax;                                        // [nmax]
+    int* wcnt = rowsK + P.nmax;                                      // [nmax/32 + 1]
+    __shared__ int sh_lim, sh_kk, sh_c, sh_bad;
+    __shared__ double wsum[8];
+    if (tid == 0) { sh_lim = k; sh_bad = 0; }
+    __syncthreads();
+    // ---- lim, K, mean, column clean: as in predict_kernel ----
+    const double w_lim = P.w_lim[pair];
+    for (int l = tid; l < k; l += T)
+        if (lam[l] > w_lim) { atomicMin(&sh_lim, l); break; }
+    const bool mok = m < (unsigned)P.w_rows;
+    const double* wrow = P.W + (size_t)m * P.w_rows;
+    const int nchunks = (n + 31) >> 5;
+    for (int ch = warp; ch < nchunks; ch += nwarps) {
+        const int j = ch * 32 + lane;
+        bool member = false;
+        if (j < n && mok) {
+            const unsigned mj = (unsigned)P.items[off + j];
+            if (mj < (unsigned)P.w_rows) member = (double)__double2float_rn(__ldg(wrow + mj)) > 0.1;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, member);
+        if (lane == 0) wcnt[ch] = __popc(bal);
+        // the membership bit is recomputed below (no per-row scratch)
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int ch = 0; ch < nchunks; ++ch) { const int cc = wcnt[ch]; wcnt[ch] = run; run += cc; }
+        sh_kk = run;
+        sh_lim = max(sh_lim, 2) < k ? max(sh_lim, 2) : k;
+    }
+    __syncthreads();
+    for (int ch = warp; ch < nchunks; ch += nwarps) {
+        const int j = ch * 32 + lane;
+        bool member = false;
+        if (j < n && mok) {
+            const unsigned mj = (unsigned)P.items[off + j];
+            if (mj < (unsigned)P.w_rows) member = (double)__double2float_rn(__ldg(wrow + mj)) > 0.1;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, member);
+        if (member) rowsK[wcnt[ch] + __popc(bal & ((1u << lane) - 1u))] = j;
+    }
+    __syncthreads();
+    const int kk = sh_kk, lim = sh_lim;
+    double rsum = 0.0;
+    for (int r = tid; r < kk; r += T) rsum += P.ratings[off + rowsK[r]];
+    rsum = block_sum_256(rsum, wsum);
+    for (int l = tid; l < cmax; l += T) cols[l] = -1;
+    __syncthreads();
+    for (int l = tid; l < lim; l += T) {
+        bool keep = false;
+        for (int r = 0; r < kk && !keep; ++r) keep = U[(size_t)rowsK[r] * k + l] >= 0.0001;
+        cols[l] = keep ? 1 : 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int cc = 0;
+        for (int l = 0; l < lim; ++l) if (cols[l] == 1) cols[cc++] = l;
+        sh_c = cc;
+    }
+    __syncthreads();
+    const int c = sh_c;
+    const double mean = (kk > 0) ? rsum / (double)kk : 0.0;
+    int status = GSI_PRED_OK;
+    double pred;
+    if (kk == 0) { status = GSI_PRED_EMPTY; pred = __longlong_as_double(0x7ff8000000000000LL); }
+    else if (c == 0) { pred = mean; }
+    else if (kk < c) { status = GSI_PRED_UNDERDETERMINED; pred = mean; }
+    else {
+        const int nt = (c + 7) >> 3, cpad = nt * 8, ld = p2_ld(cpad), wcols = cpad + 8;
+        const int fr = lane >> 2, fk = lane & 3;                      // MMA fragment row / k index of this lane
+        for (int e = tid; e < ((nt + 1) * (nt + 2) / 2) * 64; e += T) M[e] = 0.0;
+        // ---- bordered Gram: tiles (ta, tb), tb <= ta <= nt; row `nt` is the border (column cpad of As = r_K - mean) ----
+        for (int r0 = 0; r0 < kk; r0 += R) {
+            __syncthreads();                                          // the previous chunk is consumed (first pass: M is zero)
+            // a warp stages 4 rows; 8 independent gathers in flight per lane (the loads are L2-latency bound)
+            {
+                const double* urow[4];
+                double yv4[4];
+                bool live[4];
+                for (int rg = warp * 4; rg < R; rg += 32) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = rg + q;
+                    live[q] = r0 + r < kk;
+                    const int row = live[q] ? rowsK[r0 + r] : 0;
+                    urow[q] = U + (size_t)row * k;
+                    yv4[q] = live[q] ? P.ratings[off + row] - mean : 0.0;
+                }
+                for (int a0 = 0; a0 < wcols; a0 += 64) {
+                    double v[4][2];
+                    int ca[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) { const int a = a0 + lane + 32 * i; ca[i] = (a < c) ? cols[a] : -1; }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) v[q][i] = (live[q] && ca[i] >= 0) ? urow[q][ca[i]] : 0.0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int a = a0 + lane + 32 * i;
+                            if (a < wcols) As[(rg + q) * ld + a] = (a == cpad) ? yv4[q] : v[q][i];
+                        }
+                }
+                }
+            }
+            __syncthreads();
+            int seg = 0;
+            for (int ta = 0; ta <= nt; ++ta)
+                for (int s0 = 0; s0 <= ta; s0 += 4, ++seg) {
+                    if ((seg & 7) != warp) continue;
+                    const int ns = min(4, ta - s0 + 1);
+                    double2 acc[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        acc[i] = (i < ns) ? *(const double2*)(M + p2_tile(ta, s0 + i) + fr * 8 + 2 * fk) : make_double2(0.0, 0.0);
+                    const double* ap = As + fk * ld + 8 * ta + fr;
+                    const double* bp = As + fk * ld + 8 * s0 + fr;
+#pragma unroll 2
+                    for (int rr = 0; rr < R; rr += 4) {
+                        const double a = ap[rr * ld];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (i < ns) dmma(acc[i].x, acc[i].y, a, bp[rr * ld + 8 * i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (i < ns) *(double2*)(M + p2_tile(ta, s0 + i) + fr * 8 + 2 * fk) = acc[i];
+                }
+        }
+        __syncthreads();
+        // border row 1 = v^T; padded diagonal = 1
+        for (int a = tid; a < cpad; a += T) {
+            const int tb = a >> 3, j = a & 7;
+            M[p2_tile(nt, tb) + 8 + j] = (a < c) ? U[(size_t)mrow * k + cols[a]] : 0.0;
+            if (a >= c) M[p2_tile(tb, tb) + j * 8 + j] = 1.0;
+        }
+        __syncthreads();
+        // ---- blocked Cholesky over the bordered matrix ----
+        for (int jb = 0; jb < nt; ++jb) {
+            double* D = M + p2_tile(jb, jb);
+            if (warp == 0) {                                          // diagonal tile: lane i (mod 8) holds row i
+                const int i = lane & 7;
+                double r[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) r[q] = D[i * 8 + q];
+                bool ok = true;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const double piv = __shfl_sync(0xffffffffu, r[j], j);
+                    if (!(piv > 1e-14)) { ok = false; break; }        // same rule as predict_kernel; uniform over the warp
+                    const double d = sqrt(piv);
+                    r[j] = (i == j) ? d : r[j] / d;
+#pragma unroll
+                    for (int q = j + 1; q < 8; ++q) {
+                        const double lq = __shfl_sync(0xffffffffu, r[j], q);          // L[q][j]
+                        r[q] = fma(-r[j], lq, r[q]);
+                    }
+                }
+                if (!ok) { if (lane == 0) sh_bad = 1; }
+                else if (lane < 8) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) D[i * 8 + q] = (q <= i) ? r[q] : 0.0;
+                }
+            }
+            __syncthreads();
+            if (sh_bad) break;
+            // panel: rows of the tiles (ta, jb), ta = jb+1 .. nt (border included): x L_jj^T = row
+            const int nrows = (nt - jb) * 8;
+            for (int rr = tid; rr < nrows; rr += T) {
+                double* X = M + p2_tile(jb + 1 + (rr >> 3), jb) + (rr & 7) * 8;
+                double x[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) x[q] = X[q];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    double sacc = x[j];
+#pragma unroll
+                    for (int q = 0; q < j; ++q) sacc = fma(-x[q], D[j * 8 + q], sacc);
+                    x[j] = sacc / D[j * 8 + j];
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) X[q] = x[q];
+            }
+            __syncthreads();
+            // trailing update: tile (ta, tb) -= L(ta, jb) L(tb, jb)^T for jb < tb <= ta <= nt
+            int seg = 0;
+            for (int ta = jb + 1; ta <= nt; ++ta)
+                for (int s0 = jb + 1; s0 <= ta; s0 += 4, ++seg) {
+                    if ((seg & 7) != warp) continue;
+                    const int ns = min(4, ta - s0 + 1);
+                    const double* LA = M + p2_tile(ta, jb) + fr * 8 + fk;
+                    const double a0 = -LA[0], a1 = -LA[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (i < ns) {
+                            const double* LB = M + p2_tile(s0 + i, jb) + fr * 8 + fk;
+                            double2* C = (double2*)(M + p2_tile(ta, s0 + i) + fr * 8 + 2 * fk);
+                            double2 cv = *C;
+                            dmma(cv.x, cv.y, a0, LB[0]);
+                            dmma(cv.x, cv.y, a1, LB[4]);
+                            *C = cv;
+                        }
+                }
+            __syncthreads();
+        }
+        __syncthreads();
+        if (sh_bad) { status = GSI_PRED_SINGULAR; pred = mean; }
+        else pred = mean - M[p2_tile(nt, nt) + 8];
+    }
+    if (tid == 0) {
+        double p = pred;
+        if (p > 5.0) p = 5.0;
+        if (p < 1.0) p = 1.0;
+        const double real = P.ratings[pair];
+        const double d = real - p;
+        P.err[pair] = __double2float_rn(d * d);
+        P.kk[pair] = kk;
+        P.pred[pair] = pred;
+        P.status[pair] = status;
+        P.cols_used[pair] = c;
+    }
 }
