@@ -248,6 +248,15 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                 TRD_PROF(0);
                 team_barrier(bar, bar_target, T);                                   // ---- barrier 1
                 TRD_PROF(1);
+                // x' of this step (rows J0*64 .. np of acol, ONE request) is requested at once: it travels while the
+                // scalars and the panel totals are computed
+                const int J0 = (j + 1) >> 6;
+                const int mine = [&]() { const int m = NT - J0, total = m * (m + 1) / 2; return (c < total) ? (total - c + T - 1) / T : 0; }();
+                if (tid == 0 && mine > 0) {
+                    const unsigned xb = (unsigned)(np - J0 * HH_TS) * 8;
+                    mbar_expect_tx_u32(xbar_u32, xb);
+                    bulk_g2s_u32(smem_u32(xsm + J0 * HH_TS), acol + J0 * HH_TS, xb, xbar_u32);
+                }
                 // ---- scalars of the reflector (identical arithmetic in every CTA)
                 if (warp == 0) {
                     double s = 0.0;
@@ -287,19 +296,11 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                 TRD_PROF(2);
                 const double xfix = sc[3];
                 // ---- phase B: y = A x' over my tiles
-                const int J0 = (j + 1) >> 6;
                 {
-                    const int m = NT - J0, total = m * (m + 1) / 2;
-                    const int mine = (c < total) ? (total - c + T - 1) / T : 0;
                     // The tile walk lives in the issuing thread only; everybody else reads (I, J) of a stage from `desc`.
                     int issued = pre_issued;                        // tiles already requested at the end of the last step
                     if (tid == 0) {
                         if (pre_issued == 0) wi.init(J0, NT, c, T); // (else wi continues behind the tiles requested ahead)
-                        if (mine > 0) {                             // x' of this step: rows J0*64 .. np in ONE request
-                            const unsigned xb = (unsigned)(np - J0 * HH_TS) * 8;
-                            mbar_expect_tx_u32(xbar_u32, xb);
-                            bulk_g2s_u32(smem_u32(xsm + J0 * HH_TS), acol + J0 * HH_TS, xb, xbar_u32);
-                        }
                         for (; issued < min(stages, mine); ++issued) {
                             issue_tile(wi.I, wi.J, p_st);
                             p_st = (p_st + 1 == stages) ? 0 : p_st + 1;
@@ -452,12 +453,15 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                     if (tid == 0) part[c * TRD_PART + 1] = xax;
                 }
                 TRD_PROF(4);
+                // row j+1 of the panel (written in earlier steps) is fetched across the barrier
+                double wr_pre = 0.0, vr_pre = 0.0;
+                if (tid < jj) { wr_pre = __ldcg(Wp + (size_t)tid * ld + j + 1); vr_pre = __ldcg(Vp + (size_t)tid * ld + j + 1); }
                 team_barrier(bar, bar_target, T);                                   // ---- barrier 2
                 TRD_PROF(5);
                 // ---- phase C
                 const double beta = sc[0], tj = sc[1], scale = sc[2];
                 if (tid < jj) {
-                    const double wr = __ldcg(Wp + (size_t)tid * ld + j + 1), vr = __ldcg(Vp + (size_t)tid * ld + j + 1);
+                    const double wr = wr_pre, vr = vr_pre;
                     Wrow[tid] = wr; Vrow[tid] = vr;
                     Wtv[tid] = scale * (__ldcg(tot + tid) - beta * wr);
                     Vtv[tid] = scale * (__ldcg(tot + HH_NB + tid) - beta * vr);
@@ -499,6 +503,8 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                     // rows of the panel's diagonal block above the reflector
                     if (valid && !act && sub == 0) A[hh_tidx(r, j, NT)] = 0.0;      // (live rows start at the diagonal block)
                     double av = 0.0, pdot = 0.0, adot = 0.0;
+                    // next column of the (unchanged inside a panel) matrix: requested with the panel entries, not after them
+                    const double anext = (act && sub == 0 && more) ? __ldcg(A + hh_tidx(r, j + 1, NT)) : 0.0;
                     if (act) {
                         // L2-latency bound: 8 (y partials) / 16 (panel entries) independent loads in flight per thread
                         int cc = sub;
@@ -544,7 +550,7 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                         Wp[(size_t)jj * ld + r] = wr;
                         A[hh_tidx(r, j, NT)] = vr;
                         if (more) {
-                            const double an = __ldcg(A + hh_tidx(r, j + 1, NT)) - adot - vr * wj1 - wr;
+                            const double an = anext - adot - vr * wj1 - wr;
                             aown[slot * 64 + ii] = an;
                             acol[r] = an;
                             if (r >= j + 3) nrm = fma(an, an, nrm);
