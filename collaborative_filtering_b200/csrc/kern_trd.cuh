@@ -329,9 +329,9 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                     //               on a change, 3 shuffle stages leave 4 partials per column in tset, summed one tile later too
                     // x'^T A x' is x'^T y of this CTA's partial y, taken once per column below.
                     const int rrow = 8 * warp + (lane & 7);         // reduce role: lanes 0..7 of a warp own 8 entries of a 64-block (the others shadow them)
-                    double tacc[8];
+                    double tacc[8], xj[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) tacc[q] = 0.0;
+                    for (int q = 0; q < 8; ++q) { tacc[q] = 0.0; xj[q] = 0.0; }
                     int Jacc = -1, Iprev = J0, Jfl = -1;            // running column block; blocks whose partial sets wait
                     unsigned fl_par = 0;
                     auto flush_tacc = [&](double* ts) {             // 8 column sums over 32 lanes -> 4 partials per column
@@ -383,13 +383,15 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                         double2 a[8];
 #pragma unroll
                         for (int q = 0; q < 8; ++q) a[q] = tp[q * 32];
-                        double xj[8];
+                        if (J != Jacc) {                            // x_J of my 8 columns: reloaded only when the tile column changes
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const double2 v = ((const double2*)(xsm + J * HH_TS))[4 * warp + q];
-                            xj[2 * q] = v.x; xj[2 * q + 1] = v.y;
+                            for (int q = 0; q < 4; ++q) {
+                                const double2 v = ((const double2*)(xsm + J * HH_TS))[4 * warp + q];
+                                xj[2 * q] = v.x; xj[2 * q + 1] = v.y;
+                            }
                         }
-                        const double2 xi = ((const double2*)(xsm + I * HH_TS))[lane];
+                        double2 xi = ((const double2*)(xsm + I * HH_TS))[lane];
+                        if (I == J) xi = make_double2(0.0, 0.0);    // diagonal tile: the transposed product would count it twice
                         // the partial sets of the previous tile (written before its barrier)
                         sum_dset(dset + ((k + 1) & 1) * TRD_DSET_DBL, Iprev);
                         if (Jfl >= 0) sum_tset(tset + (fl_par ^ 1) * TRD_TSET_DBL, Jfl);
@@ -407,10 +409,8 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
                             Jfl = Jacc;
                         }
                         Jacc = J;
-                        if (I != J) {
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) tacc[q] = fma(a[q].x, xi.x, fma(a[q].y, xi.y, tacc[q]));
-                        }
+                        for (int q = 0; q < 8; ++q) tacc[q] = fma(a[q].x, xi.x, fma(a[q].y, xi.y, tacc[q]));
                         Iprev = I;
                         __syncthreads();
                         if (tid == 0 && issued < mine) {            // every warp has the tile in registers: refill the stage
