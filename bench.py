@@ -226,6 +226,30 @@ def predict_sample(local_rank, nmax=256):
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run (and therefore allocate the pinned record staging) on the CPUs of the NUMA node the GPU
+    hangs off, so that the 4 GB of records a rank copies back per step do not cross the socket interconnect.  Returns
+    the node, or None when the topology is not exposed (single socket, container without /sys)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception as e:  # pragma: no cover
+        log("numa binding skipped:", e)
+    return None
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -233,6 +257,7 @@ def run_gpu(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     t_gen = time.time()
@@ -407,7 +432,7 @@ def run_gpu(args, rank, world, local_rank):
             "config": {"workload": "%s shape, 1/8 user shard per GPU (LPT by n^3), synthetic W density 0.9" % args.shape,
                        "users_per_step_per_gpu": nu, "nnz_per_step_per_gpu": int(offsets[-1]), "max_n": int(deg.max()),
                        "l2": "256 MiB flush write between steps; working set per step >> 126 MB L2",
-                       "outputs_doubles_per_step": list(used)},
+                       "outputs_doubles_per_step": list(used), "numa_node_of_rank0": numa},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "steps": args.e2e_steps},
