@@ -159,6 +159,7 @@ extern "C" int gsi_destroy(gsi_ctx* c) {
     gsi_ctx_full* ctx = static_cast<gsi_ctx_full*>(c);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     drain_spans(ctx);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     Workspace& w = ctx->ws;
@@ -353,6 +354,9 @@ struct RunOut {               // where a chunk's records go
     int64_t* d_totals;        // [3] device: running lam, vec totals, overflow flag
     int32_t* d_k; int64_t* d_lam_off; int64_t* d_vec_off;   // caller-order arrays [n_users]
     double* d_sig_min;
+    // host path only: pinned destination of d_vec (same offsets).  A chunk runner that copies its eigenvector blocks itself,
+    // group by group behind the kernels of the next group, sets *vec_copied.
+    double* h_vec = nullptr; int64_t* h_bounds = nullptr; bool* vec_copied = nullptr;
 };
 
 static int upload_meta(gsi_ctx* ctx, MetaBuilder& mb, char** d_base) {
@@ -368,19 +372,24 @@ static int upload_meta(gsi_ctx* ctx, MetaBuilder& mb, char** d_base) {
     return GSI_OK;
 }
 
-static int finish_chunk(gsi_ctx* ctx, OutJobs J, const RunOut& out, int64_t max_nk, const int32_t* h_n = nullptr) {
+// offsets (scan over all jobs of the chunk) and compaction of the jobs [jb, je) (default: all)
+static int finish_chunk(gsi_ctx* ctx, OutJobs J, const RunOut& out, int64_t max_nk, const int32_t* h_n = nullptr,
+                        bool do_scan = true, int jb = 0, int je = -1) {
     Workspace& ws = WS(ctx);
     GsiSpan sp(ctx, GSI_T_COMPACT, 2);
-    out_scan_kernel<<<1, 1024, 0, ctx->stream>>>(J, out.d_totals, out.lam_cap, out.vec_cap, out.d_k, out.d_lam_off, out.d_vec_off);
-    GSI_CUDA(ctx, cudaGetLastError());
+    if (do_scan) {
+        out_scan_kernel<<<1, 1024, 0, ctx->stream>>>(J, out.d_totals, out.lam_cap, out.vec_cap, out.d_k, out.d_lam_off, out.d_vec_off);
+        GSI_CUDA(ctx, cudaGetLastError());
+    }
+    if (je < 0) je = J.nj;
     // jobs are sorted by n descending: one launch per group of similar size (h_n), so that the slice grid matches
-    int b = 0;
-    while (b < J.nj) {
-        int e = J.nj;
+    int b = jb;
+    while (b < je) {
+        int e = je;
         int64_t nk = max_nk;
         if (h_n) {
             e = b;
-            while (e < J.nj && 2 * h_n[e] > h_n[b]) ++e;
+            while (e < je && 2 * h_n[e] > h_n[b]) ++e;
             nk = (int64_t)h_n[b] * std::max(h_n[b], 2);
         }
         OutJobs G = J;
@@ -616,7 +625,7 @@ extern "C" int gsi_precompute_stream(gsi_ctx* ctx, int64_t nu, const int64_t* of
     Workspace& ws = WS(ctx);
     const int64_t nnz = offsets[nu];
     if ((rc = ws.totals.ensure(ctx, 64)) != GSI_OK) return rc;
-    if ((rc = ws.h_small.ensure(ctx, 64)) != GSI_OK) return rc;
+    if ((rc = ws.h_small.ensure(ctx, 256)) != GSI_OK) return rc;
     if ((rc = ws.items.ensure(ctx, nnz * 4)) != GSI_OK) return rc;
     if ((rc = ws.sig.ensure(ctx, nnz * 8)) != GSI_OK) return rc;
     if ((rc = ws.outk.ensure(ctx, nu * 4)) != GSI_OK) return rc;
@@ -642,6 +651,13 @@ extern "C" int gsi_precompute_stream(gsi_ctx* ctx, int64_t nu, const int64_t* of
         GSI_CUDA(ctx, cudaMemsetAsync(ws.totals.p, 0, 64, ctx->stream));
         RunOut out{ws.stage_lam.as<double>(), lcap, ws.stage_vec.as<double>(), vcap, ws.totals.as<int64_t>(),
                    ws.outk.as<int32_t>(), ws.outlam.as<int64_t>(), ws.outvec.as<int64_t>(), ws.sig.as<double>()};
+        bool vec_copied = false;
+        if (c.large && !c.bj) {                          // the Householder path copies its records group by group (hh_host.cuh)
+            if ((rc = ws.h_stage_vec.ensure(ctx, vcap * 8)) != GSI_OK) return rc;
+            out.h_vec = ws.h_stage_vec.as<double>();
+            out.h_bounds = (int64_t*)(ws.h_small.as<char>() + 64);
+            out.vec_copied = &vec_copied;
+        }
         rc = c.large ? (c.bj ? run_large_chunk : run_hh_chunk)(ctx, jobs, nj, ws.items.as<int32_t>(), out)
                      : run_small_chunk(ctx, jobs, nj, ws.items.as<int32_t>(), out);
         if (rc != GSI_OK) return rc;
@@ -656,8 +672,9 @@ extern "C" int gsi_precompute_stream(gsi_ctx* ctx, int64_t nu, const int64_t* of
         if ((rc = ws.h_stage_lam.ensure(ctx, h_tot[0] * 8)) != GSI_OK) return rc;
         if ((rc = ws.h_stage_vec.ensure(ctx, h_tot[1] * 8)) != GSI_OK) return rc;
         GSI_CUDA(ctx, cudaMemcpyAsync(ws.h_stage_lam.p, ws.stage_lam.p, h_tot[0] * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        GSI_CUDA(ctx, cudaMemcpyAsync(ws.h_stage_vec.p, ws.stage_vec.p, h_tot[1] * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (!vec_copied) GSI_CUDA(ctx, cudaMemcpyAsync(ws.h_stage_vec.p, ws.stage_vec.p, h_tot[1] * 8, cudaMemcpyDeviceToHost, ctx->stream));
         GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (vec_copied) GSI_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
         rec_user.resize(nj); rec_lam.resize(nj); rec_vec.resize(nj); rec_n.resize(nj); rec_k.resize(nj);
         for (int j = 0; j < nj; ++j) {
             const int64_t u = jobs[j].user;
@@ -1021,6 +1038,7 @@ extern "C" int gsi_timing_enable(gsi_ctx* ctx, int on) { if (!ctx) return GSI_ER
 extern "C" int gsi_timing_reset(gsi_ctx* ctx) {
     if (!ctx) return GSI_ERR_INVALID;
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     drain_spans(ctx);
     for (int i = 0; i < GSI_T_COUNT; ++i) { ctx->t_ms[i] = 0; ctx->t_launch[i] = 0; ctx->t_samples[i] = 0; }
     return GSI_OK;

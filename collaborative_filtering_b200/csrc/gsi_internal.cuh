@@ -32,6 +32,7 @@ struct gsi_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;   // record copies of a user group overlap the back-transform of the next one (host path)
     std::string err;
     int sm_count = 148;
     int64_t ws_limit = (int64_t)8 << 30;

@@ -145,7 +145,7 @@ struct HhTrace {
 // and everything smaller fills the other SMs behind them.
 static int hh_level_of(int np) { return np > 4096 ? 0 : (np > 2048 ? 1 : (np > 1024 ? 2 : 3)); }
 
-static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_team) {
+static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_team, bool defer_bt_apply = false) {
     Workspace& ws = WS(ctx);
     cudaStream_t st = ctx->stream;
     const int nj = pl.nj;
@@ -312,7 +312,7 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
         GSI_CUDA(ctx, cudaFuncSetAttribute(bt_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_smem_bytes()));
         { HhTrace tr(ctx, "bt_formt"); bt_formt_kernel<<<dim3((pl.nmax - 1 + BT_NB - 1) / BT_NB, nj), 256, bt_formt_smem_bytes(), st>>>(B); }
         GSI_CUDA(ctx, cudaMemsetAsync(D.ctl + 8, 0, 4, st));
-        { HhTrace tr(ctx, "bt_apply"); bt_apply_kernel<<<ctx->sm_count, 256, bt_smem_bytes(), st>>>(B); }
+        if (!defer_bt_apply) { HhTrace tr(ctx, "bt_apply"); bt_apply_kernel<<<ctx->sm_count, 256, bt_smem_bytes(), st>>>(B); }
         sp.end();
         GSI_CUDA(ctx, cudaGetLastError());
     }
@@ -362,30 +362,94 @@ static int run_hh_chunk(gsi_ctx* ctx, const Job* jobs, int nj, const int32_t* d_
         sp.end();
         GSI_CUDA(ctx, cudaGetLastError());
     }
-    if ((rc = hh_solve(ctx, pl, D, 0)) != GSI_OK) return rc;
-    {
-        GsiSpan sp(ctx, GSI_T_BT, 2);
-        BtParams B = hh_bt_params(pl, D);
-        HhTrace tr(ctx, "emit");
-        for (int b0 = 0; b0 < nj;) {                  // groups of similar size: grids that match the matrices
-            const int nmax = pl.jobs[b0].n;
-            int e0 = b0;
-            while (e0 < nj && 2 * pl.jobs[e0].n > nmax) ++e0;
-            const int tiles = (nmax + 31) / 32;
-            emit_sign_kernel<<<dim3((nmax + 7) / 8, e0 - b0), 256, 0, st>>>(B, D.sgn, b0);
-            emit_vec_kernel<<<dim3(tiles * tiles, 1, e0 - b0), dim3(32, 8), 0, st>>>(B, D.sgn, D.lamA, D.lamB, ws.vec_pad.as<double>(),
-                                                                               ws.lam_pad.as<double>(), tiles, b0);
-            b0 = e0;
-        }
-        sp.end();
-        GSI_CUDA(ctx, cudaGetLastError());
-    }
+    if ((rc = hh_solve(ctx, pl, D, 0, /*defer_bt_apply=*/true)) != GSI_OK) return rc;
     OutJobs J;
     J.nj = nj; J.n = D.n_arr; J.k = D.kuser; J.user = D.user; J.vec_pad = D.voff_arr; J.lam_pad = D.loff_arr;
     J.vec_dst = D.vec_dst; J.lam_dst = D.lam_dst;
     std::vector<int32_t> h_n(nj);
     for (int j = 0; j < nj; ++j) h_n[j] = pl.jobs[j].n;
-    return finish_chunk(ctx, J, out, pl.max_nk, h_n.data());
+    // The kept-eigenpair counts are final after the last merge, so the record offsets are known BEFORE the
+    // back-transform.  Device path: one back-transform launch over all users (biggest first: best balance).
+    // Host path: back-transform, emit and compaction run per group of users, SMALLEST users first (they hold half
+    // of the eigenvector volume but a seventh of the back-transform work; groups cut at 50 / 75 / 90 % of the n^2
+    // volume), and the eigenvector block of a group is copied to pinned memory on a second stream while the
+    // bigger users are still being back-transformed.
+    if ((rc = finish_chunk(ctx, J, out, pl.max_nk, h_n.data(), /*do_scan=*/true, 0, 0)) != GSI_OK) return rc;
+    const bool overlap = out.h_vec != nullptr && out.vec_copied != nullptr;
+    int gb[5] = {0, 0, 0, 0, nj};                          // job ranges [gb[g], gb[g+1]) in job order (n descending)
+    if (overlap) {
+        double tot = 0, run = 0;
+        for (int j = 0; j < nj; ++j) tot += (double)h_n[j] * h_n[j];
+        const double cut[3] = {0.5, 0.75, 0.9};
+        int g = 0;
+        gb[1] = gb[2] = gb[3] = 0;
+        for (int j = nj - 1; j >= 0 && g < 3; --j) {       // from the small end
+            run += (double)h_n[j] * h_n[j];
+            if (run >= cut[g] * tot) { gb[3 - g] = j; ++g; }
+        }
+    }
+    std::vector<int> item0(nj + 1, 0);                     // bt work items are laid out job by job (hh_build_plan)
+    for (int j = 0; j < nj; ++j) item0[j + 1] = item0[j] + (pl.jobs[j].n + BT_CB - 1) / BT_CB;
+    cudaEvent_t ev_scan = nullptr, ev_grp[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (overlap) {
+        if (!ctx->copy_stream) GSI_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int g = 0; g < 4; ++g)                        // offset of the first record of every group, then the end
+            GSI_CUDA(ctx, cudaMemcpyAsync(out.h_bounds + g, gb[g] < nj ? (const void*)(D.vec_dst + gb[g]) : (const void*)(out.d_totals + 1), 8,
+                                          cudaMemcpyDeviceToHost, st));
+        GSI_CUDA(ctx, cudaMemcpyAsync(out.h_bounds + 4, out.d_totals + 1, 8, cudaMemcpyDeviceToHost, st));
+        GSI_CUDA(ctx, cudaEventCreateWithFlags(&ev_scan, cudaEventDisableTiming));
+        GSI_CUDA(ctx, cudaEventRecord(ev_scan, st));
+    }
+    BtParams B = hh_bt_params(pl, D);
+    for (int g = 3; g >= 0; --g) {                         // smallest users first
+        const int jb = gb[g], je = gb[g + 1];
+        if (jb >= je) continue;
+        {
+            GsiSpan sp(ctx, GSI_T_BT, 1);
+            BtParams Bg = B;
+            Bg.items = B.items + item0[jb]; Bg.nitems = item0[je] - item0[jb];
+            GSI_CUDA(ctx, cudaMemsetAsync(D.ctl + 8, 0, 4, st));
+            HhTrace tr(ctx, "bt_apply");
+            bt_apply_kernel<<<ctx->sm_count, 256, bt_smem_bytes(), st>>>(Bg);
+            sp.end();
+            GSI_CUDA(ctx, cudaGetLastError());
+        }
+        {
+            GsiSpan sp(ctx, GSI_T_BT, 2);
+            HhTrace tr(ctx, "emit");
+            for (int b0 = jb; b0 < je;) {                 // sub-groups of similar size: grids that match the matrices
+                const int nmax = pl.jobs[b0].n;
+                int e0 = b0;
+                while (e0 < je && 2 * pl.jobs[e0].n > nmax) ++e0;
+                const int tiles = (nmax + 31) / 32;
+                emit_sign_kernel<<<dim3((nmax + 7) / 8, e0 - b0), 256, 0, st>>>(B, D.sgn, b0);
+                emit_vec_kernel<<<dim3(tiles * tiles, 1, e0 - b0), dim3(32, 8), 0, st>>>(B, D.sgn, D.lamA, D.lamB, ws.vec_pad.as<double>(),
+                                                                                   ws.lam_pad.as<double>(), tiles, b0);
+                b0 = e0;
+            }
+            sp.end();
+            GSI_CUDA(ctx, cudaGetLastError());
+        }
+        if ((rc = finish_chunk(ctx, J, out, pl.max_nk, h_n.data(), /*do_scan=*/false, jb, je)) != GSI_OK) return rc;
+        if (overlap) {
+            GSI_CUDA(ctx, cudaEventCreateWithFlags(&ev_grp[g], cudaEventDisableTiming));
+            GSI_CUDA(ctx, cudaEventRecord(ev_grp[g], st));
+        }
+    }
+    if (overlap) {
+        GSI_CUDA(ctx, cudaEventSynchronize(ev_scan));      // the offsets are on the host; the groups above are already queued
+        for (int g = 3; g >= 0; --g) {
+            if (!ev_grp[g]) continue;
+            const int64_t b0 = out.h_bounds[g], e0 = out.h_bounds[g + 1];
+            GSI_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev_grp[g], 0));
+            if (e0 > b0 && e0 <= out.vec_cap)
+                GSI_CUDA(ctx, cudaMemcpyAsync(out.h_vec + b0, out.d_vec + b0, (size_t)(e0 - b0) * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+        *out.vec_copied = true;                            // the caller synchronises copy_stream
+        cudaEventDestroy(ev_scan);
+        for (int g = 0; g < 4; ++g) if (ev_grp[g]) cudaEventDestroy(ev_grp[g]);
+    }
+    return GSI_OK;
 }
 
 // ---- stage-wise test hook ---------------------------------------------------------------------------
