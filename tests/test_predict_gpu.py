@@ -98,7 +98,7 @@ def test_golden_predictions(ctx, golden_dir, case, b1):
 
 def test_ml100k_precompute_then_predict_vs_oracle(ctx):
     """End to end on the GPU (precompute -> predict), checked stage-wise: the oracle predictor is
-    fed the GPU's own records.  Also exercises the global-scratch path (k > 128)."""
+    fed the GPU's own records.  Also exercises the path with M in the L2 scratch (k > 192)."""
     from collaborative_filtering_b200 import datasets as D
     r = D.make_ratings("ml-100k")
     w = D.make_weights(r.n_items, density=0.9)
@@ -125,4 +125,4 @@ def test_ml100k_precompute_then_predict_vs_oracle(ctx):
             rows.append((m, u, err, kk, pred, status, c))
     n_ok = _compare(users, recs, out, rows)
     assert n_ok >= 20
-    assert (recs.k > 128).any()                                   # global-scratch class exercised
+    assert (recs.k > 192).any()                                   # L2-scratch class exercised
