@@ -159,7 +159,7 @@ extern "C" int gsi_destroy(gsi_ctx* c) {
     gsi_ctx_full* ctx = static_cast<gsi_ctx_full*>(c);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); ctx->copy_stream = nullptr; }
     drain_spans(ctx);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     Workspace& w = ctx->ws;
@@ -1038,7 +1038,7 @@ extern "C" int gsi_timing_enable(gsi_ctx* ctx, int on) { if (!ctx) return GSI_ER
 extern "C" int gsi_timing_reset(gsi_ctx* ctx) {
     if (!ctx) return GSI_ERR_INVALID;
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     drain_spans(ctx);
     for (int i = 0; i < GSI_T_COUNT; ++i) { ctx->t_ms[i] = 0; ctx->t_launch[i] = 0; ctx->t_samples[i] = 0; }
     return GSI_OK;

@@ -215,3 +215,23 @@ def test_small_workspace_splits_into_chunks(ctx):
     for u in range(len(sel)):
         assert np.array_equal(one.lam_of(u), many.lam_of(u))          # fixed reduction orders: bit-identical
         assert np.array_equal(one.vec_of(u), many.vec_of(u))
+
+
+def test_host_path_survives_timing_reset_and_close(golden_dir):
+    """The host path copies the eigenvector blocks on a second stream; resetting the timers between two calls and closing
+    the context afterwards must leave that stream alone (regression: the reset destroyed it)."""
+    from collaborative_filtering_b200 import datasets as D
+    from collaborative_filtering_b200.api import Context
+    r = D.make_ratings("ml-100k", n_users=60)
+    w = D.make_weights(r.n_items)
+    c = Context(0)
+    try:
+        c.set_weights(w)
+        a = c.precompute(r.offsets, r.items)
+        c.timing_enable(True)
+        c.timing_reset()
+        b = c.precompute(r.offsets, r.items)
+        c.timing_reset()
+        assert np.array_equal(a.vec, b.vec) and np.array_equal(a.lam, b.lam) and np.array_equal(a.sig_min, b.sig_min)
+    finally:
+        c.close()
