@@ -339,7 +339,7 @@ static int run_hh_chunk(gsi_ctx* ctx, const Job* jobs, int nj, const int32_t* d_
         // sorted by n descending; launch per group of similar size so that the grids match the matrices.
         int ngroups = 0;
         for (int b1 = 0; b1 < nj; ++ngroups) { const int nm = pl.jobs[b1].n; while (b1 < nj && 2 * pl.jobs[b1].n > nm) ++b1; }
-        GsiSpan sp(ctx, GSI_T_LAP, 5 * ngroups);
+        GsiSpan sp(ctx, GSI_T_LAP, (getenv("GSI_LAP_UNFUSED") ? 5 : 2) * ngroups);
         HhTrace tr(ctx, "lap");
         int b0 = 0;
         while (b0 < nj) {
@@ -352,11 +352,16 @@ static int run_hh_chunk(gsi_ctx* ctx, const Job* jobs, int nj, const int32_t* d_
             C.nu = cnt; C.n = D.n_arr + b0; C.ld = D.ld_arr + b0; C.g_off = D.moff_arr + b0; C.item_off = D.ioff_arr + b0;
             C.row_off = D.roff_arr + b0;
             C.G = D.A; C.deg = D.deg; C.scale = D.scale; C.sigmax = D.sigmax + b0; C.tiled = 1;
-            lap_gather_kernel<<<dim3(tiles * tiles, 1, cnt), dim3(32, 8), 0, st>>>(C, ctx->d_w, ctx->w_rows, d_items, tiles);
-            lap_degree_kernel<<<dim3((nmax + 127) / 128, 1, cnt), 128, 0, st>>>(C);
-            lap_transform_kernel<<<dim3((nmax + 127) / 128, (nmax + 7) / 8, cnt), 128, 0, st>>>(C);
-            lap_sigmin_kernel<<<dim3((nmax + 127) / 128, 1, cnt), 128, 0, st>>>(C, out.d_sig_min);
-            lap_symmetrize_kernel<<<dim3(tiles * tiles, 1, cnt), dim3(32, 8), 0, st>>>(C, tiles, 0.0);
+            if (getenv("GSI_LAP_UNFUSED")) {                 // the five-kernel version (shared with the block-Jacobi path), for comparison
+                lap_gather_kernel<<<dim3(tiles * tiles, 1, cnt), dim3(32, 8), 0, st>>>(C, ctx->d_w, ctx->w_rows, d_items, tiles);
+                lap_degree_kernel<<<dim3((nmax + 127) / 128, 1, cnt), 128, 0, st>>>(C);
+                lap_transform_kernel<<<dim3((nmax + 127) / 128, (nmax + 7) / 8, cnt), 128, 0, st>>>(C);
+                lap_sigmin_kernel<<<dim3((nmax + 127) / 128, 1, cnt), 128, 0, st>>>(C, out.d_sig_min);
+                lap_symmetrize_kernel<<<dim3(tiles * tiles, 1, cnt), dim3(32, 8), 0, st>>>(C, tiles, 0.0);
+            } else {
+                lap_fused_gather_kernel<<<dim3((nmax + 63) / 64, 1, cnt), 256, 0, st>>>(C, ctx->d_w, ctx->w_rows, d_items);
+                lap_fused_transform_kernel<<<dim3((nmax + 63) / 64, 1, cnt), 256, 0, st>>>(C, out.d_sig_min);
+            }
             b0 = e0;
         }
         sp.end();

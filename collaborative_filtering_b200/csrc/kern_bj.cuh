@@ -182,6 +182,116 @@ __global__ void lap_symmetrize_kernel(LChunk C, int tiles_per_dim, double shift)
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused Laplacian stage of the Householder path (tile-major G): two passes over a user's matrix instead of five.
+// A CTA owns a block of 64 rows and walks the 64 x 64 tiles of that block row in column order, so the row sums keep
+// the reference's sequential j order (degree :199-203, sig_min :236-249) -- bit-exact with the kernels above.
+//   pass 1  gather W (:185-192) tile by tile through shared memory (table read along a W row, G write along a
+//           tile column, both contiguous), row sums -> deg, scale
+//   pass 2  ll2 = (s_i * ll_ij) * s_j (:211-222) on every tile of the block row, float-accumulated row norms ->
+//           sig_min, sigmax; written back: the tiles on and below the diagonal only (the diagonal tile with its
+//           upper triangle mirrored from the lower one) -- the Householder path never reads a tile above the
+//           diagonal, those keep the gathered weights
+// grid (ceil(nmax/64), 1, nu), block 256
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lap_fused_gather_kernel(LChunk C, const double* __restrict__ W, int w_rows,
+                                                               const int32_t* __restrict__ items) {
+    __shared__ double t[64][65];
+    __shared__ int idi[64], idj[64];
+    const int u = blockIdx.z;
+    const int n = C.n[u];
+    const int I = blockIdx.x, i0 = I * 64;
+    if (i0 >= n) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t ioff = C.item_off[u];
+    double* G = C.G + C.g_off[u];
+    const int NT = C.ld[u] >> 6, NTn = (n + 63) >> 6;
+    if (tid < 64) idi[tid] = (i0 + tid < n) ? items[ioff + i0 + tid] : -1;
+    double d = 0.0;                                           // row sum of row i0 + tid (threads 0..63)
+    for (int J = 0; J < NTn; ++J) {
+        __syncthreads();                                      // the previous tile is consumed (first pass: idi is written)
+        if (tid < 64) idj[tid] = (J * 64 + tid < n) ? items[ioff + J * 64 + tid] : -1;
+        __syncthreads();
+        double v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {                        // warp w: rows 8w..8w+7, two 32-column halves each
+            const int r = 8 * warp + (q >> 1), c = 32 * (q & 1) + lane;
+            const unsigned mi = (unsigned)idi[r], mj = (unsigned)idj[c];
+            v[q] = (mi < (unsigned)w_rows && mj < (unsigned)w_rows) ? __ldg(W + (size_t)mi * w_rows + mj) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) t[8 * warp + (q >> 1)][32 * (q & 1) + lane] = v[q];
+        __syncthreads();
+        double* tile = G + (((size_t)J * NT + I) << 12);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {                        // tile-major write: lanes along the rows of a tile column
+            const int e = tid + 256 * q, r = e & 63, c = e >> 6;
+            if (i0 + r < n && J * 64 + c < n) tile[(c << 6) + r] = t[r][c];
+        }
+        if (tid < 64 && i0 + tid < n) {
+            const int cn = min(64, n - J * 64);
+            for (int c = 0; c < cn; ++c) d = __dadd_rn(d, t[tid][c]);
+        }
+    }
+    if (tid < 64 && i0 + tid < n) {
+        if (d == 0.0) d = 1.0;
+        C.deg[C.row_off[u] + i0 + tid] = d;
+        C.scale[C.row_off[u] + i0 + tid] = __dsqrt_rn(__ddiv_rn(1.0, d));
+    }
+}
+
+__global__ void __launch_bounds__(256) lap_fused_transform_kernel(LChunk C, double* __restrict__ sig_min) {
+    __shared__ double t[64][65];
+    __shared__ double srow[64], drow[64], scol[64];
+    const int u = blockIdx.z;
+    const int n = C.n[u];
+    const int I = blockIdx.x, i0 = I * 64;
+    if (i0 >= n) return;
+    const int tid = threadIdx.x;
+    double* G = C.G + C.g_off[u];
+    const int NT = C.ld[u] >> 6, NTn = (n + 63) >> 6;
+    const double* deg = C.deg + C.row_off[u];
+    const double* sc = C.scale + C.row_off[u];
+    if (tid < 64) { srow[tid] = (i0 + tid < n) ? sc[i0 + tid] : 0.0; drow[tid] = (i0 + tid < n) ? deg[i0 + tid] : 0.0; }
+    float acc = 0.f;
+    for (int J = 0; J < NTn; ++J) {
+        __syncthreads();
+        if (tid < 64) scol[tid] = (J * 64 + tid < n) ? sc[J * 64 + tid] : 0.0;
+        double* tile = G + (((size_t)J * NT + I) << 12);
+        double w[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) { const int e = tid + 256 * q; w[q] = tile[e]; }     // (c << 6) + r == e
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int e = tid + 256 * q, r = e & 63, c = e >> 6;
+            const int i = i0 + r, j = J * 64 + c;
+            const double ll = (i == j) ? __dsub_rn(drow[r], w[q]) : __dsub_rn(0.0, w[q]);
+            t[r][c] = (i < n && j < n) ? __dmul_rn(__dmul_rn(srow[r], ll), scol[c]) : 0.0;
+        }
+        __syncthreads();
+        if (J <= I) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int e = tid + 256 * q, r = e & 63, c = e >> 6;
+                if (i0 + r < n && J * 64 + c < n) tile[e] = (J < I || r >= c) ? t[r][c] : t[c][r];
+            }
+        }
+        if (tid < 64 && i0 + tid < n) {
+            const int cn = min(64, n - J * 64);
+            for (int c = 0; c < cn; ++c) {
+                const double x = t[tid][c];
+                acc = __double2float_rn(__dadd_rn((double)acc, __dmul_rn(x, x)));
+            }
+        }
+    }
+    if (tid < 64 && i0 + tid < n) {
+        const float sig = __fsqrt_rn(acc);
+        sig_min[C.item_off[u] + i0 + tid] = __dadd_rn((double)sig, 0.01);
+        atomicMax(&C.sigmax[u], __float_as_uint(sig));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Block Jacobi.  Templated on the panel width M (two column blocks of B = M/2).
 //   round >= 0 : circle ordering over the nb blocks, inner sweep over the B*B CROSS pairs only
 //   round <  0 : "diagonal" round, pairs (2s, 2s+1), full cyclic sweep over all M(M-1)/2 pairs --
