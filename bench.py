@@ -185,14 +185,19 @@ def run_reference(args, rank, world):
 # BASELINE.json's metric string).  ML-100K shape, item graph built by the knn2 stage itself (cosine
 # weights), users with n <= 256, one prediction per (user, rated movie) pair.
 # ---------------------------------------------------------------------------------------------
-def predict_sample(local_rank, nmax=256):
+def predict_sample(local_rank, rank=0, world=1, nmax=256):
+    """Collective over the ranks: every rank builds the (replicated) item graph, predicts the pairs of its share of the
+    users (users are independent: dealt round robin by descending n), and the counts / squared errors / slowest kernel
+    time are all-reduced.  The returned numbers are whole-job."""
     from collaborative_filtering_b200.api import Context
     r = D.make_ratings("ml-100k")
     c2 = Context(local_rank)
     try:
         c2.knn_build(r.offsets, r.items, r.ratings, r.n_items + 1, install_weights=True)
         deg = np.diff(r.offsets)
-        sel = np.nonzero(deg <= nmax)[0]
+        sel_all = np.nonzero(deg <= nmax)[0]
+        sel_all = sel_all[np.argsort(-deg[sel_all], kind="stable")]
+        sel = np.sort(sel_all[rank::world])
         _, s_off, s_items, s_rat = D.subset(r, sel)
         recs = c2.precompute(s_off, s_items)
         c2.predict(recs, s_rat.astype(np.float64))                       # warm-up
@@ -207,17 +212,29 @@ def predict_sample(local_rank, nmax=256):
         kk_ok, c_ok = out["kk"][ok].astype(np.float64), out["cols"][ok].astype(np.float64)
         # algorithmic flops of the reference's per-pair solve: Gram + inverse + products
         flop = float((2 * kk_ok * c_ok ** 2 + (2.0 / 3.0) * c_ok ** 3 + 2 * kk_ok * c_ok + 2 * c_ok ** 2).sum())
-        tf = flop / (tm["ms"] * 1e-3) / 1e12
+        kernel_ms, se_ok, n_ok = tm["ms"], float(out["err"][ok].astype(np.float64).sum()), int(ok.sum())
+        if world > 1:                                     # whole-job numbers: sums over the ranks, time of the slowest rank
+            import torch
+            import torch.distributed as dist
+            dev = torch.device("cuda", local_rank)
+            sums = torch.tensor([npairs, flop, se_ok, n_ok], dtype=torch.float64, device=dev)
+            mx = torch.tensor([kernel_ms, wall], dtype=torch.float64, device=dev)
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            npairs, flop, se_ok, n_ok = int(sums[0].item()), float(sums[1].item()), float(sums[2].item()), int(sums[3].item())
+            kernel_ms, wall = float(mx[0].item()), float(mx[1].item())
+        tf = flop / (kernel_ms * 1e-3) / 1e12 / world       # per-GPU rate against the per-GPU peak
         peak = c2.measure_fp64_tflops(True)
-        return {"value": npairs / (tm["ms"] * 1e-3), "unit": "predictions/s", "e2e_value": npairs / wall,
+        tm = dict(tm, ms=kernel_ms)
+        return {"value": npairs / (tm["ms"] * 1e-3), "unit": "predictions/s", "e2e_value": npairs / wall, "n_gpus": world,
                 "roofline": {"kernel": "predict2_kernel (bordered Gram + blocked Cholesky, FP64 MMA)", "bound": "fp64 tensor",
                              "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak if peak else None,
                              "algorithmic_flop": flop, "peak_source": "DMMA m8n8k4 probe measured live (gsi_measure_fp64_tflops)"},
-                "pairs": npairs, "well_posed_fraction": float(ok.mean()), "kernel_ms": tm["ms"], "launches": tm["launches"],
-                "rmse_well_posed": float(np.sqrt(np.mean(out["err"][ok]))) if ok.any() else None,
-                "sample": "ml-100k shape, knn2-built item graph, %d users with n <= %d, every (user, rated movie) pair; "
-                          "value = kernel time (CUDA events), e2e_value = gsi_predict_host wall time with host buffers"
-                          % (len(sel), nmax)}
+                "pairs": npairs, "well_posed_fraction": n_ok / max(1, npairs), "kernel_ms": tm["ms"], "launches": tm["launches"],
+                "rmse_well_posed": float(np.sqrt(se_ok / n_ok)) if n_ok else None,
+                "sample": "ml-100k shape, knn2-built item graph, %d users with n <= %d dealt over %d rank(s), every (user, rated "
+                          "movie) pair; value = kernel time (CUDA events, slowest rank), e2e_value = gsi_predict_host wall time "
+                          "with host buffers; counts and squared errors all-reduced" % (len(sel_all), nmax, world)}
     finally:
         c2.close()
 
@@ -364,6 +381,11 @@ def run_gpu(args, rank, world, local_rank):
     h2d_bytes = int(items.nbytes)
     d2h_bytes = d2h[0] // max(1, args.e2e_steps)
 
+    # ---- auxiliary predictions/s sample: a collective over the ranks (users dealt over the GPUs, sums all-reduced) ----
+    predict_aux = None
+    if not args.no_predict:
+        predict_aux = predict_sample(local_rank, rank, world)
+
     if rank == 0:
         # ---- roofline of the dominant kernel group (live CUDA-event times of the timed region) ----
         def est_ms(name):
@@ -422,9 +444,6 @@ def run_gpu(args, rank, world, local_rank):
             w_host = d_w.cpu().numpy()
             rate, desc, cores = cpu_reference_rate(w_host, offsets, items, budget_s=args.cpu_budget)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
-        predict_aux = None
-        if not args.no_predict:
-            predict_aux = predict_sample(local_rank)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
