@@ -27,6 +27,7 @@ import random
 import shutil
 import subprocess
 import sys
+import time
 from collections import OrderedDict
 
 BIN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bin")
@@ -98,9 +99,9 @@ def _link(src: str, dst: str) -> None:
 
 
 def run_pipeline(cross_dir: str, workdir: str, folds=None, pct: int = 20, seed: int = 31413, bin_dir: str = BIN_DIR,
-                 precompute_tool: str = "precompute_local", threads: int = 8, log=sys.stderr) -> list:
+                 precompute_tool: str = "precompute_local", threads: int = 8, log=sys.stderr, stage_timeout=None) -> list:
     """One pass of run_test_precompute.sh per fold inside `workdir` (the tools are cwd-relative).
-    Returns one dict per fold: the RMSE summary of its out_res.{i}."""
+    Returns one dict per fold: the RMSE summary of its out_res.{i} and the wall seconds of every tool."""
     if folds is None:
         folds = sorted(int(os.path.basename(p)[1:-6]) for p in glob.glob(os.path.join(cross_dir, "u*.train")))
     os.makedirs(workdir, exist_ok=True)
@@ -113,20 +114,23 @@ def run_pipeline(cross_dir: str, workdir: str, folds=None, pct: int = 20, seed: 
         os.makedirs(mv)
         _link(os.path.join(cross_dir, "u%d.train" % i), os.path.join(mv, "u%d.train" % i))
         _link(os.path.join(cross_dir, "u%d.test" % i), os.path.join(mv, "u%d.validate" % i))
-        for stale in glob.glob(os.path.join(workdir, "out_*_of_*")) + glob.glob(os.path.join(workdir, "out_eigen_")):
+        for stale in glob.glob(os.path.join(workdir, "out_*_of_*")) + glob.glob(os.path.join(workdir, "out_eigen_*")):
             os.remove(stale)
+        stage_s = {}
         for tool, args in (("knn", []), ("knn2", []), (precompute_tool, [str(threads)]), ("local_calc_precomp", ["--pct", str(pct)])):
             exe = os.path.join(bin_dir, tool)
             if not os.path.exists(exe):
                 raise FileNotFoundError("%s is not built (run `make -C collaborative_filtering_b200/csrc`)" % exe)
-            subprocess.run([exe] + args, cwd=workdir, env=env, check=True, stdout=subprocess.DEVNULL)
+            t0 = time.perf_counter()
+            subprocess.run([exe] + args, cwd=workdir, env=env, check=True, stdout=subprocess.DEVNULL, timeout=stage_timeout)
+            stage_s[tool] = round(time.perf_counter() - t0, 3)
         parts = sorted(glob.glob(os.path.join(workdir, "out_res_*_of_*")))
         merged = os.path.join(workdir, "out_res.%d" % i)
         with open(merged, "w") as out:                       # cat out_res_* > out_res.$i
             for p in parts:
                 with open(p, "r") as f:
                     shutil.copyfileobj(f, out)
-        summary = dict(rmse_from_out_res([merged]), fold=i)
+        summary = dict(rmse_from_out_res([merged]), fold=i, seconds=stage_s)
         print(json.dumps(summary), file=log)
         results.append(summary)
     return results
