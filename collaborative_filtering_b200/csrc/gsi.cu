@@ -823,7 +823,8 @@ extern "C" int gsi_predict_device(gsi_ctx* ctx, int64_t nu, const int64_t* h_off
                 if ((rc = ws.pred_work.ensure(ctx, (size_t)wave * stride * 8)) != GSI_OK) return rc;
                 P.cmax = kwave; P.work = ws.pred_work.as<double>(); P.work_stride = stride; P.task_base = (int)b;
                 P.chunk_rows = 64;                                  // as many staged rows as fit beside the index arrays
-                while (P.chunk_rows > 8 && predict2_smem_bytes(P.cmax, nmax, false, P.chunk_rows) > 72 * 1024) P.chunk_rows /= 2;
+                static const size_t stage_cap = getenv("GSI_PRED_STAGE_KB") ? (size_t)atoi(getenv("GSI_PRED_STAGE_KB")) * 1024 : 110 * 1024;   // two CTAs per SM
+                while (P.chunk_rows > 8 && predict2_smem_bytes(P.cmax, nmax, false, P.chunk_rows) > stage_cap) P.chunk_rows /= 2;
                 const size_t smem = predict2_smem_bytes(P.cmax, nmax, false, P.chunk_rows);
                 if (smem > 226 * 1024) return gsi_fail(ctx, GSI_ERR_INVALID, "predict: user too large for the staging buffers (n=%d, k=%d)", nmax, kwave);
                 GSI_CUDA(ctx, cudaFuncSetAttribute(predict2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
