@@ -15,7 +15,7 @@ SO_PATH = os.path.join(_HERE, "libgsi.so")
 
 GSI_OK, GSI_ERR_INVALID, GSI_ERR_CUDA, GSI_ERR_NOMEM, GSI_ERR_STATE, GSI_ERR_CAPACITY, GSI_ERR_SINK = range(7)
 T_NAMES = ["eig_cta", "lap", "bj_gram", "bj_inner", "bj_update", "finalize", "compact", "predict", "knn",
-           "trd", "dc", "dc_gemm", "bt"]
+           "trd", "dc", "dc_gemm", "bt", "cheby"]
 
 c_i64p = ctypes.POINTER(ctypes.c_int64)
 c_i32p = ctypes.POINTER(ctypes.c_int32)
@@ -60,6 +60,7 @@ SYMBOLS = {
     "gsi_knn_corated_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                             ctypes.c_void_p]),
     "gsi_knn3_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 6),
+    "gsi_cheby_filter_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 4 + [ctypes.c_int] + [ctypes.c_void_p] * 2),
     "gsi_timing_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "gsi_timing_reset": (ctypes.c_int, [ctypes.c_void_p]),
     "gsi_timing_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

@@ -237,6 +237,19 @@ class Context:
         nv = int(np.count_nonzero((cnt > 0) | (has > 0)))
         return (float(total) / nv if nv else float("nan")), err, cnt, has
 
+    # ---- Chebyshev graph filter (cheby.cpp) ----
+    def cheby_filter(self, row_off, col, w, x, coef) -> np.ndarray:
+        """y = 0.5 c0 T0 + c1 T1 + ... on the normalised Laplacian of the CSR graph (out-edges, vertices 0..nv-1),
+        exactly the three engines of cheby.cpp:312-375."""
+        row_off = np.ascontiguousarray(row_off, dtype=np.int64)
+        col = np.ascontiguousarray(col, dtype=np.int32)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        coef = np.ascontiguousarray(coef, dtype=np.float64)
+        y = np.zeros(len(x), dtype=np.float64)
+        self._check(self._lib.gsi_cheby_filter_host(self._h, len(x), _ptr(row_off), _ptr(col), _ptr(w), _ptr(x), len(coef), _ptr(coef), _ptr(y)))
+        return y
+
     # ---- measurement ----
     def timing_enable(self, on: bool = True):
         self._check(self._lib.gsi_timing_enable(self._h, int(on)))

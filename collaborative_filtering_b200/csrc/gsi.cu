@@ -19,6 +19,7 @@
 #include "kern_trd.cuh"
 #include "kern_dc.cuh"
 #include "kern_bt.cuh"
+#include "kern_cheby.cuh"
 
 static thread_local std::string g_tls_err;
 
@@ -99,6 +100,7 @@ struct PinBuf {
 
 struct Workspace {
     DevBuf k_off, k_items, k_rat, k_cnt, k_num, k_S, k_ecnt, k_eoff, k_ea, k_eb, k_ew, k_co, k_err, k_mcnt, k_has;
+    DevBuf c_off, c_col, c_w, c_wn, c_vec;          // Chebyshev filter: CSR, normalised weights, 5 vertex vectors
     int64_t knn_edges = 0;
     DevBuf pred_meta, pred_work, p_off, p_items, p_wlim, p_rat, p_k, p_lamoff, p_vecoff, p_lam, p_vec, p_err, p_kk, p_pred, p_status, p_cols;
     DevBuf meta, vec_pad, lam_pad, G, rows, cols, perm, hpart, q, totals, items, sig, outk, outlam, outvec, stage_vec, stage_lam, probe;
@@ -170,7 +172,7 @@ extern "C" int gsi_destroy(gsi_ctx* c) {
                     &w.p_lam, &w.p_vec, &w.p_err, &w.p_kk, &w.p_pred, &w.p_status, &w.p_cols};
     for (auto b : d2) b->release();
     DevBuf* d3[] = {&w.k_off, &w.k_items, &w.k_rat, &w.k_cnt, &w.k_num, &w.k_S, &w.k_ecnt, &w.k_eoff, &w.k_ea, &w.k_eb, &w.k_ew,
-                    &w.k_co, &w.k_err, &w.k_mcnt, &w.k_has};
+                    &w.k_co, &w.k_err, &w.k_mcnt, &w.k_has, &w.c_off, &w.c_col, &w.c_w, &w.c_wn, &w.c_vec};
     for (auto b : d3) b->release();
     DevBuf* d4[] = {&w.hhA, &w.hhQa, &w.hhQb, &w.hhS, &w.hhvec, &w.hhivec, &w.trd_acol, &w.trd_ypart, &w.trd_part, &w.trd_panels};
     for (auto b : d4) b->release();
@@ -1030,6 +1032,59 @@ extern "C" int gsi_knn3_host(gsi_ctx* ctx, int64_t nu, const int64_t* off, const
     GSI_CUDA(ctx, cudaMemcpyAsync(movie_err_sum, ws.k_err.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, st));
     GSI_CUDA(ctx, cudaMemcpyAsync(movie_cnt, ws.k_mcnt.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, st));
     GSI_CUDA(ctx, cudaMemcpyAsync(has_edge, ws.k_has.p, (size_t)rows, cudaMemcpyDeviceToHost, st));
+    GSI_CUDA(ctx, cudaStreamSynchronize(st));
+    return GSI_OK;
+}
+
+// ---- Chebyshev graph filter (cheby.cpp) -----------------------------------------------------------
+extern "C" int gsi_cheby_filter_host(gsi_ctx* ctx, int64_t nv, const int64_t* row_off, const int32_t* col, const double* w,
+                                     const double* x, int ncoef, const double* coef, double* y) {
+    if (!ctx) return gsi_fail(nullptr, GSI_ERR_INVALID, "null context");
+    if (nv < 0 || nv > INT32_MAX || !row_off || ncoef < 2 || !coef || (nv > 0 && (!x || !y)))
+        return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_cheby_filter_host: need nv >= 0, ncoef >= 2 and non-null arrays");
+    if (nv == 0) return GSI_OK;
+    const int64_t nnz = row_off[nv];
+    if (row_off[0] != 0 || nnz < 0 || (nnz > 0 && (!col || !w))) return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_cheby_filter_host: bad CSR");
+    for (int64_t i = 0; i < nv; ++i)
+        if (row_off[i + 1] < row_off[i]) return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_cheby_filter_host: row offsets must not decrease");
+    for (int64_t e = 0; e < nnz; ++e)
+        if (col[e] < 0 || col[e] >= nv) return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_cheby_filter_host: column %d outside 0..%lld", col[e], (long long)nv - 1);
+    GSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    Workspace& ws = WS(ctx);
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if ((rc = ws.c_off.ensure(ctx, (nv + 1) * 8)) != GSI_OK) return rc;
+    if ((rc = ws.c_col.ensure(ctx, std::max<int64_t>(nnz, 1) * 4)) != GSI_OK) return rc;
+    if ((rc = ws.c_w.ensure(ctx, std::max<int64_t>(nnz, 1) * 8)) != GSI_OK) return rc;
+    if ((rc = ws.c_wn.ensure(ctx, std::max<int64_t>(nnz, 1) * 8)) != GSI_OK) return rc;
+    if ((rc = ws.c_vec.ensure(ctx, 5 * nv * 8)) != GSI_OK) return rc;
+    GSI_CUDA(ctx, cudaMemcpyAsync(ws.c_off.p, row_off, (nv + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (nnz) {
+        GSI_CUDA(ctx, cudaMemcpyAsync(ws.c_col.p, col, nnz * 4, cudaMemcpyHostToDevice, st));
+        GSI_CUDA(ctx, cudaMemcpyAsync(ws.c_w.p, w, nnz * 8, cudaMemcpyHostToDevice, st));
+    }
+    double* deg = ws.c_vec.as<double>();
+    double* t[3] = {deg + nv, deg + 2 * nv, deg + 3 * nv};
+    double* yd = deg + 4 * nv;
+    GSI_CUDA(ctx, cudaMemcpyAsync(t[0], x, nv * 8, cudaMemcpyHostToDevice, st));
+    const int64_t* d_off = ws.c_off.as<int64_t>();
+    const int32_t* d_col = ws.c_col.as<int32_t>();
+    const unsigned grid = (unsigned)((nv * 32 + 255) / 256);
+    {
+        GsiSpan sp(ctx, GSI_T_CHEBY, ncoef + 1);
+        cheby_degree_kernel<<<grid, 256, 0, st>>>((int)nv, d_off, ws.c_w.as<double>(), deg);
+        cheby_normalise_kernel<<<grid, 256, 0, st>>>((int)nv, d_off, d_col, ws.c_w.as<double>(), deg, ws.c_wn.as<double>());
+        // superstep 1: t[0] = T0 = x, t[1] = T1;  superstep k: T_{k+1} from T_k (cur) and T_{k-1} (old), rotating buffers
+        cheby_step_kernel<<<grid, 256, 0, st>>>((int)nv, d_off, d_col, ws.c_wn.as<double>(), t[0], t[0], t[1], yd, coef[0], coef[1], 1);
+        int old = 0, cur = 1, nxt = 2;
+        for (int k = 2; k < ncoef; ++k) {
+            cheby_step_kernel<<<grid, 256, 0, st>>>((int)nv, d_off, d_col, ws.c_wn.as<double>(), t[cur], t[old], t[nxt], yd, coef[k], 0.0, 0);
+            const int tmp = old; old = cur; cur = nxt; nxt = tmp;
+        }
+        sp.end();
+        GSI_CUDA(ctx, cudaGetLastError());
+    }
+    GSI_CUDA(ctx, cudaMemcpyAsync(y, yd, nv * 8, cudaMemcpyDeviceToHost, st));
     GSI_CUDA(ctx, cudaStreamSynchronize(st));
     return GSI_OK;
 }

@@ -187,6 +187,18 @@ int gsi_knn_corated_host(gsi_ctx* ctx, int64_t n_users, const int64_t* offsets, 
 int gsi_knn3_host(gsi_ctx* ctx, int64_t n_users, const int64_t* offsets, const int32_t* items,
                   const float* ratings, float* movie_err_sum, int32_t* movie_cnt, uint8_t* has_edge);
 
+/* ---- Chebyshev polynomial graph filter (cheby.cpp) ---------------------------------------------- *
+ * y = 0.5 c0 T0 + sum_{k >= 1} c_k T_k(x) on the normalised Laplacian of ONE graph, interval [0, 2]
+ * (cheby.cpp:17-19): T0 = x, T1 = L x - x, T_{k+1} = 2 (L T_k - T_k) - T_{k-1}, with
+ * L = I - D^-1/2 W D^-1/2 and d_i = the sum of the out-edge weights of i (degree_program, :155-183).
+ * Replaces the three GraphLab engines of cheby.cpp:312-375 (degree, init values, ncoef - 2 synchronous
+ * supersteps).  The graph is a CSR over out-edges with the vertices numbered 0 .. nv-1: every kept line
+ * `a b w` of graph_topology (w > 0.1, :96-99) contributes a -> b and b -> a, duplicates are kept.
+ * ncoef >= 2; with ncoef == 2 the reference reads coeff[2] out of bounds (:262) -- here the filter stops
+ * after c1.  All pointers are host memory; y receives nv values. */
+int gsi_cheby_filter_host(gsi_ctx* ctx, int64_t nv, const int64_t* row_off, const int32_t* col, const double* w,
+                          const double* x, int ncoef, const double* coef, double* y);
+
 /* ---- measurement helpers ------------------------------------------------------------------- */
 
 /* Accumulated device time (ms, CUDA events on the context's stream) per kernel class since the
@@ -205,7 +217,8 @@ enum {
     GSI_T_DC = 10,         /* divide & conquer on the tridiagonal: secular/deflation kernels      */
     GSI_T_DC_GEMM = 11,    /* divide & conquer merge GEMMs (DMMA)                                 */
     GSI_T_BT = 12,         /* back-transformation of the kept eigenvectors (DMMA) + emit          */
-    GSI_T_COUNT = 13
+    GSI_T_CHEBY = 13,      /* Chebyshev graph filter supersteps                                   */
+    GSI_T_COUNT = 14
 };
 int gsi_timing_enable(gsi_ctx* ctx, int on);
 int gsi_timing_reset(gsi_ctx* ctx);

@@ -584,3 +584,75 @@ def fold_split(ratings, num_div: int, rng: np.random.Generator):
         train = [t for j in range(len(test)) if j != i for t in test[j]]
         folds.append((train, test[i]))
     return folds
+
+
+# ---------------------------------------------------------------------------------------------------
+# Chebyshev polynomial graph filter -- cheby.cpp.  Test infrastructure like the rest of this file.
+# ---------------------------------------------------------------------------------------------------
+def cheby_parse_topology(text: str):
+    """graph_loader (cheby.cpp:86-103): lines `a b w`; a line is kept iff w > 0.1 (double) and adds BOTH directions."""
+    edges = []
+    for line in text.splitlines():
+        tok = line.split()
+        if len(tok) < 3:
+            continue
+        a, b, w = int(tok[0]), int(tok[1]), float(tok[2])
+        if w > 0.1:
+            edges.append((a, b, w))
+            edges.append((b, a, w))
+    return edges
+
+
+def cheby_parse_signal(text: str):
+    """graph_signal_loader (:105-118): lines `vertex value`."""
+    sig = {}
+    for line in text.splitlines():
+        tok = line.split()
+        if len(tok) >= 2:
+            sig[int(tok[0])] = float(tok[1])
+    return sig
+
+
+def cheby_parse_coeff(text: str):
+    """filter_loader (:120-135): every number of every line, in order."""
+    return [float(t) for t in text.split()]
+
+
+def cheby_filter(edges, signal: dict, coeff):
+    """The three engines of cheby.cpp:312-375 on directed edges (source, target, weight) -- degree_program (:155-183),
+    init_values_program (:189-227), cheby_program (:232-273, synchronous supersteps) with arange = [0, 2] (:17-19).
+    Vertices that only appear in the topology have an uninitialised signal in the reference; here they read 0.
+    With two coefficients the reference reads coeff[2] out of bounds (:262); here the filter stops after c1.
+    Returns {vertex: filtered value}."""
+    a1, a2 = (2.0 - 0.0) / 2, (2.0 + 0.0) / 2
+    verts = sorted(set(signal) | {e[0] for e in edges} | {e[1] for e in edges})
+    idx = {v: i for i, v in enumerate(verts)}
+    nv = len(verts)
+    src = np.array([idx[e[0]] for e in edges], dtype=np.int64)
+    dst = np.array([idx[e[1]] for e in edges], dtype=np.int64)
+    w = np.array([e[2] for e in edges], dtype=np.float64)
+    deg = np.zeros(nv)
+    np.add.at(deg, src, w)                                             # sum over the out-edges
+    wn = w / np.sqrt(deg[dst] * deg[src]) if len(w) else w            # :209-210, :251-252
+
+    def adj(t):                                                        # gather over the out-edges: sum wn * t[target]
+        out = np.zeros(nv)
+        np.add.at(out, src, wn * t[dst])
+        return out
+
+    x = np.array([signal.get(v, 0.0) for v in verts], dtype=np.float64)
+    coeff = list(coeff)
+    assert len(coeff) >= 2
+    t_old = x.copy()
+    t_cur = (x - adj(x) - a2 * x) / a1
+    val = 0.5 * coeff[0] * t_old + coeff[1] * t_cur
+    for k in range(2, len(coeff)):
+        t_new = (2 / a1) * (t_cur - adj(t_cur) - a2 * t_cur) - t_old
+        val = val + coeff[k] * t_new
+        t_old, t_cur = t_cur, t_new
+    return {v: float(val[idx[v]]) for v in verts}
+
+
+def cheby_format(values: dict) -> str:
+    """graph_signal_writer (:140-148): `id value\\n` in default stream formatting, ascending id (order is free)."""
+    return "".join("%d %s\n" % (v, fmt_g(values[v])) for v in sorted(values))
