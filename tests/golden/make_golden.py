@@ -133,7 +133,36 @@ def run_precompute_case(name, rng):
     print(name, "k =", [len(r.lam) for r in recs])
 
 
+def run_cheby_case(name, seed=31413 + 7, nv=48, density=0.25, ncoef=9):
+    """cheby.cpp inputs (coeff, graph_topology, graph_signal) and the oracle's graph_filtered_signal: sub-threshold weights,
+    a duplicate line, an isolated vertex, a vertex that only appears in the topology."""
+    rng = np.random.default_rng(seed)
+    d = os.path.join(HERE, name)
+    os.makedirs(d, exist_ok=True)
+    ids = np.sort(rng.choice(np.arange(1, 4 * nv), size=nv, replace=False))
+    lines = []
+    for i in range(nv):
+        for j in range(i + 1, nv):
+            if rng.random() < density:
+                lines.append((int(ids[i]), int(ids[j]), float(np.round(rng.uniform(0.02, 1.0), 6))))
+    lines.append(lines[3])
+    lines.append((int(ids[0]), 4 * nv + 50, 0.75))                             # 4 nv + 50 has no graph_signal line
+    topo = "".join("%d %d %s\n" % (a, b, O.fmt_g(w)) for a, b, w in lines)
+    signal = {int(v): float(np.round(rng.normal(3.5, 1.0), 4)) for v in ids}
+    signal[4 * nv + 7] = 2.5                                                   # isolated
+    sig_text = "".join("%d %s\n" % (v, O.fmt_g(x)) for v, x in signal.items())
+    coeff_text = " ".join(O.fmt_g(float(np.round(c, 5))) for c in rng.normal(0, 1, ncoef)) + "\n"
+    open(os.path.join(d, "graph_topology"), "w").write(topo)
+    open(os.path.join(d, "graph_signal"), "w").write(sig_text)
+    open(os.path.join(d, "coeff"), "w").write(coeff_text)
+    out = O.cheby_filter(O.cheby_parse_topology(topo), O.cheby_parse_signal(sig_text), O.cheby_parse_coeff(coeff_text))
+    open(os.path.join(d, "graph_filtered_signal_1_of_1"), "w").write(O.cheby_format(out))
+    np.savez(os.path.join(d, "oracle.npz"), vertex=np.array(sorted(out), dtype=np.int64), value=np.array([out[v] for v in sorted(out)]))
+    print(name, len(out), "vertices")
+
+
 if __name__ == "__main__":
+    run_cheby_case("cheby_small")
     rng = np.random.default_rng(31413)
     run_case("tiny_int", rng, half=False)
     run_case("tiny_half", rng, half=True, n_train=90, n_val=10, n_items=50)

@@ -131,3 +131,29 @@ def test_cheby_cli(tmp_path):
     lines = open(os.path.join(cwd, "graph_filtered_signal_1_of_1")).read().splitlines()
     same = sum(1 for a, b in zip(lines, O.cheby_format(ref).splitlines()) if a == b)
     assert same >= 0.99 * len(lines)                                             # identical text except for last-digit rounding ties
+
+
+def test_golden_fixture_is_reproducible(golden_dir):
+    """tests/golden/cheby_small (written by tests/golden/make_golden.py): the oracle reproduces the committed output."""
+    d = os.path.join(golden_dir, "cheby_small")
+    out = O.cheby_filter(O.cheby_parse_topology(open(os.path.join(d, "graph_topology")).read()),
+                         O.cheby_parse_signal(open(os.path.join(d, "graph_signal")).read()),
+                         O.cheby_parse_coeff(open(os.path.join(d, "coeff")).read()))
+    assert O.cheby_format(out) == open(os.path.join(d, "graph_filtered_signal_1_of_1")).read()
+    z = np.load(os.path.join(d, "oracle.npz"))
+    assert np.array_equal(z["vertex"], np.array(sorted(out))) and np.allclose(z["value"], [out[v] for v in sorted(out)], rtol=0, atol=1e-13)
+
+
+@pytest.mark.gpu
+def test_cli_on_the_golden_fixture(golden_dir, tmp_path):
+    import shutil
+    d = os.path.join(golden_dir, "cheby_small")
+    for f in ("coeff", "graph_topology", "graph_signal"):
+        shutil.copy(os.path.join(d, f), str(tmp_path / f))
+    p = subprocess.run([os.path.join(BIN, "cheby")], cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+    assert p.returncode == 0, p.stdout.decode()
+    z = np.load(os.path.join(d, "oracle.npz"))
+    got = O.cheby_parse_signal(open(str(tmp_path / "graph_filtered_signal_1_of_1")).read())
+    assert sorted(got) == z["vertex"].tolist()                                   # incl. the vertex without a graph_signal line
+    ref = dict(zip(z["vertex"].tolist(), z["value"].tolist()))
+    assert max(abs(got[v] - ref[v]) for v in ref) <= 1e-5 * max(1.0, max(abs(x) for x in ref.values()))
