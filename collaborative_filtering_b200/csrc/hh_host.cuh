@@ -163,10 +163,29 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
         P.nlevels = 0;
         size_t smem = 0;
         int b = 0;
-        while (b < nj) {                                           // jobs are sorted by n descending
+        // users whose matrix fits in shared memory go to the CTA-resident kernel (jobs are sorted by n descending: the tail)
+        static const int small_cap = getenv("GSI_TRD_SMALL_MAX") ? std::min(TRD_SMALL_MAX, atoi(getenv("GSI_TRD_SMALL_MAX"))) : TRD_SMALL_MAX;
+        int nj_big = nj;
+        if (forced_team <= 0) while (nj_big > 0 && pl.jobs[nj_big - 1].n <= small_cap) --nj_big;
+        {   // next to big users the small ones are free filler for the persistent kernel (its length is the biggest user's
+            // chain): they only move when they are a real share of the chunk's work
+            double w_small = 0, w_all = 0;
+            for (int j = 0; j < nj; ++j) { const double c3 = (double)pl.jobs[j].n * pl.jobs[j].n * pl.jobs[j].n; w_all += c3; if (j >= nj_big) w_small += c3; }
+            if (nj_big > 0 && w_small < 0.05 * w_all && !getenv("GSI_TRD_SMALL_MAX")) nj_big = nj;
+        }
+        if (nj_big < nj) {
+            const size_t ssm = trd_small_smem_bytes(pl.jobs[nj_big].n);
+            GSI_CUDA(ctx, cudaFuncSetAttribute(trd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+            GsiSpan sp(ctx, GSI_T_TRD, 1);
+            HhTrace tr(ctx, "trd_small");
+            trd_small_kernel<<<nj - nj_big, TRD_THREADS, ssm, st>>>(D.jobs, nj_big, D.A, D.d, D.e, D.tau);
+            sp.end();
+            GSI_CUDA(ctx, cudaGetLastError());
+        }
+        while (b < nj_big) {                                       // jobs are sorted by n descending
             const int lv = hh_level_of(pl.jobs[b].np);
             int e = b;
-            while (e < nj && hh_level_of(pl.jobs[e].np) == lv) ++e;
+            while (e < nj_big && hh_level_of(pl.jobs[e].np) == lv) ++e;
             TrdLevel& L = P.lv[P.nlevels++];
             L.T = forced_team > 0 ? std::min(sms, forced_team) : level_T[lv];
             L.job0 = b; L.njobs = e - b; L.npmax = pl.jobs[b].np;
@@ -214,12 +233,12 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
         }
         P.prof = ctx->trace ? (long long*)(D.ctl + 3840) : nullptr;
         GSI_CUDA(ctx, cudaMemsetAsync(D.ctl, 0, HH_CTL_INTS * 4, st));
-        GSI_CUDA(ctx, cudaFuncSetAttribute(trd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (P.nlevels > 0) GSI_CUDA(ctx, cudaFuncSetAttribute(trd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GsiSpan sp(ctx, GSI_T_TRD, 1);
         void* args[] = {&P};
         cudaEvent_t ta = nullptr, tb = nullptr;
         if (ctx->trace) { cudaEventCreate(&ta); cudaEventCreate(&tb); cudaEventRecord(ta, st); }
-        GSI_CUDA(ctx, cudaLaunchCooperativeKernel((void*)trd_kernel, dim3(sms), dim3(TRD_THREADS), args, smem, st));
+        if (P.nlevels > 0) GSI_CUDA(ctx, cudaLaunchCooperativeKernel((void*)trd_kernel, dim3(sms), dim3(TRD_THREADS), args, smem, st));
         sp.end();
         if (ctx->trace) {
             cudaEventRecord(tb, st); cudaEventSynchronize(tb);

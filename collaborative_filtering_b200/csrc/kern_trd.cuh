@@ -708,3 +708,92 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) trd_kernel(TrdParams P) {
         P.prof[16 + blockIdx.x] = (long long)t;
     }
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Tridiagonalisation of the users whose whole matrix fits in shared memory (n <= TRD_SMALL_MAX): one CTA per user,
+// unblocked Householder (LAPACK dsytd2 scheme) on a full symmetric copy in shared memory -- no L2 round trips and no
+// team barriers between the columns, which is what the persistent kernel above spends most of its time on for
+// matrices of two or three tiles.  Same outputs: d, e, tau and the reflectors in the columns of A (tile-major, 1 at
+// row j+1, zeros above inside the diagonal tile), same sign conventions, fixed reduction order.
+// ---------------------------------------------------------------------------------------------------
+#define TRD_SMALL_MAX 160
+static inline size_t trd_small_smem_bytes(int nmax) { return ((size_t)nmax * (nmax | 1) + 3 * (size_t)nmax + 64) * sizeof(double); }
+
+__global__ void __launch_bounds__(TRD_THREADS, 1) trd_small_kernel(const HJob* __restrict__ jobs, int job0, double* __restrict__ Aall,
+                                                                   double* __restrict__ dall, double* __restrict__ eall,
+                                                                   double* __restrict__ tauall) {
+    extern __shared__ __align__(16) double tsm[];
+    const HJob jb = jobs[job0 + blockIdx.x];
+    const int n = jb.n, NT = jb.np >> 6, ld = n | 1, tid = threadIdx.x;
+    double* As = tsm;                       // [n][ld] column-major, full symmetric
+    double* v = As + (size_t)n * ld;        // [n]
+    double* p = v + n;
+    double* w = p + n;
+    double* red = w + n;                    // [64]
+    double* A = Aall + jb.m_off;
+    double* dvec = dall + jb.r_off;
+    double* evec = eall + jb.r_off;
+    double* tvec = tauall + jb.r_off;
+    // the tiles on / below the diagonal hold sym(lower(L)); mirror into the upper triangle
+    for (int e = tid; e < n * n; e += TRD_THREADS) {
+        const int c = e / n, r = e - c * n;
+        if (r >= c) {
+            const double a = __ldcg(A + hh_tidx(r, c, NT));
+            As[r + (size_t)c * ld] = a;
+            As[c + (size_t)r * ld] = a;
+        }
+    }
+    __syncthreads();
+    for (int j = 0; j < n - 1; ++j) {
+        // ---- reflector of column j: alpha = A[j+1][j], s = sum_{r >= j+2} A[r][j]^2
+        double s = 0.0;
+        for (int r = j + 2 + tid; r < n; r += TRD_THREADS) { const double a = As[r + (size_t)j * ld]; s = fma(a, a, s); }
+        s = cta_sum_d(s, red);
+        const double alpha = As[j + 1 + (size_t)j * ld];
+        double beta, tj, scale;
+        if (s == 0.0) { beta = alpha; tj = 0.0; scale = 0.0; }
+        else {
+            beta = -copysign(sqrt(fma(alpha, alpha, s)), alpha);
+            tj = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+        }
+        if (tid == 0) { dvec[j] = As[j + (size_t)j * ld]; evec[j] = beta; tvec[j] = tj; }
+        for (int r = tid; r < n; r += TRD_THREADS) {
+            const double vr = (r <= j) ? 0.0 : (r == j + 1 ? 1.0 : scale * As[r + (size_t)j * ld]);
+            v[r] = vr;
+            if (r >= (j & ~63)) A[hh_tidx(r, j, NT)] = vr;        // reflector column (zeros above, inside the diagonal tile)
+        }
+        __syncthreads();
+        // ---- p = A v over the trailing block (rows / columns > j); thread per row, four partial sums
+        for (int i = j + 1 + tid; i < n; i += TRD_THREADS) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int k = j + 1;
+            for (; k + 3 < n; k += 4) {
+                a0 = fma(As[i + (size_t)k * ld], v[k], a0);
+                a1 = fma(As[i + (size_t)(k + 1) * ld], v[k + 1], a1);
+                a2 = fma(As[i + (size_t)(k + 2) * ld], v[k + 2], a2);
+                a3 = fma(As[i + (size_t)(k + 3) * ld], v[k + 3], a3);
+            }
+            for (; k < n; ++k) a0 = fma(As[i + (size_t)k * ld], v[k], a0);
+            p[i] = (a0 + a1) + (a2 + a3);
+        }
+        __syncthreads();
+        double pv = 0.0;
+        for (int i = j + 1 + tid; i < n; i += TRD_THREADS) pv = fma(p[i], v[i], pv);
+        pv = cta_sum_d(pv, red);
+        // w = tau p - (tau^2 / 2)(p^T v) v
+        const double alpha2 = -0.5 * tj * tj * pv;
+        for (int i = j + 1 + tid; i < n; i += TRD_THREADS) w[i] = fma(tj, p[i], alpha2 * v[i]);
+        __syncthreads();
+        // ---- A22 -= v w^T + w v^T (both triangles)
+        for (int i = j + 1 + tid; i < n; i += TRD_THREADS) {
+            const double vi = v[i], wi = w[i];
+            for (int k = j + 1; k < n; ++k) {
+                double* a = As + i + (size_t)k * ld;
+                *a = *a - (vi * w[k] + wi * v[k]);
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) dvec[n - 1] = As[n - 1 + (size_t)(n - 1) * ld];
+}

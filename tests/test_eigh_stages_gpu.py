@@ -39,7 +39,8 @@ def _householder_q(v, tau):
     return q
 
 
-@pytest.mark.parametrize("n,density,team", [(33, 0.9, 1), (64, 0.5, 1), (65, 0.9, 2), (161, 0.9, 1), (200, 0.1, 4),
+@pytest.mark.parametrize("n,density,team", [(33, 0.9, 0), (97, 0.3, 0), (128, 0.9, 0), (160, 0.9, 0),      # team 0: the default routing (n <= 160: CTA-resident tridiagonalisation)
+                                            (33, 0.9, 1), (64, 0.5, 1), (65, 0.9, 2), (161, 0.9, 1), (200, 0.1, 4),
                                             (257, 0.9, 3), (500, 0.9, 1), (777, 0.5, 8), (1000, 0.9, 16),
                                             (1100, 0.9, 2), (2100, 0.9, 148)])
 def test_stages_against_oracle(ctx, n, density, team):
