@@ -185,6 +185,24 @@ def run_reference(args, rank, world):
 # BASELINE.json's metric string).  ML-100K shape, item graph built by the knn2 stage itself (cosine
 # weights), users with n <= 256, one prediction per (user, rated movie) pair.
 # ---------------------------------------------------------------------------------------------
+def deal_users(deg, nmax, rank, world):
+    """Users with n <= nmax, dealt round robin over the ranks by descending n (users are independent units)."""
+    sel_all = np.nonzero(deg <= nmax)[0]
+    sel_all = sel_all[np.argsort(-deg[sel_all], kind="stable")]
+    return sel_all, np.sort(sel_all[rank::world])
+
+
+def reduce_predict_stats(npairs, flop, se_ok, n_ok, kernel_ms, wall, device):
+    """all-reduce of (pair count, flops, sum of squared errors, well-posed count) and the slowest rank's times."""
+    import torch
+    import torch.distributed as dist
+    sums = torch.tensor([npairs, flop, se_ok, n_ok], dtype=torch.float64, device=device)
+    mx = torch.tensor([kernel_ms, wall], dtype=torch.float64, device=device)
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    return int(sums[0].item()), float(sums[1].item()), float(sums[2].item()), int(sums[3].item()), float(mx[0].item()), float(mx[1].item())
+
+
 def predict_sample(local_rank, rank=0, world=1, nmax=256):
     """Collective over the ranks: every rank builds the (replicated) item graph, predicts the pairs of its share of the
     users (users are independent: dealt round robin by descending n), and the counts / squared errors / slowest kernel
@@ -195,9 +213,7 @@ def predict_sample(local_rank, rank=0, world=1, nmax=256):
     try:
         c2.knn_build(r.offsets, r.items, r.ratings, r.n_items + 1, install_weights=True)
         deg = np.diff(r.offsets)
-        sel_all = np.nonzero(deg <= nmax)[0]
-        sel_all = sel_all[np.argsort(-deg[sel_all], kind="stable")]
-        sel = np.sort(sel_all[rank::world])
+        sel_all, sel = deal_users(deg, nmax, rank, world)
         _, s_off, s_items, s_rat = D.subset(r, sel)
         recs = c2.precompute(s_off, s_items)
         c2.predict(recs, s_rat.astype(np.float64))                       # warm-up
@@ -215,14 +231,8 @@ def predict_sample(local_rank, rank=0, world=1, nmax=256):
         kernel_ms, se_ok, n_ok = tm["ms"], float(out["err"][ok].astype(np.float64).sum()), int(ok.sum())
         if world > 1:                                     # whole-job numbers: sums over the ranks, time of the slowest rank
             import torch
-            import torch.distributed as dist
-            dev = torch.device("cuda", local_rank)
-            sums = torch.tensor([npairs, flop, se_ok, n_ok], dtype=torch.float64, device=dev)
-            mx = torch.tensor([kernel_ms, wall], dtype=torch.float64, device=dev)
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            npairs, flop, se_ok, n_ok = int(sums[0].item()), float(sums[1].item()), float(sums[2].item()), int(sums[3].item())
-            kernel_ms, wall = float(mx[0].item()), float(mx[1].item())
+            npairs, flop, se_ok, n_ok, kernel_ms, wall = reduce_predict_stats(
+                npairs, flop, se_ok, n_ok, kernel_ms, wall, torch.device("cuda", local_rank))
         tf = flop / (kernel_ms * 1e-3) / 1e12 / world       # per-GPU rate against the per-GPU peak
         peak = c2.measure_fp64_tflops(True)
         tm = dict(tm, ms=kernel_ms)

@@ -74,3 +74,46 @@ def test_two_rank_gloo_sharding(tmp_path):
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "OK" in outs[0]
+
+
+_WORKER2 = r"""
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+import bench
+from collaborative_filtering_b200 import datasets as D
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["PORT"], rank=rank, world_size=2)
+r = D.make_ratings("ml-100k", n_users=120)
+deg = np.diff(r.offsets)
+sel_all, mine = bench.deal_users(deg, 200, rank, 2)
+other = bench.deal_users(deg, 200, 1 - rank, 2)[1]
+assert len(np.intersect1d(mine, other)) == 0 and np.array_equal(np.sort(np.concatenate([mine, other])), np.sort(sel_all))
+assert abs(int(deg[mine].sum()) - int(deg[other].sum())) <= int(deg[sel_all].max())          # dealt by descending n: balanced
+pairs = int(deg[mine].sum())
+out = bench.reduce_predict_stats(pairs, 2.0 * pairs, 0.5 * pairs, pairs - rank, 10.0 + rank, 0.1 * (rank + 1), torch.device("cpu"))
+tot = int(deg[sel_all].sum())
+assert out[0] == tot and out[1] == 2.0 * tot and abs(out[2] - 0.5 * tot) < 1e-9 and out[3] == tot - 1
+assert out[4] == 11.0 and abs(out[5] - 0.2) < 1e-12                                          # the slowest rank's times
+print("OK", out[0])
+dist.destroy_process_group()
+""" % ROOT
+
+
+def test_two_rank_gloo_predict_sample_reduction(tmp_path):
+    """bench.py's predictions/s sample at N > 1: the users are dealt over the ranks and the counts / squared errors are summed,
+    the times maxed (world_size-2 gloo on CPU)."""
+    script = tmp_path / "worker2.py"
+    script.write_text(_WORKER2)
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "OK" in outs[0] and "OK" in outs[1]
