@@ -300,7 +300,12 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
         {
             GsiSpan sp(ctx, GSI_T_DC, 6);
             if (ctx->trace) fprintf(stderr, "[gsi trace] dc level %d: %d nodes, mmax %d\n", l, P.nnodes, mmax);
-            { HhTrace tr(ctx, "  deflate"); dc_deflate_kernel<<<P.nnodes, 256, 0, st>>>(P); }
+            {
+                HhTrace tr(ctx, "  deflate");
+                const size_t dsm = dc_deflate_smem_bytes(mmax);
+                GSI_CUDA(ctx, cudaFuncSetAttribute(dc_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(dsm, 48 * 1024)));
+                dc_deflate_kernel<<<P.nnodes, 256, dsm, st>>>(P);
+            }
             {
                 HhTrace tr(ctx, "  secular");       // lanes per root grow with the merge size (few, big merges near the top)
                 if (mmax <= 256) dc_secular_kernel<1><<<dim3(P.nnodes, (mmax + 127) / 128), 128, 0, st>>>(P);

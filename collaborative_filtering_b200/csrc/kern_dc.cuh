@@ -137,7 +137,11 @@ __global__ void __launch_bounds__(128) dc_leaf_kernel(const HJob* __restrict__ j
 // ---------------------------------------------------------------------------------------------
 // deflation: one CTA (256 threads) per merge node
 // ---------------------------------------------------------------------------------------------
+// dynamic shared memory: the merged pole list (d, z, source index, type) of the node -- the deflation scan and the map
+// construction are serial chains over it (one thread), which must not run on global-memory latency
+static inline size_t dc_deflate_smem_bytes(int mmax) { return (size_t)mmax * (8 + 8 + 4 + 4) + 64; }
 __global__ void __launch_bounds__(256) dc_deflate_kernel(DcParams P) {
+    extern __shared__ __align__(16) unsigned char dfl_smem[];
     const DcNode nd = P.nodes[P.node0 + blockIdx.x];
     DcState& st = P.state[P.node0 + blockIdx.x];
     const HJob jb = P.jobs[nd.job];
@@ -146,6 +150,10 @@ __global__ void __launch_bounds__(256) dc_deflate_kernel(DcParams P) {
     double* Qin = (P.in_b ? P.Qb : P.Qa) + jb.m_off + (size_t)off * ld + off;      // block (off, off)
     const double* lamIn = (P.in_b ? P.lamB : P.lamA) + vb;
     double* ds = P.ds + vb; double* zs = P.zs + vb; int32_t* src = P.src + vb;
+    double* s_ds = (double*)dfl_smem;                   // [m]
+    double* s_zs = s_ds + m;                            // [m]
+    int32_t* s_src = (int32_t*)(s_zs + m);              // [m]
+    int32_t* s_type = s_src + m;                        // [m] 1 top, 2 dense, 3 bottom
     const double beta = P.e[jb.r_off + off + n1 - 1];
     const double sgn = beta >= 0.0 ? 1.0 : -1.0;
     const double rho = 2.0 * fabs(beta);
@@ -167,7 +175,8 @@ __global__ void __launch_bounds__(256) dc_deflate_kernel(DcParams P) {
         }
         const double zi = (i < n1) ? Qin[(size_t)i * ld + (n1 - 1)] : sgn * Qin[(size_t)i * ld + n1];
         const double zz = zi * 0.70710678118654752440;
-        ds[rank] = v; zs[rank] = zz; src[rank] = i;
+        s_ds[rank] = v; s_zs[rank] = zz; s_src[rank] = i; s_type[rank] = (i < n1) ? 1 : 3;
+        src[rank] = i;
         dmax = fmax(dmax, fabs(v)); zmax = fmax(zmax, fabs(zz));
     }
     // CTA max
@@ -180,33 +189,29 @@ __global__ void __launch_bounds__(256) dc_deflate_kernel(DcParams P) {
     dmax = 0.0; zmax = 0.0;
     for (int w = 0; w < 8; ++w) { dmax = fmax(dmax, red[w]); zmax = fmax(zmax, red[8 + w]); }
     const double tol = 8.0 * DC_EPS * fmax(dmax, zmax);
-    // (b) serial deflation scan (thread 0).  zs[i] = 0 marks a deflated pole afterwards; the type is kept
-    // in the sign-free integer array gmap (1 top, 2 dense, 3 bottom) until the maps are built.
-    int32_t* type = P.gmap + vb;
+    // (b) serial deflation scan (thread 0, on the shared-memory copy).  zs[i] = 0 marks a deflated pole afterwards.
     double* rot = P.rot + 4 * vb;
-    for (int i = tid; i < m; i += 256) type[i] = (src[i] < n1) ? 1 : 3;
-    __syncthreads();
     if (tid == 0) {
         int nrot = 0;
         if (rho * zmax <= tol) {
-            for (int i = 0; i < m; ++i) zs[i] = 0.0;
+            for (int i = 0; i < m; ++i) s_zs[i] = 0.0;
         } else {
             int pj = -1;
             for (int i = 0; i < m; ++i) {
-                if (rho * fabs(zs[i]) <= tol) { zs[i] = 0.0; continue; }
+                if (rho * fabs(s_zs[i]) <= tol) { s_zs[i] = 0.0; continue; }
                 if (pj >= 0) {
-                    double s = zs[pj], c = zs[i];
+                    double s = s_zs[pj], c = s_zs[i];
                     const double tt = hypot(c, s);
-                    const double t = ds[i] - ds[pj];
+                    const double t = s_ds[i] - s_ds[pj];
                     c /= tt; s = -s / tt;
                     if (fabs(t * c * s) <= tol) {
-                        zs[i] = tt; zs[pj] = 0.0;
-                        const double t2 = ds[pj] * c * c + ds[i] * s * s;
-                        ds[i] = ds[pj] * s * s + ds[i] * c * c;
-                        ds[pj] = t2;
-                        if (type[pj] != type[i]) { type[i] = 2; type[pj] = 2; }
+                        s_zs[i] = tt; s_zs[pj] = 0.0;
+                        const double t2 = s_ds[pj] * c * c + s_ds[i] * s * s;
+                        s_ds[i] = s_ds[pj] * s * s + s_ds[i] * c * c;
+                        s_ds[pj] = t2;
+                        if (s_type[pj] != s_type[i]) { s_type[i] = 2; s_type[pj] = 2; }
                         rot[4 * nrot] = c; rot[4 * nrot + 1] = s;
-                        rot[4 * nrot + 2] = (double)src[pj]; rot[4 * nrot + 3] = (double)src[i];
+                        rot[4 * nrot + 2] = (double)s_src[pj]; rot[4 * nrot + 3] = (double)s_src[i];
                         ++nrot;
                     }
                 }
@@ -216,6 +221,7 @@ __global__ void __launch_bounds__(256) dc_deflate_kernel(DcParams P) {
         nrot_s = nrot;
     }
     __syncthreads();
+    for (int i = tid; i < m; i += 256) { ds[i] = s_ds[i]; zs[i] = s_zs[i]; }       // the global copies other kernels read
     // (c) apply the rotations to the columns of Qin, in order
     const int nrot = nrot_s;
     for (int r = 0; r < nrot; ++r) {
@@ -233,19 +239,19 @@ __global__ void __launch_bounds__(256) dc_deflate_kernel(DcParams P) {
     if (tid == 0) {
         int k1 = 0, k2 = 0, k3 = 0;
         for (int i = 0; i < m; ++i)
-            if (zs[i] != 0.0) { const int t = type[i]; k1 += (t == 1); k2 += (t == 2); k3 += (t == 3); }
+            if (s_zs[i] != 0.0) { const int t = s_type[i]; k1 += (t == 1); k2 += (t == 2); k3 += (t == 3); }
         const int k = k1 + k2 + k3;
         int g1 = 0, g2 = k1, g3 = k1 + k2, s = 0, t = 0;
         double* dk = P.dk + vb; double* zk = P.zk + vb; double* dval = P.dval + vb;
         int32_t* colsrc = P.colsrc + vb; int32_t* dsrc = P.dsrc + vb; int32_t* gmap = P.gmap + vb;
         for (int i = 0; i < m; ++i) {
-            if (zs[i] != 0.0) {
-                const int ty = type[i];
+            if (s_zs[i] != 0.0) {
+                const int ty = s_type[i];
                 const int g = (ty == 1) ? g1++ : (ty == 2 ? g2++ : g3++);
-                dk[s] = ds[i]; zk[s] = zs[i]; colsrc[g] = src[i];
-                gmap[s] = g;          // s <= i, so type[] entries not yet read are never overwritten
+                dk[s] = s_ds[i]; zk[s] = s_zs[i]; colsrc[g] = s_src[i];
+                gmap[s] = g;
                 ++s;
-            } else { dsrc[t] = src[i]; dval[t] = ds[i]; ++t; }
+            } else { dsrc[t] = s_src[i]; dval[t] = s_ds[i]; ++t; }
         }
         st.k = k; st.k1 = k1; st.k2 = k2; st.k3 = k3; st.kneed = k; st.rho = rho;
     }
