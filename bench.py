@@ -430,7 +430,7 @@ def run_gpu(args, rank, world, local_rank):
             "frac": trd_gbs / hbm_peak if hbm_peak else None,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture of this same
             # workload (profiles/r01d_prof_trd_raw.csv): 1.841 TB + 67.2 GB per launch
-            "traffic": 1.908e12 if (args.shape == "ml-10m" and not use_bj and ctx.small_max == 80) else None,
+            "traffic": 1.908e12 if (args.shape == "ml-10m" and not use_bj and ctx.small_max <= 80) else None,
             "peak_source": hbm_src,
             "algorithmic_bytes_per_launch": trd_bytes, "avg_launch_ms": trd_ms,
             "algorithmic_bytes_per_unit": "1.375 n^3 per user (4/3 n^3 half-matrix symv stream + n^3/24 trailing update)",

@@ -21,7 +21,7 @@
 #define GSI_S_MAX_N (32 * GSI_S_MAX_EPT)
 // measured crossover (scripts/sweep_degree.py, profiles/r01b_degree_sweep.md): the Householder + D&C path is faster
 // than the CTA-resident Jacobi kernel from n ~ 80 on (2.1x at n = 128)
-#define GSI_SMALL_DEFAULT 80
+#define GSI_SMALL_DEFAULT 44     // measured crossover (profiles/r01k_degree_sweep.md): above it Householder + D&C wins
 
 // block Jacobi (large path): panels of M columns = two blocks of M/2; M is 64 (default) or 32
 // largest n on the Householder path: its tridiagonalisation kernel keeps two np-long vectors in shared memory
