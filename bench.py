@@ -450,7 +450,7 @@ def run_gpu(args, rank, world, local_rank):
         launches = int(sum(v["launches"] for v in timing.values()) // args.steps)
         # ---- CPU baseline on this box's host cores (bounded sample) ----
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:               # reported baseline: rank 0 at N = 1 only
             w_host = d_w.cpu().numpy()
             rate, desc, cores = cpu_reference_rate(w_host, offsets, items, budget_s=args.cpu_budget)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
