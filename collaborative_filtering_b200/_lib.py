@@ -54,6 +54,7 @@ SYMBOLS = {
     "gsi_predict_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 8 + [ctypes.c_int64, ctypes.c_void_p,
                                         ctypes.c_int64] + [ctypes.c_void_p] * 6),
     "gsi_predict_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 18),
+    "gsi_local_calc_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 10),
     "gsi_knn_build_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "gsi_knn_edges_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),

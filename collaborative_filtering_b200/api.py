@@ -190,6 +190,27 @@ class Context:
             _ptr(mask), _ptr(err), _ptr(kk), _ptr(pred), _ptr(status), _ptr(cols)))
         return dict(err=err, kk=kk, pred=pred, status=status, cols=cols)
 
+    def local_calc(self, offsets, items, ratings, pair_mask=None) -> dict:
+        """Per-movie variant (local_calc.cpp; gsi_local_calc_host): one prediction per (user, movie) test
+        rating given as a user CSR; the item graph is the weight table set with set_weights*.  Returns
+        arrays [nnz] aligned with ``items`` (status 4 = no line in the reference's out_res)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        items = np.ascontiguousarray(items, dtype=np.int32)
+        ratings = np.ascontiguousarray(ratings, dtype=np.float64)
+        nnz = int(offsets[-1])
+        assert len(items) == nnz and len(ratings) == nnz
+        mask = None if pair_mask is None else np.ascontiguousarray(pair_mask, dtype=np.uint8)
+        err = np.zeros(nnz, dtype=np.float32)
+        kk = np.zeros(nnz, dtype=np.int32)
+        pred = np.zeros(nnz, dtype=np.float64)
+        status = np.zeros(nnz, dtype=np.int32)
+        cols = np.zeros(nnz, dtype=np.int32)
+        w_lim = np.zeros(nnz, dtype=np.float64)
+        self._check(self._lib.gsi_local_calc_host(
+            self._h, len(offsets) - 1, _ptr(offsets), _ptr(items), _ptr(ratings), _ptr(mask),
+            _ptr(err), _ptr(kk), _ptr(pred), _ptr(status), _ptr(cols), _ptr(w_lim)))
+        return dict(err=err, kk=kk, pred=pred, status=status, cols=cols, w_lim=w_lim)
+
     # ---- knn chain (knn.cpp / knn2.cpp / knn3.cpp) ----
     def knn_build(self, offsets, items, ratings, rows: int, install_weights: bool = True):
         """knn2 over the TRAIN ratings (CSR by user).  Returns the out_fin_ edges (m1, m2, w float32)

@@ -20,6 +20,7 @@
 #include "kern_dc.cuh"
 #include "kern_bt.cuh"
 #include "kern_cheby.cuh"
+#include "kern_lc.cuh"
 
 static thread_local std::string g_tls_err;
 
@@ -568,6 +569,7 @@ static int run_large_chunk(gsi_ctx* ctx, const Job* jobs, int nj, const int32_t*
 }
 
 #include "hh_host.cuh"
+#include "lc_host.cuh"
 
 static int check_csr(gsi_ctx* ctx, int64_t nu, const int64_t* off, const int32_t* items) {
     if (off[0] != 0) return gsi_fail(ctx, GSI_ERR_INVALID, "offsets[0] must be 0");

@@ -1,0 +1,319 @@
+// Kernels of the per-MOVIE variant (local_calc.cpp:262-526): one local graph per movie (the
+// movie and its out-neighbours in the thresholded item graph), its normalised Laplacian L, P = L L^T, and per
+// (movie, test user) pair the exact cutoff w_lim = sigma_min(L[unrated rows, :]) = sqrt(lambda_min(P[unrated, unrated]))
+// followed by the band-limited least-squares prediction.  Both eigensolves (one per movie, one per pair) run on the
+// batched Householder / divide & conquer / back-transform pipeline of hh_host.cuh; the kernels here only build its
+// inputs (tile-major symmetric matrices) and consume its outputs.
+#pragma once
+#include "gsi_internal.cuh"
+#include "kern_trd.cuh"
+
+#define LC_PAD_N 48          // smallest matrix handed to the pipeline; smaller ones are extended by LC_PAD_DIAG * I
+#define LC_PAD_DIAG 8.0      // above every eigenvalue of L (<= 2) and of L_h L_h^T (<= 4)
+
+struct LcMovie {
+    int n;                   // nodes of the local graph, node 0 = the movie itself (local_calc.cpp:283-290)
+    int k;                   // kept eigenpairs (set by the host after the solve)
+    int64_t node_off;        // into nodes[] / scale[] / deg[] / lam[]
+    int64_t l_off;           // into L / P: n*n doubles, row-major
+    int64_t vec_off;         // into vec: n*k doubles, column-major, ld = n
+};
+
+struct LcFill {              // source of one pipeline job: value(r, c) = src[idx[max(r,c)] * ld + idx[min(r,c)]]
+    const double* src; const int32_t* idx;    // idx == nullptr: identity
+    int ld, n_real;
+};
+
+struct LcPair {
+    int movie;               // index into the chunk's LcMovie array
+    int kk;                  // known ratings: local nodes (other than node 0) this user rated
+    int64_t k_off;           // into kidx / krat
+    double real;             // the user's own rating of the movie (ground truth)
+};
+
+// Weight of the item-graph edge a -> b as local_calc sees it: graph_loader (local_calc.cpp:102-117) parses the
+// weight into a float, keeps the edge iff that float > 0.1 (double compare) and stores the float widened to double.
+__device__ __forceinline__ double lc_edge(const double* __restrict__ W, int rows, int a, int b) {
+    if (a == b || a >= rows || b >= rows || a < 0 || b < 0) return 0.0;
+    const float f = (float)W[(size_t)a * rows + b];
+    return ((double)f > 0.1) ? (double)f : 0.0;
+}
+
+// ww(i, j) of the local graph (local_calc.cpp:324-335): neighbour rows hold w(i -> j); row 0 AND column 0 hold
+// w(m -> i) (the "fix" of :331-333 overwrites whatever the neighbour loop left in column 0).
+__device__ __forceinline__ double lc_ww(const double* __restrict__ W, int rows, const int32_t* __restrict__ nd, int i, int j) {
+    if (i == j) return 0.0;
+    if (i == 0) return lc_edge(W, rows, nd[0], nd[j]);
+    if (j == 0) return lc_edge(W, rows, nd[0], nd[i]);
+    return lc_edge(W, rows, nd[i], nd[j]);
+}
+
+// ---- neighbour lists of the thresholded item graph ------------------------------------------------------------
+__global__ void lc_nbr_count_kernel(const double* __restrict__ W, int rows, int32_t* __restrict__ cnt) {
+    const int m = blockIdx.x;
+    int c = 0;
+    for (int j = threadIdx.x; j < rows; j += blockDim.x) c += lc_edge(W, rows, m, j) != 0.0;
+    __shared__ int red[32];
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+        cnt[m] = s;
+    }
+}
+
+// one warp per row, ordered compaction (ascending target id)
+__global__ void lc_nbr_fill_kernel(const double* __restrict__ W, int rows, const int64_t* __restrict__ off, int32_t* __restrict__ nbr) {
+    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= rows) return;
+    int64_t o = off[m];
+    for (int j0 = 0; j0 < rows; j0 += 32) {
+        const int j = j0 + lane;
+        const bool keep = j < rows && lc_edge(W, rows, m, j) != 0.0;
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
+        if (keep) nbr[o + __popc(b & ((1u << lane) - 1u))] = j;
+        o += __popc(b);
+    }
+}
+
+// ---- normalised Laplacian of every local graph of a chunk (local_calc.cpp:347-374) ------------------------------
+// d_i = sum_j ww(i, j), j ascending (:353-360); s_i = sqrt(1 / d_i) (dd.inverse() then elementwise sqrt, :368-372);
+// L_ij = fl(fl(s_i * (dd - ww)_ij) * s_j) (:364, :374).  Also the largest row norm of L as float bits: an upper bound
+// of every pair's cutoff (sigma_min of a row subset <= the norm of any of its rows), used to truncate the spectrum.
+__global__ void lc_laplacian_kernel(const LcMovie* __restrict__ movies, const int32_t* __restrict__ nodes,
+                                    const double* __restrict__ W, int rows, double* __restrict__ deg, double* __restrict__ scale,
+                                    double* __restrict__ L, unsigned int* __restrict__ sigmax) {
+    const LcMovie M = movies[blockIdx.x];
+    const int n = M.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int32_t* nd = nodes + M.node_off;
+    double* d = deg + M.node_off;
+    double* s = scale + M.node_off;
+    double* Lm = L + M.l_off;
+    __shared__ unsigned int smax;
+    if (tid == 0) smax = 0u;
+    for (int i = tid; i < n; i += blockDim.x) {
+        double acc = 0.0;
+        for (int j = 0; j < n; ++j) acc = __dadd_rn(acc, lc_ww(W, rows, nd, i, j));
+        d[i] = acc;
+        s[i] = sqrt(1.0 / acc);
+    }
+    __syncthreads();
+    for (int i = warp; i < n; i += nw) {
+        const double di = d[i], si = s[i];
+        double nrm = 0.0;
+        for (int j = lane; j < n; j += 32) {
+            const double ll = (i == j) ? di : -lc_ww(W, rows, nd, i, j);
+            const double v = __dmul_rn(__dmul_rn(si, ll), s[j]);
+            Lm[(size_t)i * n + j] = v;
+            nrm = fma(v, v, nrm);
+        }
+        for (int o = 16; o; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+        if (lane == 0) atomicMax(&smax, __float_as_uint(__double2float_ru(sqrt(nrm))));
+    }
+    __syncthreads();
+    if (tid == 0) sigmax[blockIdx.x] = smax;
+}
+
+// ---- P = L L^T (the matrix whose principal submatrices are L_h L_h^T, local_calc.cpp:435), lower tiles only ----
+#define LC_GT 64
+#define LC_GK 16
+__global__ void __launch_bounds__(256) lc_gram_kernel(const LcMovie* __restrict__ movies, const double* __restrict__ L, double* __restrict__ P) {
+    const LcMovie M = movies[blockIdx.z];
+    const int n = M.n, bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi || bi * LC_GT >= n) return;
+    const double* Lm = L + M.l_off;
+    double* Pm = P + M.l_off;
+    __shared__ double As[LC_GK][LC_GT + 1], Bs[LC_GK][LC_GT + 1];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int k0 = 0; k0 < n; k0 += LC_GK) {
+        for (int e = tid; e < LC_GT * LC_GK; e += 256) {
+            const int r = e / LC_GK, kq = e % LC_GK;
+            const int ra = bi * LC_GT + r, rb = bj * LC_GT + r, kc = k0 + kq;
+            As[kq][r] = (ra < n && kc < n) ? Lm[(size_t)ra * n + kc] : 0.0;
+            Bs[kq][r] = (rb < n && kc < n) ? Lm[(size_t)rb * n + kc] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kq = 0; kq < LC_GK; ++kq) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { av[a] = As[kq][ty * 4 + a]; bv[a] = Bs[kq][tx * 4 + a]; }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int r = bi * LC_GT + ty * 4 + a, c = bj * LC_GT + tx * 4 + b;
+            if (r < n && c < n) Pm[(size_t)r * n + c] = acc[a][b];
+        }
+}
+
+// ---- tile-major symmetric input of one pipeline job (the buffer is zero-initialised by hh_alloc) -----------------
+__global__ void __launch_bounds__(256) lc_fill_kernel(const HJob* __restrict__ jobs, const LcFill* __restrict__ fills, double* __restrict__ A) {
+    const HJob J = jobs[blockIdx.x];
+    const int NT = J.np >> 6, tr = blockIdx.y % NT, tc = blockIdx.y / NT;
+    if (blockIdx.y >= NT * NT || tr * 64 >= J.n || tc * 64 >= J.n) return;
+    const LcFill F = fills[blockIdx.x];
+    double* Aj = A + J.m_off;
+    const int r = tr * 64 + (threadIdx.x & 63);
+    for (int cc = threadIdx.x >> 6; cc < 64; cc += 4) {
+        const int c = tc * 64 + cc;
+        if (r >= J.n || c >= J.n) continue;
+        double v = 0.0;
+        if (r < F.n_real && c < F.n_real) {
+            const int hi = max(r, c), lo = min(r, c);
+            const int ih = F.idx ? F.idx[hi] : hi, il = F.idx ? F.idx[lo] : lo;
+            v = F.src[(size_t)ih * F.ld + il];
+        } else if (r == c) {
+            v = LC_PAD_DIAG;
+        }
+        Aj[hh_tidx(r, c, NT)] = v;
+    }
+}
+
+// ---- results of the per-movie solve: eigenvalues (all n) and the kept eigenvectors, padding rows dropped -------------
+__global__ void lc_take_kernel(const HJob* __restrict__ jobs, const LcMovie* __restrict__ movies, const double* __restrict__ Qa,
+                               const double* __restrict__ Qb, const double* __restrict__ lamA, const double* __restrict__ lamB,
+                               double* __restrict__ lam, double* __restrict__ vec) {
+    const HJob J = jobs[blockIdx.x];
+    const LcMovie M = movies[blockIdx.x];
+    const bool in_b = J.levels & 1;
+    const double* Q = (in_b ? Qb : Qa) + J.m_off;
+    const double* ls = (in_b ? lamB : lamA) + J.r_off;
+    for (int i = threadIdx.x; i < M.n; i += blockDim.x) lam[M.node_off + i] = ls[i];
+    const int64_t tot = (int64_t)M.n * M.k;
+    for (int64_t e = threadIdx.x; e < tot; e += blockDim.x) {
+        const int c = (int)(e / M.n), r = (int)(e % M.n);
+        vec[M.vec_off + e] = Q[(size_t)c * J.np + r];
+    }
+}
+
+// w_lim = sqrt(smallest eigenvalue of L_h L_h^T) (local_calc.cpp:435-436); sqrt of a negative rounding residue is NaN
+// there as well
+__global__ void lc_wlim_kernel(const HJob* __restrict__ jobs, int nj, const double* __restrict__ lamA, const double* __restrict__ lamB,
+                               double* __restrict__ w_lim) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nj) return;
+    const HJob J = jobs[j];
+    w_lim[j] = sqrt(((J.levels & 1) ? lamB : lamA)[J.r_off]);
+}
+
+// ---- prediction (local_calc.cpp:443-499) ---------------------------------------------------------------------------
+// lim = max(2, first lambda > w_lim) (:443-451); A = U[known rows, :lim], v = U[0, :lim] (:456-478); M = A^T A,
+// pred = v^T M^-1 A^T (r - mean) + mean (:484-491) as (G^-1 v) . (G^-1 rhs) with M = G G^T (Cholesky; pivot rule as in
+// predict2_kernel), clamp to [1, 5] and squared error (:494-499).  No column clean in this variant.
+// One CTA per pair at a time; A, M and the two right-hand sides live in a per-CTA global scratch (L2 resident).
+__global__ void __launch_bounds__(256) lc_predict_kernel(const LcPair* __restrict__ pairs, int npairs, const LcMovie* __restrict__ movies,
+                                                         const double* __restrict__ lam, const double* __restrict__ vec,
+                                                         const int32_t* __restrict__ kidx, const double* __restrict__ krat,
+                                                         const double* __restrict__ w_lim, double* scratch, size_t scratch_per_cta,
+                                                         float* __restrict__ err, double* __restrict__ pred, int32_t* __restrict__ status,
+                                                         int32_t* __restrict__ cols) {
+    __shared__ int s_lim;
+    __shared__ double s_mean;
+    const int tid = threadIdx.x;
+    double* base = scratch + (size_t)blockIdx.x * scratch_per_cta;
+    for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
+        const LcPair Pp = pairs[p];
+        const LcMovie M = movies[Pp.movie];
+        const int n = M.n, k = M.k, kk = Pp.kk;
+        const double* lm = lam + M.node_off;
+        const double* U = vec + M.vec_off;
+        const double wl = w_lim[p];
+        __syncthreads();
+        if (tid == 0) {
+            s_lim = k;
+            double sum = 0.0;
+            for (int t = 0; t < kk; ++t) sum += krat[Pp.k_off + t];
+            s_mean = sum / (double)kk;
+        }
+        __syncthreads();
+        for (int l = tid; l < k; l += blockDim.x)
+            if (lm[l] > wl) atomicMin(&s_lim, l);
+        __syncthreads();
+        const int lim = min(max(s_lim, 2), k);
+        const double mean = s_mean;
+        int st = GSI_PRED_OK;
+        double pr = mean;
+        if (kk == 0) {
+            st = GSI_PRED_EMPTY;                          // 0/0 -> NaN (:487)
+        } else if (kk < lim) {
+            st = GSI_PRED_UNDERDETERMINED;                // rank-deficient Gram: the mean of the known ratings
+        } else {
+            double* A = base;                             // kk x lim, row-major
+            double* Mm = A + (size_t)kk * lim;            // lim x lim, lower triangle used
+            double* y1 = Mm + (size_t)lim * lim;          // A^T (r - mean)
+            double* y2 = y1 + lim;                        // v
+            for (int e = tid; e < kk * lim; e += blockDim.x) {
+                const int t = e / lim, a = e % lim;
+                A[e] = U[(size_t)a * n + kidx[Pp.k_off + t]];
+            }
+            __syncthreads();
+            for (int e = tid; e < lim * lim; e += blockDim.x) {
+                const int a = e / lim, b = e % lim;
+                if (b > a) continue;
+                double acc = 0.0;
+                for (int t = 0; t < kk; ++t) acc = fma(A[(size_t)t * lim + a], A[(size_t)t * lim + b], acc);
+                Mm[e] = acc;
+            }
+            for (int a = tid; a < lim; a += blockDim.x) {
+                double acc = 0.0;
+                for (int t = 0; t < kk; ++t) acc = fma(A[(size_t)t * lim + a], krat[Pp.k_off + t] - mean, acc);
+                y1[a] = acc;
+                y2[a] = U[(size_t)a * n];
+            }
+            bool singular = false;
+            for (int j = 0; j < lim; ++j) {
+                __syncthreads();
+                const double piv = Mm[(size_t)j * lim + j];
+                if (!(piv > 1e-14)) { singular = true; break; }        // uniform across the CTA
+                const double dj = sqrt(piv), y1j = y1[j] / dj, y2j = y2[j] / dj;
+                __syncthreads();
+                for (int i = j + 1 + tid; i < lim; i += blockDim.x) {
+                    const double lij = Mm[(size_t)i * lim + j] / dj;
+                    Mm[(size_t)i * lim + j] = lij;
+                    y1[i] = fma(-lij, y1j, y1[i]);
+                    y2[i] = fma(-lij, y2j, y2[i]);
+                }
+                if (tid == 0) { y1[j] = y1j; y2[j] = y2j; }
+                __syncthreads();
+                const int w = lim - j - 1;
+                for (int e = tid; e < w * w; e += blockDim.x) {
+                    const int i = j + 1 + e / w, c = j + 1 + e % w;
+                    if (c <= i) Mm[(size_t)i * lim + c] = fma(-Mm[(size_t)i * lim + j], Mm[(size_t)c * lim + j], Mm[(size_t)i * lim + c]);
+                }
+            }
+            __syncthreads();
+            if (singular) {
+                st = GSI_PRED_SINGULAR;
+            } else if (tid == 0) {
+                double acc = 0.0;
+                for (int j = 0; j < lim; ++j) acc = fma(y1[j], y2[j], acc);
+                pr = acc + mean;
+            }
+        }
+        if (tid == 0) {
+            double pc = pr;
+            if (pc > 5.0) pc = 5.0;
+            if (pc < 1.0) pc = 1.0;
+            const double d = Pp.real - pc;
+            err[p] = (float)(d * d);
+            pred[p] = pr;
+            status[p] = st;
+            cols[p] = lim;
+        }
+    }
+}

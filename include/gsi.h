@@ -162,6 +162,26 @@ int gsi_predict_device(gsi_ctx* ctx, int64_t n_users, const int64_t* h_offsets, 
                        const uint8_t* pair_mask, float* d_err, int32_t* d_kk, double* d_pred,
                        int32_t* d_status, int32_t* d_cols, int64_t* n_pairs_done);
 
+/* ---- local_calc  (replaces vertex_program::gather/apply of the per-MOVIE variant, local_calc.cpp:246-526;
+ *      SURVEY.md 8f.2).  For every movie m that has test ratings: the local graph {m} + out-neighbours(m)
+ *      (edge a -> b iff (float)weights(a, b) > 0.1, carrying that float, graph_loader :102-117), its adjacency
+ *      with row and column 0 = w(m -> i) (:324-335), normalised Laplacian L (:347-374) and eigenpairs of the
+ *      lower triangle (:378); for every test user u of m: unrated nodes (incl. m itself) -> exact cutoff
+ *      w_lim = sqrt(lambda_min(L_h L_h^T)) with L_h = the unrated rows of L (:417-436), lim = max(2, first
+ *      lambda > w_lim) (:443-451), least squares on the rated rows of U[:, :lim] (:456-491), clamp, squared
+ *      error (:494-499).  No out_eigen_ records are involved; the item graph comes from gsi_set_weights_*.
+ *
+ * Test ratings are given per user in CSR form exactly as for gsi_predict_host (items need not be sorted,
+ * each (user, movie) at most once); rating 0 means "not rated" as in the reference (:406-413).  Outputs are
+ * [nnz], aligned with items: pair t = (user u, movie items[t]).  status GSI_PRED_SKIPPED marks pairs the
+ * reference emits no line for: masked out (pair_mask, --pct), movie id outside the table, or a local graph
+ * of fewer than 3 nodes (:271-272).  kk == 0 gives NaN (GSI_PRED_EMPTY); kk < lim (only possible through
+ * the max(.,2) rule) GSI_PRED_UNDERDETERMINED with pred = mean of the known ratings.  cols = lim.
+ * w_lim may be NULL.  Self edges of the table are ignored. */
+int gsi_local_calc_host(gsi_ctx* ctx, int64_t n_users, const int64_t* offsets, const int32_t* items,
+                        const double* ratings, const uint8_t* pair_mask, float* err, int32_t* kk,
+                        double* pred, int32_t* status, int32_t* cols, double* w_lim);
+
 /* ---- knn chain  (replaces the GraphLab vertex programs of knn.cpp:160-298, the edge transform
  *      weights_calc knn2.cpp:127-146 and knn_program / error_vertex_data knn3.cpp:185-256) ------ *
  *

@@ -381,6 +381,104 @@ def local_calc_precomp(user_data: dict, graph: dict, test_rat: dict, coldrop_sig
     return out
 
 
+# --------------------------------------------------------------------------------------
+# local_calc.cpp: the per-MOVIE variant.  One local graph per movie (the movie
+# and its out-neighbours), one eigensolve per movie, and per (movie, test user) pair the exact
+# cutoff sigma_min(L_h) from one more eigensolve.
+# --------------------------------------------------------------------------------------
+def item_graph_weights(fin_edges):
+    """graph_loader (local_calc.cpp:102-117): edge a -> b kept iff (float)w > 0.1; the edge carries
+    ``edge_data(weight)``, i.e. the FLOAT-rounded weight widened to double.  {a: {b: w}}."""
+    g: dict[int, dict] = {}
+    for a, b, w in fin_edges:
+        if edge_kept(w):
+            g.setdefault(int(a), {})[int(b)] = float(np.float32(w))
+    return g
+
+
+def local_graph(m: int, gw: dict):
+    """Adjacency of the local graph of movie ``m`` (local_calc.cpp:265-335).  Node 0 is m, nodes
+    1.. are its out-neighbours (hash order in the reference; ascending id here, B6).
+    ww(i, j) = w(i -> j) between neighbours (:326-330); weights to movies outside the local graph
+    land on column 0 through ``indices[]``'s default value and are overwritten (:331-333) by the
+    fix-up ww(0, i) = ww(i, 0) = w(m -> i).  Self edges are not part of the item graph (knn2 never
+    emits one) and are ignored."""
+    neigh = sorted(j for j in gw.get(m, {}) if j != m)
+    nodes = [m] + neigh
+    idx = {v: i for i, v in enumerate(nodes)}
+    n = len(nodes)
+    ww = np.zeros((n, n), dtype=np.float64)
+    for i in neigh:
+        for j2, w in gw.get(i, {}).items():
+            if j2 in idx and j2 != i and j2 != m:
+                ww[idx[i], idx[j2]] = w
+        ww[0, idx[i]] = gw[m][i]
+        ww[idx[i], 0] = gw[m][i]
+    return nodes, ww
+
+
+def local_calc_movie(m: int, gw: dict, test_rat: dict):
+    """vertex_program::apply for one movie, --pct 100 (local_calc.cpp:262-526).  Returns rows
+    (movie, user', err float32, kk, pred, status, lim, w_lim) in ascending user' order, or [] when
+    the local graph has fewer than 3 nodes (:271-272) or the movie has no test ratings."""
+    nodes, ww = local_graph(m, gw)
+    n = len(nodes)
+    users = sorted(test_rat.get(m, {}))
+    if n < 3 or not users:
+        return []
+    _, _, ll2 = normalized_laplacian(ww)                 # :347-374 (no zero degree: every row holds w(m -> i) > 0.1)
+    lam, uu = eig_lower(ll2)                             # :378
+    out = []
+    for u in users:
+        rat = np.array([float(test_rat.get(v, {}).get(u, 0.0)) for v in nodes])   # :305-321
+        rat_real = rat[0]
+        rat[0] = 0.0                                     # :405
+        unrated = rat == 0.0                             # :406-413
+        rated = ~unrated
+        kk = int(rated.sum())
+        ll2_h = ll2[unrated, :]                          # :420-431
+        with np.errstate(invalid="ignore"):
+            w_lim = float(np.sqrt(np.linalg.eigvalsh(ll2_h @ ll2_h.T).min()))     # :435-436
+        lim = cutoff(lam, w_lim)                         # :443-451 (NaN never compares greater: lim = n)
+        vv = uu[0, :lim]                                 # :456-478
+        uu_hh = uu[rated, :lim]
+        usr_rat = rat[rated]
+        status = PRED_OK
+        if kk == 0:
+            status, pred = PRED_EMPTY, float("nan")      # 0/0 :487
+        else:
+            mm = uu_hh.T @ uu_hh                         # :484-485
+            rat_mean = usr_rat.sum() / kk
+            rhs = uu_hh.T @ (usr_rat - rat_mean)
+            if kk < lim:
+                status = PRED_UNDERDETERMINED
+            try:
+                x = np.linalg.solve(mm, rhs)
+                if status == PRED_OK and np.linalg.cond(mm) > 1e8:
+                    status = PRED_SINGULAR
+            except np.linalg.LinAlgError:
+                x = np.full(lim, np.nan)
+                status = PRED_SINGULAR if status == PRED_OK else status
+            pred = float(vv @ x) + rat_mean              # :490-491
+        p = pred
+        if p > 5:                                        # :494-497
+            p = 5.0
+        if p < 1:
+            p = 1.0
+        err = (rat_real - p) ** 2                        # :499
+        out.append((m, u, np.float32(err), kk, pred, status, lim, w_lim))
+    return out
+
+
+def local_calc(fin_edges, test_rat: dict):
+    """Both engines of local_calc.cpp over every vertex (:614-648), ascending movie id."""
+    gw = item_graph_weights(fin_edges)
+    out = []
+    for m in sorted(test_rat):
+        out.extend(local_calc_movie(m, gw, test_rat))
+    return out
+
+
 def format_res(rows) -> str:
     """graph_writer::save_vertex (local_calc_precomp.cpp:393-404): "movie user' mse kk\\n"."""
     return "".join("%d %d %s %d\n" % (m, u, fmt_g(e), kk) for m, u, e, kk, *_ in rows)

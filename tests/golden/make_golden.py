@@ -161,9 +161,27 @@ def run_cheby_case(name, seed=31413 + 7, nv=48, density=0.25, ncoef=9):
     print(name, len(out), "vertices")
 
 
+def run_local_calc_case(name):
+    """Per-movie variant (local_calc.cpp) on the out_fin_ / out_test_rat_ texts of an existing case."""
+    d = os.path.join(HERE, name)
+    fin_rt = O.parse_fin(open(os.path.join(d, "out_fin_1_of_1")).read())
+    test_rt = O.parse_rat(open(os.path.join(d, "out_test_rat_1_of_1")).read())
+    rows = O.local_calc(fin_rt, test_rt)
+    open(os.path.join(d, "out_res_local_calc"), "w").write(O.format_res(rows))
+    np.savez_compressed(
+        os.path.join(d, "local_calc.npz"),
+        movie=np.array([r[0] for r in rows], dtype=np.int64), user=np.array([r[1] for r in rows], dtype=np.int64),
+        err=np.array([r[2] for r in rows], dtype=np.float32), kk=np.array([r[3] for r in rows], dtype=np.int32),
+        pred=np.array([r[4] for r in rows], dtype=np.float64), status=np.array([r[5] for r in rows], dtype=np.int32),
+        lim=np.array([r[6] for r in rows], dtype=np.int32), w_lim=np.array([r[7] for r in rows], dtype=np.float64))
+    print(name, "local_calc:", len(rows), "rows, rmse", O.rmse_of(rows))
+
+
 if __name__ == "__main__":
     run_cheby_case("cheby_small")
     rng = np.random.default_rng(31413)
     run_case("tiny_int", rng, half=False)
     run_case("tiny_half", rng, half=True, n_train=90, n_val=10, n_items=50)
     run_precompute_case("precompute_rand", rng)
+    run_local_calc_case("tiny_int")
+    run_local_calc_case("tiny_half")

@@ -1,0 +1,96 @@
+"""CPU tests of the oracle's restatement of the per-movie variant (local_calc.cpp:262-526):
+golden reproducibility, the reference's column-0 fix-up, and the identities the exact cutoff satisfies
+(w_lim is the smallest singular value of the unrated rows of L; it never exceeds the norm of any of those rows,
+which is what lets the GPU path truncate the per-movie spectrum at the largest row norm)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gsi_oracle as O
+
+
+def _random_case(seed, n_items=40, n_users=30, density=0.5):
+    rng = np.random.default_rng(seed)
+    fin = []
+    for a in range(1, n_items + 1):
+        for b in range(a + 1, n_items + 1):
+            if rng.random() < density:
+                w = float("%g" % np.float32(rng.uniform(0.05, 1.0)))
+                fin.append((a, b, w))
+                fin.append((b, a, w))
+    test = {}
+    for u in range(1, n_users + 1):
+        its = rng.choice(np.arange(1, n_items + 1), size=int(rng.integers(3, 15)), replace=False)
+        for m in its:
+            test.setdefault(int(m), {})[O.UIMAX - u] = float(rng.integers(1, 6))
+    return fin, test
+
+
+@pytest.mark.parametrize("case", ["tiny_int", "tiny_half"])
+def test_golden_reproducible(golden_dir, case):
+    d = os.path.join(golden_dir, case)
+    z = np.load(os.path.join(d, "local_calc.npz"))
+    fin = O.parse_fin(open(os.path.join(d, "out_fin_1_of_1")).read())
+    test_rat = O.parse_rat(open(os.path.join(d, "out_test_rat_1_of_1")).read())
+    rows = O.local_calc(fin, test_rat)
+    assert [r[0] for r in rows] == z["movie"].tolist() and [r[1] for r in rows] == z["user"].tolist()
+    assert [r[3] for r in rows] == z["kk"].tolist() and [r[5] for r in rows] == z["status"].tolist()
+    assert [r[6] for r in rows] == z["lim"].tolist()
+    ok = z["status"] == O.PRED_OK
+    assert np.abs(np.array([r[4] for r in rows])[ok] - z["pred"][ok]).max() <= 1e-9
+    assert np.abs(np.array([r[7] for r in rows])[ok] - z["w_lim"][ok]).max() <= 1e-12
+    assert O.format_res(rows) == open(os.path.join(d, "out_res_local_calc")).read()
+
+
+def test_local_graph_fixup_and_scope():
+    # 1 -> {2, 3}; 2 -> {1, 3, 9}; 3 -> {2}; 9 is outside the local graph of 1; weights deliberately asymmetric
+    fin = [(1, 2, 0.5), (1, 3, 0.7), (2, 1, 0.9), (2, 3, 0.3), (2, 9, 0.8), (3, 2, 0.4), (3, 1, 0.05), (9, 2, 0.8)]
+    gw = O.item_graph_weights(fin)
+    assert 1 not in gw[3]                                            # (float)0.05 > 0.1 is false: no edge
+    nodes, ww = O.local_graph(1, gw)
+    assert nodes == [1, 2, 3]
+    f = lambda x: float(np.float32(x))
+    expect = np.array([[0, f(0.5), f(0.7)], [f(0.5), 0, f(0.3)], [f(0.7), f(0.4), 0]])
+    assert np.array_equal(ww, expect)                                # column 0 = row 0 = w(1 -> i), local_calc.cpp:331-333
+    assert O.local_calc_movie(9, gw, {9: {5: 3.0}}) == []            # fewer than 3 nodes: no output (:271-272)
+
+
+@pytest.mark.parametrize("seed,density", [(1, 0.5), (2, 0.15), (3, 0.9)])
+def test_cutoff_identities(seed, density):
+    fin, test = _random_case(seed, density=density)
+    gw = O.item_graph_weights(fin)
+    seen = 0
+    for m in sorted(test):
+        nodes, ww = O.local_graph(m, gw)
+        if len(nodes) < 3:
+            continue
+        _, _, ll2 = O.normalized_laplacian(ww)
+        row_norm = np.sqrt((ll2 * ll2).sum(axis=1))
+        for (mm, u, err, kk, pred, status, lim, w_lim) in O.local_calc_movie(m, gw, test):
+            if kk == 0:
+                assert status == O.PRED_EMPTY and np.isnan(pred) and np.isnan(err)
+                continue
+            rated = np.array([v != m and u in test.get(v, {}) for v in nodes])
+            assert rated.sum() == kk
+            sv = np.linalg.svd(ll2[~rated, :], compute_uv=False)
+            assert abs(sv.min() - w_lim) <= 1e-7 * max(1.0, sv.min())
+            assert w_lim <= row_norm[~rated].min() + 1e-12
+            if lim > 2:
+                assert lim <= kk and status != O.PRED_UNDERDETERMINED       # uniqueness set: the Gram has full rank
+            seen += 1
+    assert seen > 20
+
+
+def test_asymmetric_table_is_tolerance_level():
+    """The reference reads whichever direction of an edge pair its hash order visits (lower triangle of a
+    non-symmetric ll2); a table whose directions differ at the 1e-3 level moves w_lim by about as much --
+    with the bit-symmetric weights knn2 produces the order is immaterial."""
+    fin, test = _random_case(5)
+    rng = np.random.default_rng(99)
+    fin_a = [(a, b, float("%g" % (w * (1.0 + 1e-3 * rng.standard_normal()))) if (a > b and w > 0.12) else w) for a, b, w in fin]
+    r0 = O.local_calc(fin, test)
+    r1 = O.local_calc(fin_a, test)
+    assert [(r[0], r[1], r[3]) for r in r0] == [(r[0], r[1], r[3]) for r in r1]
+    d = [abs(a[7] - b[7]) for a, b in zip(r0, r1) if a[3] > 0]
+    assert max(d) < 5e-2
