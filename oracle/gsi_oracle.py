@@ -419,8 +419,12 @@ def local_graph(m: int, gw: dict):
 
 def local_calc_movie(m: int, gw: dict, test_rat: dict):
     """vertex_program::apply for one movie, --pct 100 (local_calc.cpp:262-526).  Returns rows
-    (movie, user', err float32, kk, pred, status, lim, w_lim) in ascending user' order, or [] when
-    the local graph has fewer than 3 nodes (:271-272) or the movie has no test ratings."""
+    (movie, user', err float32, kk, pred, status, lim, w_lim, gap) in ascending user' order, or []
+    when the local graph has fewer than 3 nodes (:271-272) or the movie has no test ratings.
+    ``gap`` = lambda[lim] - lambda[lim-1] (inf when every eigenpair is used): when the cutoff -- usually
+    the max(.,2) rule -- falls inside a cluster of equal eigenvalues, U[:, :lim] depends on the
+    eigensolver's arbitrary basis of that cluster and so does the reference's own prediction; parity
+    tests compare predictions only where gap > 1e-6 (eigenvectors up to subspace rotation)."""
     nodes, ww = local_graph(m, gw)
     n = len(nodes)
     users = sorted(test_rat.get(m, {}))
@@ -466,7 +470,8 @@ def local_calc_movie(m: int, gw: dict, test_rat: dict):
         if p < 1:
             p = 1.0
         err = (rat_real - p) ** 2                        # :499
-        out.append((m, u, np.float32(err), kk, pred, status, lim, w_lim))
+        gap = float(lam[lim] - lam[lim - 1]) if lim < n else float("inf")
+        out.append((m, u, np.float32(err), kk, pred, status, lim, w_lim, gap))
     return out
 
 

@@ -173,7 +173,8 @@ def run_local_calc_case(name):
         movie=np.array([r[0] for r in rows], dtype=np.int64), user=np.array([r[1] for r in rows], dtype=np.int64),
         err=np.array([r[2] for r in rows], dtype=np.float32), kk=np.array([r[3] for r in rows], dtype=np.int32),
         pred=np.array([r[4] for r in rows], dtype=np.float64), status=np.array([r[5] for r in rows], dtype=np.int32),
-        lim=np.array([r[6] for r in rows], dtype=np.int32), w_lim=np.array([r[7] for r in rows], dtype=np.float64))
+        lim=np.array([r[6] for r in rows], dtype=np.int32), w_lim=np.array([r[7] for r in rows], dtype=np.float64),
+        gap=np.array([r[8] for r in rows], dtype=np.float64))
     print(name, "local_calc:", len(rows), "rows, rmse", O.rmse_of(rows))
 
 

@@ -37,7 +37,7 @@ def test_golden_reproducible(golden_dir, case):
     assert [r[0] for r in rows] == z["movie"].tolist() and [r[1] for r in rows] == z["user"].tolist()
     assert [r[3] for r in rows] == z["kk"].tolist() and [r[5] for r in rows] == z["status"].tolist()
     assert [r[6] for r in rows] == z["lim"].tolist()
-    ok = z["status"] == O.PRED_OK
+    ok = (z["status"] == O.PRED_OK) & (z["gap"] > 1e-6)
     assert np.abs(np.array([r[4] for r in rows])[ok] - z["pred"][ok]).max() <= 1e-9
     assert np.abs(np.array([r[7] for r in rows])[ok] - z["w_lim"][ok]).max() <= 1e-12
     assert O.format_res(rows) == open(os.path.join(d, "out_res_local_calc")).read()
@@ -67,7 +67,7 @@ def test_cutoff_identities(seed, density):
             continue
         _, _, ll2 = O.normalized_laplacian(ww)
         row_norm = np.sqrt((ll2 * ll2).sum(axis=1))
-        for (mm, u, err, kk, pred, status, lim, w_lim) in O.local_calc_movie(m, gw, test):
+        for (mm, u, err, kk, pred, status, lim, w_lim, gap) in O.local_calc_movie(m, gw, test):
             if kk == 0:
                 assert status == O.PRED_EMPTY and np.isnan(pred) and np.isnan(err)
                 continue

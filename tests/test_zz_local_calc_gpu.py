@@ -4,7 +4,8 @@ restatement of local_calc.cpp:262-526.
 Tolerances: kk and status classes exact (every pair the oracle classifies as well-posed must be GSI_PRED_OK);
 w_lim within 1e-8 (abs); lim exact unless an eigenvalue lies within 1e-7 of the cutoff (reported, at most 1 %
 of the pairs); pred within 1e-6 (abs) and RMSE within 1e-6 on the well-posed pairs with identical lim
-(north_star asks 1e-4).  Both sides use ascending neighbour order (B6).  The file sorts last on purpose: it
+(north_star asks 1e-4) whose cutoff does not split a cluster of equal eigenvalues (gap > 1e-6: inside a cluster
+the eigenvectors are defined up to rotation only, SURVEY.md 8c, and the reference's own answer is arbitrary).  Both sides use ascending neighbour order (B6).  The file sorts last on purpose: it
 exercises the newest entry point."""
 import os
 import shutil
@@ -58,8 +59,8 @@ def _run_and_compare(ctx, fin, test_rat, min_ok=10):
     emitted = {(r[0], r[1]) for r in rows}
     for key, t in pos.items():                      # pairs the reference writes no line for
         assert (out["status"][t] == 4) == (key not in emitted), key
-    n_ok, ties, se_g, se_o = 0, 0, 0.0, 0.0
-    for (m, u, err, kk, pred, status, lim, w_lim) in rows:
+    n_ok, ties, n_split, se_g, se_o = 0, 0, 0, 0.0, 0.0
+    for (m, u, err, kk, pred, status, lim, w_lim, gap) in rows:
         t = pos[(m, u)]
         assert out["kk"][t] == kk, (m, u)
         if status == O.PRED_EMPTY:
@@ -71,6 +72,9 @@ def _run_and_compare(ctx, fin, test_rat, min_ok=10):
             continue
         if status == O.PRED_UNDERDETERMINED:
             assert out["status"][t] == 2
+        if gap <= 1e-6:                              # the cutoff splits a cluster of equal eigenvalues: the prediction depends
+            n_split += 1                             # on the solver's arbitrary basis of that cluster (reference included)
+            continue
         if status == O.PRED_OK:
             assert out["status"][t] == 0, (m, u, out["status"][t])
             assert abs(out["pred"][t] - pred) <= 1e-6, (m, u, out["pred"][t], pred)
