@@ -145,7 +145,8 @@ struct HhTrace {
 // and everything smaller fills the other SMs behind them.
 static int hh_level_of(int np) { return np > 4096 ? 0 : (np > 2048 ? 1 : (np > 1024 ? 2 : 3)); }
 
-static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_team, bool defer_bt_apply = false) {
+// tridiagonalisation only (uses D.jobs, D.A, D.d, D.e, D.tau, D.ctl): A = Q T Q^T, T in (d, e), reflectors in A / tau
+static int hh_trd(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_team) {
     Workspace& ws = WS(ctx);
     cudaStream_t st = ctx->stream;
     const int nj = pl.nj;
@@ -278,6 +279,14 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
             cudaEventDestroy(ta); cudaEventDestroy(tb);
         }
     }
+    return GSI_OK;
+}
+
+static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_team, bool defer_bt_apply = false) {
+    cudaStream_t st = ctx->stream;
+    const int nj = pl.nj;
+    int rc;
+    if ((rc = hh_trd(ctx, pl, D, forced_team)) != GSI_OK) return rc;
     // ---------------- divide & conquer
     DcParams P;
     P.jobs = D.jobs; P.nodes = D.nodes; P.state = D.state; P.Qa = D.Qa; P.Qb = D.Qb; P.S = D.S; P.lamA = D.lamA; P.lamB = D.lamB;

@@ -1,9 +1,10 @@
 // Kernels of the per-MOVIE variant (local_calc.cpp:262-526): one local graph per movie (the
 // movie and its out-neighbours in the thresholded item graph), its normalised Laplacian L, P = L L^T, and per
 // (movie, test user) pair the exact cutoff w_lim = sigma_min(L[unrated rows, :]) = sqrt(lambda_min(P[unrated, unrated]))
-// followed by the band-limited least-squares prediction.  Both eigensolves (one per movie, one per pair) run on the
-// batched Householder / divide & conquer / back-transform pipeline of hh_host.cuh; the kernels here only build its
-// inputs (tile-major symmetric matrices) and consume its outputs.
+// followed by the band-limited least-squares prediction.  The per-movie eigensolve runs on the batched Householder /
+// divide & conquer / back-transform pipeline of hh_host.cuh, the per-pair one on its tridiagonalisation stage followed
+// by a Sturm-count bracket of the smallest eigenvalue; the kernels here build the pipeline's inputs (tile-major
+// symmetric matrices) and consume its outputs.
 #pragma once
 #include "gsi_internal.cuh"
 #include "kern_trd.cuh"
@@ -201,14 +202,55 @@ __global__ void lc_take_kernel(const HJob* __restrict__ jobs, const LcMovie* __r
     }
 }
 
-// w_lim = sqrt(smallest eigenvalue of L_h L_h^T) (local_calc.cpp:435-436); sqrt of a negative rounding residue is NaN
-// there as well
-__global__ void lc_wlim_kernel(const HJob* __restrict__ jobs, int nj, const double* __restrict__ lamA, const double* __restrict__ lamB,
-                               double* __restrict__ w_lim) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+// Smallest eigenvalue of the tridiagonal T = (d, e) of every job by multi-section on the Sturm count (the pair solves
+// need nothing else, so divide & conquer and the back-transform are skipped for them): one warp per job, each lane runs
+// the count recurrence q_i = d_i - x - e_{i-1}^2 / q_{i-1} (LAPACK dstebz pivmin safeguard) for its own x, the bracket
+// shrinks 33-fold per round from the Gershgorin interval.  w_lim = sqrt(lambda_min(L_h L_h^T)) (local_calc.cpp:435-436);
+// the sqrt of a negative rounding residue is NaN there as well.
+__global__ void __launch_bounds__(128) lc_tmin_kernel(const HJob* __restrict__ jobs, int nj, const double* __restrict__ dvec,
+                                                      const double* __restrict__ evec, double* __restrict__ w_lim) {
+    const int j = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (j >= nj) return;
     const HJob J = jobs[j];
-    w_lim[j] = sqrt(((J.levels & 1) ? lamB : lamA)[J.r_off]);
+    const int n = J.n;
+    const double* d = dvec + J.r_off;
+    const double* e = evec + J.r_off;
+    double lo = 1e300, hi = -1e300, emax = 0.0;
+    for (int i = lane; i < n; i += 32) {
+        const double el = i > 0 ? fabs(e[i - 1]) : 0.0, er = i < n - 1 ? fabs(e[i]) : 0.0;
+        lo = fmin(lo, d[i] - el - er);
+        hi = fmax(hi, d[i] + el + er);
+        emax = fmax(emax, er);
+    }
+    for (int o = 16; o; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+    }
+    const double pivmin = 2.2250738585072014e-308 * fmax(1.0, emax * emax);
+    const double span = fmax(fabs(lo), fabs(hi));
+    lo -= 2.0 * 2.220446049250313e-16 * span * n + 2.0 * pivmin;      // count(lo) == 0, count(hi) >= 1
+    hi += 2.0 * 2.220446049250313e-16 * span * n + 2.0 * pivmin;
+    for (int round = 0; round < 16; ++round) {
+        const double w = hi - lo;
+        if (!(w > 2.220446049250313e-16 * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin)) break;
+        const double x = lo + w * (double)(lane + 1) / 33.0;
+        double q = d[0] - x;
+        if (fabs(q) < pivmin) q = -pivmin;
+        int below = q < 0.0;
+        for (int i = 1; i < n && !below; ++i) {                          // only "is the count zero" matters
+            const double ei = e[i - 1];
+            q = d[i] - x - ei * ei / q;
+            if (fabs(q) < pivmin) q = -pivmin;
+            below = q < 0.0;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, below != 0);        // monotone in the lane (x ascending)
+        const int first = b ? __ffs(b) - 1 : 32;
+        const double nlo = first == 0 ? lo : __shfl_sync(0xffffffffu, x, first - 1 < 0 ? 0 : first - 1);
+        const double nhi = first == 32 ? hi : __shfl_sync(0xffffffffu, x, first > 31 ? 31 : first);
+        lo = nlo; hi = nhi;
+    }
+    if (lane == 0) w_lim[j] = sqrt(0.5 * (lo + hi));
 }
 
 // ---- prediction (local_calc.cpp:443-499) ---------------------------------------------------------------------------

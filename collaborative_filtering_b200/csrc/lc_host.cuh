@@ -5,7 +5,7 @@
 //   lc_laplacian -> L per movie            lc_fill + hh_solve -> eigenpairs of sym(lower(L)) up to max row norm + 0.01
 //   lc_gram      -> P = L L^T per movie
 // and per chunk of (movie, user) pairs of those movies (most unrated nodes first):
-//   lc_fill (gather P[unrated, unrated]) + hh_solve -> smallest eigenvalue -> w_lim        lc_predict -> err / pred
+//   lc_fill (gather P[unrated, unrated]) + hh_trd + lc_tmin -> smallest eigenvalue -> w_lim        lc_predict -> err / pred
 #pragma once
 
 struct LcArena {              // device allocations that live until the end of the call / of a chunk
@@ -31,9 +31,10 @@ struct LcArena {              // device allocations that live until the end of t
 
 struct LcLight { int movie; int32_t user; int64_t t; int kk; int n_unr; };     // a pair before its index lists are built
 
-// pipeline input for `fills.size()` jobs (already sorted by n descending), solve, leave the results in D
+// pipeline input for `fills.size()` jobs (already sorted by n descending), full solve with the cutoff at
+// (float)(sigmax + 0.01) per job, results left in D
 static int lc_solve(gsi_ctx* ctx, const std::vector<Job>& jobs, const std::vector<LcFill>& fills, const unsigned int* d_sigmax,
-                    float sigmax_const, LcArena& ar, HhPlan& pl, HhDev& D) {
+                    LcArena& ar, HhPlan& pl, HhDev& D) {
     cudaStream_t st = ctx->stream;
     const int nj = (int)jobs.size();
     int rc;
@@ -44,12 +45,7 @@ static int lc_solve(gsi_ctx* ctx, const std::vector<Job>& jobs, const std::vecto
     const int NT = pl.npmax >> 6;
     lc_fill_kernel<<<dim3(nj, NT * NT), 256, 0, st>>>(D.jobs, d_fills, D.A);
     GSI_CUDA(ctx, cudaGetLastError());
-    if (d_sigmax) {
-        GSI_CUDA(ctx, cudaMemcpyAsync(D.sigmax, d_sigmax, (size_t)nj * 4, cudaMemcpyDeviceToDevice, st));
-    } else {
-        std::vector<float> sm(nj, sigmax_const);
-        GSI_CUDA(ctx, cudaMemcpyAsync(D.sigmax, sm.data(), (size_t)nj * 4, cudaMemcpyHostToDevice, st));
-    }
+    GSI_CUDA(ctx, cudaMemcpyAsync(D.sigmax, d_sigmax, (size_t)nj * 4, cudaMemcpyDeviceToDevice, st));
     return hh_solve(ctx, pl, D, 0);
 }
 
@@ -164,7 +160,7 @@ extern "C" int gsi_local_calc_host(gsi_ctx* ctx, int64_t nu, const int64_t* offs
                 fills[j] = LcFill{d_L + movies[j].l_off, nullptr, movies[j].n, movies[j].n};
             }
             HhPlan pl; HhDev D;
-            if ((rc = lc_solve(ctx, jobs, fills, d_sig, 0.f, ch, pl, D)) != GSI_OK) return rc;
+            if ((rc = lc_solve(ctx, jobs, fills, d_sig, ch, pl, D)) != GSI_OK) return rc;
             std::vector<int32_t> h_k(nm);
             GSI_CUDA(ctx, cudaMemcpyAsync(h_k.data(), D.kuser, (size_t)nm * 4, cudaMemcpyDeviceToHost, st));
             GSI_CUDA(ctx, cudaStreamSynchronize(st));
@@ -214,9 +210,9 @@ extern "C" int gsi_local_calc_host(gsi_ctx* ctx, int64_t nu, const int64_t* offs
         while (pb < light.size()) {
             size_t pe = pb;
             int64_t pused = 0;
-            while (pe < light.size() && pe - pb < 4096) {
+            while (pe < light.size() && pe - pb < 16384) {
                 const int64_t c = npad(light[pe].n_unr) * npad(light[pe].n_unr);
-                if (pe > pb && pused + c > budget) break;
+                if (pe > pb && pused + c > 4 * budget) break;
                 pused += c; ++pe;
             }
             const int np_ = (int)(pe - pb);
@@ -256,7 +252,9 @@ extern "C" int gsi_local_calc_host(gsi_ctx* ctx, int64_t nu, const int64_t* offs
             if ((rc = pc.alloc(ctx, &d_err, (size_t)np_)) != GSI_OK) return rc;
             if ((rc = pc.alloc(ctx, &d_status, (size_t)np_)) != GSI_OK) return rc;
             if ((rc = pc.alloc(ctx, &d_cols, (size_t)np_)) != GSI_OK) return rc;
-            {   // exact cutoff: smallest eigenvalue of L_h L_h^T = P[unrated, unrated] (:417-436); two vectors kept
+            {   // exact cutoff: smallest eigenvalue of L_h L_h^T = P[unrated, unrated] (:417-436).  Only that one value is
+                // needed, so a pair job is tridiagonalised (the input matrix is its only np^2 buffer) and the smallest
+                // eigenvalue of T is bracketed on the Sturm count; divide & conquer and back-transform are skipped.
                 std::vector<Job> jobs(np_);
                 std::vector<LcFill> fills(np_);
                 for (int p = 0; p < np_; ++p) {
@@ -264,9 +262,23 @@ extern "C" int gsi_local_calc_host(gsi_ctx* ctx, int64_t nu, const int64_t* offs
                     jobs[p] = Job{p, std::max(light[pb + p].n_unr, LC_PAD_N), 0};
                     fills[p] = LcFill{d_P + M.l_off, d_uidx + u_off[p], M.n, light[pb + p].n_unr};
                 }
-                HhPlan pl; HhDev D;
-                if ((rc = lc_solve(ctx, jobs, fills, nullptr, -1.0f, pc, pl, D)) != GSI_OK) return rc;
-                lc_wlim_kernel<<<(np_ + 127) / 128, 128, 0, st>>>(D.jobs, np_, D.lamA, D.lamB, d_wl);
+                HhPlan pl;
+                hh_build_plan(jobs.data(), np_, pl);
+                HhDev D;
+                memset(&D, 0, sizeof D);
+                HJob* d_jobs; LcFill* d_fills; double *d_A, *d_tv; int* d_ctl;
+                if ((rc = pc.upload(ctx, &d_jobs, pl.jobs)) != GSI_OK) return rc;
+                if ((rc = pc.upload(ctx, &d_fills, fills)) != GSI_OK) return rc;
+                if ((rc = pc.alloc(ctx, &d_A, (size_t)pl.mtot)) != GSI_OK) return rc;
+                if ((rc = pc.alloc(ctx, &d_tv, (size_t)pl.rtot * 3)) != GSI_OK) return rc;
+                if ((rc = pc.alloc(ctx, &d_ctl, (size_t)HH_CTL_INTS)) != GSI_OK) return rc;
+                GSI_CUDA(ctx, cudaMemsetAsync(d_A, 0, (size_t)pl.mtot * 8, st));
+                D.jobs = d_jobs; D.A = d_A; D.d = d_tv; D.e = d_tv + pl.rtot; D.tau = d_tv + 2 * pl.rtot; D.ctl = d_ctl;
+                const int NT = pl.npmax >> 6;
+                lc_fill_kernel<<<dim3(np_, NT * NT), 256, 0, st>>>(D.jobs, d_fills, D.A);
+                GSI_CUDA(ctx, cudaGetLastError());
+                if ((rc = hh_trd(ctx, pl, D, 0)) != GSI_OK) return rc;
+                lc_tmin_kernel<<<(np_ + 3) / 4, 128, 0, st>>>(D.jobs, np_, D.d, D.e, d_wl);
                 GSI_CUDA(ctx, cudaGetLastError());
             }
             const size_t per_cta = capA + capM;
