@@ -117,7 +117,8 @@ __global__ void lc_laplacian_kernel(const LcMovie* __restrict__ movies, const in
     if (tid == 0) sigmax[blockIdx.x] = smax;
 }
 
-// ---- P = L L^T (the matrix whose principal submatrices are L_h L_h^T, local_calc.cpp:435), lower tiles only ----
+// ---- P = L L^T (the matrix whose principal submatrices are L_h L_h^T, local_calc.cpp:435): lower tiles computed,
+// both triangles written ----
 #define LC_GT 64
 #define LC_GK 16
 __global__ void __launch_bounds__(256) lc_gram_kernel(const LcMovie* __restrict__ movies, const double* __restrict__ L, double* __restrict__ P) {
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(256) lc_gram_kernel(const LcMovie* __restrict_
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int r = bi * LC_GT + ty * 4 + a, c = bj * LC_GT + tx * 4 + b;
-            if (r < n && c < n) Pm[(size_t)r * n + c] = acc[a][b];
+            if (r < n && c < n) { Pm[(size_t)r * n + c] = acc[a][b]; Pm[(size_t)c * n + r] = acc[a][b]; }
         }
 }
 
@@ -202,19 +203,10 @@ __global__ void lc_take_kernel(const HJob* __restrict__ jobs, const LcMovie* __r
     }
 }
 
-// Smallest eigenvalue of the tridiagonal T = (d, e) of every job by multi-section on the Sturm count (the pair solves
-// need nothing else, so divide & conquer and the back-transform are skipped for them): one warp per job, each lane runs
-// the count recurrence q_i = d_i - x - e_{i-1}^2 / q_{i-1} (LAPACK dstebz pivmin safeguard) for its own x, the bracket
-// shrinks 33-fold per round from the Gershgorin interval.  w_lim = sqrt(lambda_min(L_h L_h^T)) (local_calc.cpp:435-436);
-// the sqrt of a negative rounding residue is NaN there as well.
-__global__ void __launch_bounds__(128) lc_tmin_kernel(const HJob* __restrict__ jobs, int nj, const double* __restrict__ dvec,
-                                                      const double* __restrict__ evec, double* __restrict__ w_lim) {
-    const int j = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (j >= nj) return;
-    const HJob J = jobs[j];
-    const int n = J.n;
-    const double* d = dvec + J.r_off;
-    const double* e = evec + J.r_off;
+// Smallest eigenvalue of a symmetric tridiagonal T = (d[0..n), e[0..n-1)) by multi-section on the Sturm count, one warp:
+// each lane runs the count recurrence q_i = d_i - x - e_{i-1}^2 / q_{i-1} (LAPACK dstebz pivmin safeguard) for its own x,
+// the bracket shrinks 33-fold per round from the Gershgorin interval.  Every lane returns the same value.
+__device__ __forceinline__ double lc_warp_tmin(const double* d, const double* e, int n, int lane) {
     double lo = 1e300, hi = -1e300, emax = 0.0;
     for (int i = lane; i < n; i += 32) {
         const double el = i > 0 ? fabs(e[i - 1]) : 0.0, er = i < n - 1 ? fabs(e[i]) : 0.0;
@@ -250,7 +242,105 @@ __global__ void __launch_bounds__(128) lc_tmin_kernel(const HJob* __restrict__ j
         const double nhi = first == 32 ? hi : __shfl_sync(0xffffffffu, x, first > 31 ? 31 : first);
         lo = nlo; hi = nhi;
     }
-    if (lane == 0) w_lim[j] = sqrt(0.5 * (lo + hi));
+    return 0.5 * (lo + hi);
+}
+
+// Exact path of the pair solves: the job has been tridiagonalised (hh_trd), its one needed eigenvalue is the smallest
+// one of T -- divide & conquer and the back-transform are skipped.  w_lim = sqrt(lambda_min(L_h L_h^T))
+// (local_calc.cpp:435-436); the sqrt of a negative rounding residue is NaN there as well.
+__global__ void __launch_bounds__(128) lc_tmin_kernel(const HJob* __restrict__ jobs, int nj, const double* __restrict__ dvec,
+                                                      const double* __restrict__ evec, double* __restrict__ w_lim) {
+    const int j = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= nj) return;
+    const HJob J = jobs[j];
+    const double t = lc_warp_tmin(dvec + J.r_off, evec + J.r_off, J.n, lane);
+    if (lane == 0) w_lim[j] = sqrt(t);
+}
+
+// Fast path of the pair solves: Lanczos on G = P[unrated, unrated] without ever forming G.  All pairs of a movie share
+// the movie's P (L2 resident); a CTA iterates on a full-length vector that is zero on the rated nodes, so one step is a
+// dense, coalesced n x n GEMV with P plus the mask.  The smallest eigenvector of G is close to the positive vector
+// D^(1/2) 1 restricted to the unrated nodes, hence the constant start vector; on the ML-100K shape the smallest Ritz value
+// is converged to 1e-15 after 8-24 steps.  The Ritz value is the smallest eigenvalue of the Lanczos tridiagonal
+// (lc_warp_tmin), checked every 4 steps; a pair is done when it stops moving (|d theta| <= 1e-14 max(1, theta)), when the
+// Krylov space is exhausted (beta ~ 0 or as many steps as unrated nodes), and is handed to the exact path (conv = 0) when
+// neither happens within LC_LZ_MAX steps.
+#define LC_LZ_MAX 96
+__device__ __forceinline__ double lc_block_sum(double v, double* red) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w];
+    return s;
+}
+
+__global__ void __launch_bounds__(256) lc_lanczos_kernel(const LcPair* __restrict__ pairs, int npairs, const LcMovie* __restrict__ movies,
+                                                         const double* __restrict__ P, const int32_t* __restrict__ kidx, int nmax,
+                                                         double* __restrict__ w_lim, int32_t* __restrict__ conv) {
+    extern __shared__ double lz_sm[];
+    double* q = lz_sm;                  // [nmax] current Lanczos vector (zero on the rated nodes)
+    double* qp = q + nmax;              // [nmax] previous one
+    double* w = qp + nmax;              // [nmax]
+    unsigned char* mask = (unsigned char*)(w + nmax);     // [nmax] 1 = unrated
+    __shared__ double alpha_s[LC_LZ_MAX], beta_s[LC_LZ_MAX], red[8], theta_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
+        const LcPair Pp = pairs[p];
+        const LcMovie M = movies[Pp.movie];
+        const int n = M.n, n_unr = n - Pp.kk;
+        const double* Pm = P + M.l_off;
+        __syncthreads();
+        for (int i = tid; i < n; i += 256) mask[i] = 1;
+        __syncthreads();
+        for (int t = tid; t < Pp.kk; t += 256) mask[kidx[Pp.k_off + t]] = 0;
+        __syncthreads();
+        const double q0 = 1.0 / sqrt((double)n_unr);
+        for (int i = tid; i < n; i += 256) { q[i] = mask[i] ? q0 : 0.0; qp[i] = 0.0; }
+        __syncthreads();
+        const int kmax = min(LC_LZ_MAX, n_unr);
+        double beta_prev = 0.0, theta = 0.0, theta_old = 1e300;
+        int done = 0;
+        for (int k = 0; k < kmax; ++k) {
+            for (int a = warp; a < n; a += 8) {                      // w = mask (P q) - beta_prev * q_prev
+                double acc = 0.0;
+                if (mask[a]) {
+                    const double* row = Pm + (size_t)a * n;
+                    for (int j = lane; j < n; j += 32) acc = fma(row[j], q[j], acc);
+                    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    acc -= beta_prev * qp[a];
+                }
+                if (lane == 0) w[a] = acc;
+            }
+            __syncthreads();
+            double part = 0.0;
+            for (int i = tid; i < n; i += 256) part = fma(q[i], w[i], part);
+            const double alpha = lc_block_sum(part, red);
+            part = 0.0;
+            for (int i = tid; i < n; i += 256) { const double v = w[i] - alpha * q[i]; w[i] = v; part = fma(v, v, part); }
+            const double beta = sqrt(lc_block_sum(part, red));
+            if (tid == 0) { alpha_s[k] = alpha; beta_s[k] = beta; }
+            const bool exhausted = (k == n_unr - 1) || !(beta > 1e-14 * (fabs(alpha) + beta_prev));
+            const bool check = exhausted || (k + 1 >= 8 && ((k + 1) & 3) == 0);
+            if (check) {
+                __syncthreads();
+                if (warp == 0) {
+                    const double t = lc_warp_tmin(alpha_s, beta_s, k + 1, lane);
+                    if (lane == 0) theta_s = t;
+                }
+                __syncthreads();
+                theta = theta_s;
+                if (exhausted || fabs(theta_old - theta) <= 1e-14 * fmax(1.0, fabs(theta))) { done = 1; break; }
+                theta_old = theta;
+            }
+            for (int i = tid; i < n; i += 256) { const double v = q[i]; q[i] = w[i] / beta; qp[i] = v; }
+            beta_prev = beta;
+            __syncthreads();
+        }
+        if (tid == 0) { w_lim[p] = sqrt(theta); conv[p] = done; }
+    }
 }
 
 // ---- prediction (local_calc.cpp:443-499) ---------------------------------------------------------------------------

@@ -5,7 +5,10 @@
 //   lc_laplacian -> L per movie            lc_fill + hh_solve -> eigenpairs of sym(lower(L)) up to max row norm + 0.01
 //   lc_gram      -> P = L L^T per movie
 // and per chunk of (movie, user) pairs of those movies (most unrated nodes first):
-//   lc_fill (gather P[unrated, unrated]) + hh_trd + lc_tmin -> smallest eigenvalue -> w_lim        lc_predict -> err / pred
+//   fast path   lc_lanczos: smallest Ritz value of P[unrated, unrated] through the movie's P        -> w_lim
+//   exact path  lc_fill (gather P[unrated, unrated]) + hh_trd + lc_tmin (pairs the fast path gives up on, GSI_LC_EXACT=1,
+//               local graphs too big for the fast path's shared memory)                              -> w_lim
+//   lc_predict -> err / pred
 #pragma once
 
 struct LcArena {              // device allocations that live until the end of the call / of a chunk
@@ -205,17 +208,9 @@ extern "C" int gsi_local_calc_host(gsi_ctx* ctx, int64_t nu, const int64_t* offs
             }
             for (int i = 0; i < n; ++i) pos[nodes[movies[j].node_off + i]] = -1;
         }
-        std::stable_sort(light.begin(), light.end(), [](const LcLight& a, const LcLight& b) { return a.n_unr > b.n_unr; });
-        size_t pb = 0;
-        while (pb < light.size()) {
-            size_t pe = pb;
-            int64_t pused = 0;
-            while (pe < light.size() && pe - pb < 16384) {
-                const int64_t c = npad(light[pe].n_unr) * npad(light[pe].n_unr);
-                if (pe > pb && pused + c > 4 * budget) break;
-                pused += c; ++pe;
-            }
-            const int np_ = (int)(pe - pb);
+        // one batch of pairs: index lists, cutoff (Lanczos fast path or exact tridiagonalisation), prediction, results
+        const size_t lz_smem = (size_t)nmax * 25 + 64;
+        auto run_pairs = [&](const LcLight* lp, int np_, bool exact, std::vector<LcLight>* retry) -> int {
             LcArena pc;
             std::vector<LcPair> pairs(np_);
             std::vector<int32_t> kidx, uidx;
@@ -223,7 +218,7 @@ extern "C" int gsi_local_calc_host(gsi_ctx* ctx, int64_t nu, const int64_t* offs
             std::vector<int64_t> u_off(np_);
             size_t capA = 1, capM = 1;
             for (int p = 0; p < np_; ++p) {
-                const LcLight& Lp = light[pb + p];
+                const LcLight& Lp = lp[p];
                 const LcMovie& M = movies[Lp.movie];
                 for (int i = 0; i < M.n; ++i) pos[nodes[M.node_off + i]] = i;
                 pairs[p] = LcPair{Lp.movie, Lp.kk, (int64_t)kidx.size(), ratings[Lp.t]};
@@ -235,7 +230,7 @@ extern "C" int gsi_local_calc_host(gsi_ctx* ctx, int64_t nu, const int64_t* offs
                 size_t q = 0;
                 for (int i = 0; i < M.n; ++i) {
                     if (q < known.size() && known[q].first == i) { kidx.push_back(i); krat.push_back(known[q].second); ++q; }
-                    else uidx.push_back(i);
+                    else if (exact) uidx.push_back(i);
                 }
                 for (int i = 0; i < M.n; ++i) pos[nodes[M.node_off + i]] = -1;
                 const size_t lm = (size_t)std::min(Lp.kk, M.k);
@@ -252,15 +247,23 @@ extern "C" int gsi_local_calc_host(gsi_ctx* ctx, int64_t nu, const int64_t* offs
             if ((rc = pc.alloc(ctx, &d_err, (size_t)np_)) != GSI_OK) return rc;
             if ((rc = pc.alloc(ctx, &d_status, (size_t)np_)) != GSI_OK) return rc;
             if ((rc = pc.alloc(ctx, &d_cols, (size_t)np_)) != GSI_OK) return rc;
-            {   // exact cutoff: smallest eigenvalue of L_h L_h^T = P[unrated, unrated] (:417-436).  Only that one value is
+            int32_t* d_conv = nullptr;
+            if (!exact) {   // fast path: Lanczos on P[unrated, unrated] through the movie's P, no per-pair matrix (kern_lc.cuh)
+                if ((rc = pc.alloc(ctx, &d_conv, (size_t)np_)) != GSI_OK) return rc;
+                GSI_CUDA(ctx, cudaFuncSetAttribute(lc_lanczos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz_smem));
+                const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / lz_smem));
+                lc_lanczos_kernel<<<std::min(np_, per_sm * ctx->sm_count), 256, lz_smem, st>>>(d_pairs, np_, d_movies, d_P, d_kidx, nmax, d_wl, d_conv);
+                GSI_CUDA(ctx, cudaGetLastError());
+            }
+            if (exact) {   // exact cutoff: smallest eigenvalue of L_h L_h^T = P[unrated, unrated] (:417-436).  Only that one value is
                 // needed, so a pair job is tridiagonalised (the input matrix is its only np^2 buffer) and the smallest
                 // eigenvalue of T is bracketed on the Sturm count; divide & conquer and back-transform are skipped.
                 std::vector<Job> jobs(np_);
                 std::vector<LcFill> fills(np_);
                 for (int p = 0; p < np_; ++p) {
                     const LcMovie& M = movies[pairs[p].movie];
-                    jobs[p] = Job{p, std::max(light[pb + p].n_unr, LC_PAD_N), 0};
-                    fills[p] = LcFill{d_P + M.l_off, d_uidx + u_off[p], M.n, light[pb + p].n_unr};
+                    jobs[p] = Job{p, std::max(lp[p].n_unr, LC_PAD_N), 0};
+                    fills[p] = LcFill{d_P + M.l_off, d_uidx + u_off[p], M.n, lp[p].n_unr};
                 }
                 HhPlan pl;
                 hh_build_plan(jobs.data(), np_, pl);
@@ -296,12 +299,37 @@ extern "C" int gsi_local_calc_host(gsi_ctx* ctx, int64_t nu, const int64_t* offs
             GSI_CUDA(ctx, cudaMemcpyAsync(h_wl.data(), d_wl, (size_t)np_ * 8, cudaMemcpyDeviceToHost, st));
             GSI_CUDA(ctx, cudaMemcpyAsync(h_status.data(), d_status, (size_t)np_ * 4, cudaMemcpyDeviceToHost, st));
             GSI_CUDA(ctx, cudaMemcpyAsync(h_cols.data(), d_cols, (size_t)np_ * 4, cudaMemcpyDeviceToHost, st));
+            std::vector<int32_t> h_conv(np_, 1);
+            if (d_conv) GSI_CUDA(ctx, cudaMemcpyAsync(h_conv.data(), d_conv, (size_t)np_ * 4, cudaMemcpyDeviceToHost, st));
             GSI_CUDA(ctx, cudaStreamSynchronize(st));
             for (int p = 0; p < np_; ++p) {
-                const int64_t t0 = light[pb + p].t;
+                if (!h_conv[p]) { retry->push_back(lp[p]); continue; }       // not converged: the exact path decides
+                const int64_t t0 = lp[p].t;
                 err[t0] = h_err[p]; pred[t0] = h_pred[p]; status[t0] = h_status[p]; cols[t0] = h_cols[p];
                 if (w_lim) w_lim[t0] = h_wl[p];
             }
+            return GSI_OK;
+        };
+        const char* fe = getenv("GSI_LC_EXACT");               // GSI_LC_EXACT=1: every pair takes the exact path (tests, comparison)
+        const bool lanczos = !(fe && atoi(fe) != 0) && lz_smem <= 200 * 1024;
+        std::vector<LcLight> retry;
+        if (lanczos) {                                          // movie order: the pairs of a movie share its P in L2
+            for (size_t pb = 0; pb < light.size(); pb += 32768)
+                if ((rc = run_pairs(light.data() + pb, (int)std::min<size_t>(32768, light.size() - pb), false, &retry)) != GSI_OK) return rc;
+        } else {
+            retry.swap(light);
+        }
+        std::stable_sort(retry.begin(), retry.end(), [](const LcLight& a, const LcLight& b) { return a.n_unr > b.n_unr; });
+        size_t pb = 0;
+        while (pb < retry.size()) {
+            size_t pe = pb;
+            int64_t pused = 0;
+            while (pe < retry.size() && pe - pb < 16384) {
+                const int64_t c = npad(retry[pe].n_unr) * npad(retry[pe].n_unr);
+                if (pe > pb && pused + c > 4 * budget) break;
+                pused += c; ++pe;
+            }
+            if ((rc = run_pairs(retry.data() + pb, (int)(pe - pb), true, nullptr)) != GSI_OK) return rc;
             pb = pe;
         }
         GSI_CUDA(ctx, cudaStreamSynchronize(st));

@@ -123,6 +123,28 @@ def test_random(ctx, seed, n_items, n_users, density, lo, hi):
     _run_and_compare(ctx, fin, test, min_ok=50)
 
 
+@pytest.mark.parametrize("which", ["golden", "random"])
+def test_exact_path(ctx, golden_dir, monkeypatch, which):
+    """GSI_LC_EXACT=1 sends every pair through the tridiagonalisation + Sturm bracket instead of the Lanczos fast path;
+    both must meet the same bar against the oracle and agree with each other."""
+    if which == "golden":
+        d = os.path.join(golden_dir, "tiny_int")
+        fin = O.parse_fin(open(os.path.join(d, "out_fin_1_of_1")).read())
+        test = O.parse_rat(open(os.path.join(d, "out_test_rat_1_of_1")).read())
+    else:
+        fin, test = _random_case(2, 60, 25, 0.15, 3, 20)
+    users, offsets, items, ratings = _csr(test)
+    _run_and_compare(ctx, fin, test, min_ok=50)
+    fast = ctx.local_calc(offsets, items, ratings)
+    monkeypatch.setenv("GSI_LC_EXACT", "1")
+    _run_and_compare(ctx, fin, test, min_ok=50)
+    exact = ctx.local_calc(offsets, items, ratings)
+    assert np.array_equal(fast["status"], exact["status"]) and np.array_equal(fast["kk"], exact["kk"])
+    sel = fast["kk"] > 0
+    assert np.abs(fast["w_lim"][sel] - exact["w_lim"][sel]).max() <= 1e-9
+    assert (fast["cols"][sel] == exact["cols"][sel]).mean() >= 0.99
+
+
 def test_pair_mask_and_repeat(ctx):
     fin, test = _random_case(4, 40, 20, 0.5, 3, 12)
     a = np.array([e[0] for e in fin], dtype=np.int32)
