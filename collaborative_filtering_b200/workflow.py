@@ -99,9 +99,14 @@ def _link(src: str, dst: str) -> None:
 
 
 def run_pipeline(cross_dir: str, workdir: str, folds=None, pct: int = 20, seed: int = 31413, bin_dir: str = BIN_DIR,
-                 precompute_tool: str = "precompute_local", threads: int = 8, log=sys.stderr, stage_timeout=None) -> list:
-    """One pass of run_test_precompute.sh per fold inside `workdir` (the tools are cwd-relative).
-    Returns one dict per fold: the RMSE summary of its out_res.{i} and the wall seconds of every tool."""
+                 precompute_tool: str = "precompute_local", threads: int = 8, log=sys.stderr, stage_timeout=None,
+                 variant: str = "precomp") -> list:
+    """One pass of run_test_precompute.sh (variant "precomp": knn; knn2; precompute_local; local_calc_precomp --pct) or of
+    run_test.sh (variant "local_calc": knn; knn2; local_calc -- the per-movie tool, run_test.sh:15-17) per fold inside
+    `workdir` (the tools are cwd-relative).  Returns one dict per fold: the RMSE summary of its out_res.{i} and the wall
+    seconds of every tool."""
+    if variant not in ("precomp", "local_calc"):
+        raise ValueError("variant must be 'precomp' or 'local_calc'")
     if folds is None:
         folds = sorted(int(os.path.basename(p)[1:-6]) for p in glob.glob(os.path.join(cross_dir, "u*.train")))
     os.makedirs(workdir, exist_ok=True)
@@ -117,7 +122,9 @@ def run_pipeline(cross_dir: str, workdir: str, folds=None, pct: int = 20, seed: 
         for stale in glob.glob(os.path.join(workdir, "out_*_of_*")) + glob.glob(os.path.join(workdir, "out_eigen_*")):
             os.remove(stale)
         stage_s = {}
-        for tool, args in (("knn", []), ("knn2", []), (precompute_tool, [str(threads)]), ("local_calc_precomp", ["--pct", str(pct)])):
+        stages = ((("knn", []), ("knn2", []), (precompute_tool, [str(threads)]), ("local_calc_precomp", ["--pct", str(pct)]))
+                  if variant == "precomp" else (("knn", []), ("knn2", []), ("local_calc", ["--pct", str(pct)])))
+        for tool, args in stages:
             exe = os.path.join(bin_dir, tool)
             if not os.path.exists(exe):
                 raise FileNotFoundError("%s is not built (run `make -C collaborative_filtering_b200/csrc`)" % exe)
@@ -146,13 +153,15 @@ def main(argv=None) -> int:
     a.add_argument("--seed", type=int, default=31413)
     b = sub.add_parser("rmse", help="RMSE over out_res files")
     b.add_argument("paths", nargs="+")
-    c = sub.add_parser("run", help="knn; knn2; precompute_local; local_calc_precomp per fold (run_test_precompute.sh)")
+    c = sub.add_parser("run", help="knn; knn2; precompute_local; local_calc_precomp per fold (run_test_precompute.sh), or "
+                                   "knn; knn2; local_calc with --variant local_calc (run_test.sh)")
     c.add_argument("cross_dir")
     c.add_argument("workdir")
     c.add_argument("--pct", type=int, default=20)
     c.add_argument("--folds", default=None)
     c.add_argument("--seed", type=int, default=31413)
     c.add_argument("--tool", default="precompute_local", choices=["precompute_local", "precompute_local_threads"])
+    c.add_argument("--variant", default="precomp", choices=["precomp", "local_calc"])
     args = ap.parse_args(argv)
     if args.cmd == "fold":
         print(fold_cross_validation(args.filename, args.num_div, args.out, args.seed))
@@ -160,7 +169,7 @@ def main(argv=None) -> int:
         print(json.dumps(rmse_from_out_res(args.paths)))
     else:
         folds = [int(x) for x in args.folds.split(",")] if args.folds else None
-        res = run_pipeline(args.cross_dir, args.workdir, folds, args.pct, args.seed, precompute_tool=args.tool)
+        res = run_pipeline(args.cross_dir, args.workdir, folds, args.pct, args.seed, precompute_tool=args.tool, variant=args.variant)
         tot = sum(r["mse"] * r["predictions"] for r in res if r["predictions"])
         cnt = sum(r["predictions"] for r in res)
         print(json.dumps({"folds": res, "rmse": math.sqrt(tot / cnt) if cnt else float("nan"), "predictions": cnt}))

@@ -104,3 +104,8 @@ def test_pipeline_two_folds(tmp_path):
     assert text == open(os.path.join(work, "out_res.2")).read() and strip(a) == strip(b)
     assert set(a["seconds"]) == {"knn", "knn2", "precompute_local", "local_calc_precomp"}
     assert 0 < a["predictions"] + a["nan"] < res[1]["predictions"] + res[1]["nan"]
+
+
+def test_run_pipeline_rejects_unknown_variant(tmp_path):
+    with pytest.raises(ValueError):
+        WF.run_pipeline(str(tmp_path), str(tmp_path / "w"), folds=[0], variant="nope")

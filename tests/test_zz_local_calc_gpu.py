@@ -181,3 +181,32 @@ def test_cli(tmp_path, golden_dir, case):
             assert abs(float(gr[2]) - float(rr[2])) <= 1e-4 * max(1.0, float(rr[2])), (gr, rr)
     p = subprocess.run([os.path.join(BIN, "local_calc"), "--bogus"], cwd=cwd, stdout=subprocess.PIPE)
     assert p.returncode == 1 and b"Error in parsing" in p.stdout
+
+
+def test_workflow_variant(tmp_path):
+    """run_test.sh restated (knn; knn2; local_calc per fold) through the workflow driver."""
+    from collaborative_filtering_b200 import datasets as D
+    from collaborative_filtering_b200 import workflow as WF
+    r = D.make_ratings("ml-100k", n_users=120)
+    src = str(tmp_path / "u.data")
+    users, items, ratings = r.triples()
+    with open(src, "w") as f:
+        for u, i, x in zip(users, items, ratings):
+            f.write("%d\t%d\t%d\n" % (u, i, int(x)))
+    cv = str(tmp_path / "cross_validation")
+    assert WF.fold_cross_validation(src, 4, cv, seed=3) == 4
+    work = str(tmp_path / "work")
+    res = WF.run_pipeline(cv, work, folds=[1], pct=100, seed=5, log=open(os.devnull, "w"), variant="local_calc")
+    assert [x["fold"] for x in res] == [1] and set(res[0]["seconds"]) == {"knn", "knn2", "local_calc"}
+    n_test = sum(1 for _ in open(os.path.join(cv, "u1.test")))
+    assert 0 < res[0]["predictions"] + res[0]["nan"] <= n_test          # movies with a local graph of < 3 nodes emit no line
+    assert 0.0 <= res[0]["rmse"] <= 4.0
+    lines = open(os.path.join(work, "out_res.1")).read().splitlines()
+    assert len(lines) == res[0]["predictions"] + res[0]["nan"] and all(len(l.split()) == 4 for l in lines)
+    # the oracle on the same fold files: same emitted pairs, RMSE to 1e-4 (north_star) when no cutoff splits a cluster
+    rd = lambda p: [(int(a), int(b), float(c)) for a, b, c in (l.split()[:3] for l in open(p))]
+    rat, test_rat, edg = O.knn1(rd(os.path.join(cv, "u1.train")), rd(os.path.join(cv, "u1.test")))
+    rows = O.local_calc(O.parse_fin(O.format_fin(O.knn2(rat, edg))), O.parse_rat(O.format_rat(test_rat)))
+    assert [(l.split()[0], l.split()[1], l.split()[3]) for l in lines] == [(str(x[0]), str(x[1]), str(x[3])) for x in rows]
+    if all(x[8] > 1e-6 and x[5] == O.PRED_OK for x in rows):
+        assert abs(res[0]["rmse"] - O.rmse_of(rows)[0]) <= 1e-4
