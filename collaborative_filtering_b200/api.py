@@ -211,6 +211,22 @@ class Context:
             _ptr(err), _ptr(kk), _ptr(pred), _ptr(status), _ptr(cols), _ptr(w_lim)))
         return dict(err=err, kk=kk, pred=pred, status=status, cols=cols, w_lim=w_lim)
 
+    def local_calc_shard(self, offsets, items, ratings, n_nodes, rank: int, world: int, pair_mask=None) -> dict:
+        """This rank's share of a multi-GPU local_calc run: movie vertices are dealt over the ranks by cost
+        (shard.shard_movies; ``n_nodes[m]`` = 1 + out-degree of movie m in the thresholded item graph), every rank
+        passes the whole test CSR and computes the pairs of its own movies; the other pairs come back with status 4
+        and are merged by the caller (all-reduce of counts / squared errors, or a gather of the arrays)."""
+        from . import shard
+        items = np.ascontiguousarray(items, dtype=np.int32)
+        n_nodes = np.asarray(n_nodes)
+        keep = np.ones(len(items), dtype=bool) if pair_mask is None else np.asarray(pair_mask).astype(bool)
+        inside = items < len(n_nodes)
+        n_pairs = np.bincount(items[keep & inside], minlength=len(n_nodes))
+        owner = shard.shard_movies(n_nodes, n_pairs, world)
+        mask = np.zeros(len(items), dtype=np.uint8)
+        mask[inside] = shard.local_calc_pair_mask(items[inside], owner, rank, keep[inside])
+        return self.local_calc(offsets, items, ratings, pair_mask=mask)
+
     # ---- knn chain (knn.cpp / knn2.cpp / knn3.cpp) ----
     def knn_build(self, offsets, items, ratings, rows: int, install_weights: bool = True):
         """knn2 over the TRAIN ratings (CSR by user).  Returns the out_fin_ edges (m1, m2, w float32)

@@ -40,3 +40,40 @@ def imbalance(deg, owner, n_shards: int) -> float:
     cost = user_cost(deg)
     loads = np.bincount(owner, weights=cost, minlength=n_shards)
     return float(loads.max() / loads.mean())
+
+
+# ---- per-movie variant (local_calc.cpp): the independent unit is the MOVIE vertex -- its local graph, its eigensolve and
+# all predictions for its test users live together (vertex_program::apply, local_calc.cpp:262-526) ---------------------
+def movie_cost(n_nodes, n_pairs) -> np.ndarray:
+    """Cost model of one movie vertex: a full eigensolve of its local graph (n nodes) plus, per test user, about twenty
+    Lanczos steps of one n x n GEMV each (the fast path of gsi_local_calc_host).  Movies without pairs cost nothing."""
+    n = np.asarray(n_nodes, dtype=np.float64)
+    p = np.asarray(n_pairs, dtype=np.float64)
+    return np.where(p > 0, 9.0 * n ** 3 + 40.0 * n ** 2 * p, 0.0)
+
+
+def shard_movies(n_nodes, n_pairs, world: int) -> np.ndarray:
+    """owner[movie] in [0, world): LPT over movie_cost, deterministic, identical on every rank."""
+    cost = movie_cost(n_nodes, n_pairs)
+    order = np.lexsort((np.arange(len(cost)), -cost))
+    owner = np.zeros(len(cost), dtype=np.int32)
+    heap = [(0.0, s) for s in range(world)]
+    heapq.heapify(heap)
+    for m in order:
+        if cost[m] == 0.0:
+            break
+        load, s = heapq.heappop(heap)
+        owner[m] = s
+        heapq.heappush(heap, (load + cost[m], s))
+    return owner
+
+
+def local_calc_pair_mask(items, owner, rank: int, base_mask=None) -> np.ndarray:
+    """pair_mask for gsi_local_calc_host on `rank`: the pairs whose movie this rank owns (and that `base_mask`, e.g. the
+    --pct sample, keeps).  Every rank passes the whole test CSR, so a user's ratings of the other movies stay visible as
+    known ratings; outputs of the other ranks' pairs come back as GSI_PRED_SKIPPED and are merged by the host."""
+    items = np.asarray(items)
+    mask = (np.asarray(owner)[items] == rank).astype(np.uint8)
+    if base_mask is not None:
+        mask &= np.asarray(base_mask, dtype=np.uint8)
+    return mask

@@ -117,3 +117,68 @@ def test_two_rank_gloo_predict_sample_reduction(tmp_path):
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "OK" in outs[0] and "OK" in outs[1]
+
+
+def test_movie_sharding_for_local_calc():
+    """Per-movie variant: movies are dealt by cost, the ranks' pair masks partition the requested pairs."""
+    r = D.make_ratings("ml-100k")
+    rng = np.random.default_rng(7)
+    n_nodes = rng.integers(1, 1200, size=r.n_items + 1)
+    n_pairs = np.bincount(r.items, minlength=r.n_items + 1)
+    base = (rng.random(len(r.items)) < 0.5).astype(np.uint8)
+    for world in (1, 2, 8):
+        owner = SH.shard_movies(n_nodes, n_pairs, world)
+        assert owner.min() >= 0 and owner.max() <= world - 1
+        masks = [SH.local_calc_pair_mask(r.items, owner, k, base) for k in range(world)]
+        assert np.array_equal(np.sum(masks, axis=0).astype(np.uint8), base)      # each kept pair on exactly one rank
+        loads = np.bincount(owner, weights=SH.movie_cost(n_nodes, n_pairs), minlength=world)
+        heaviest = SH.movie_cost(n_nodes, n_pairs).max() / loads.mean()
+        assert loads.max() / loads.mean() <= max(1.05, heaviest + 1e-9)
+        for k in range(world):                                                  # all pairs of a movie on its owner
+            assert set(np.unique(r.items[masks[k] == 1])) <= set(np.nonzero(owner == k)[0])
+
+
+_WORKER_LC = r"""
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, %r)
+from collaborative_filtering_b200 import datasets as D, shard as SH
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["PORT"],
+                        rank=int(os.environ["RANK"]), world_size=2)
+rank = dist.get_rank()
+r = D.make_ratings("ml-100k")
+n_pairs = np.bincount(r.items, minlength=r.n_items + 1)
+n_nodes = (np.arange(r.n_items + 1) * 7919) %% 900 + 3          # same on both ranks (a stand-in for the graph's out-degrees)
+owner = SH.shard_movies(n_nodes, n_pairs, 2)
+mask = SH.local_calc_pair_mask(r.items, owner, rank)
+# what the host merge does: every pair computed once, squared errors and counts all-reduced
+done = torch.from_numpy(mask.astype(np.int32))
+dist.all_reduce(done)
+stats = torch.tensor([float(mask.sum()), float((r.ratings[mask == 1].astype(np.float64) ** 2).sum())], dtype=torch.float64)
+dist.all_reduce(stats)
+if rank == 0:
+    assert int(done.min()) == 1 and int(done.max()) == 1, "pair masks must partition the pairs"
+    assert stats[0].item() == len(r.items)
+    assert abs(stats[1].item() - float((r.ratings.astype(np.float64) ** 2).sum())) < 1e-6
+    print("OK", stats.tolist())
+dist.destroy_process_group()
+""" % ROOT
+
+
+def test_gloo_world2_movie_deal_and_reduce(tmp_path):
+    script = tmp_path / "worker_lc.py"
+    script.write_text(_WORKER_LC)
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = []
+    for rk in range(2):
+        env = dict(os.environ, RANK=str(rk), PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=300)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "OK" in outs[0]
