@@ -16,6 +16,10 @@
 // The thread pool restates precompute_local_threads.cpp:300-314 (boost::threadpool, one task per
 // user, shared read-only weights) with std::thread workers and an atomic task counter; the text
 // record of :196-211 is formatted per user (printf("%g") == default ostream formatting).
+//
+// local_calc_movie() / cpuref_local_calc() restate the per-MOVIE variant's vertex program
+// (/root/reference/local_calc.cpp:262-526) the same way: the same solver pair for both of its eigensolves, the dense
+// products and the LU inverse it executes per user.  Validated against oracle/gsi_oracle.py in tests/test_local_calc.py.
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -304,9 +308,161 @@ void compute_eigens(Job& job, int u, std::string& text) {
     }
 }
 
+// ---- local_calc.cpp: vertex_program::apply for one movie vertex (:262-526), restated with the same solvers --------
+// Inputs are the arrays gsi_local_calc_host takes (dense directed weight table, test ratings as a CSR by user); the
+// by-movie view of the ratings is built by the caller below.  `honest` executes the reference's dense degree-matrix
+// inverse and the two n^3 products (:368-374) like compute_eigens above; the per-user work is always the reference's:
+// the GEMM ll2_h * ll2_h^T, a full eigensolve of it (:435), the normal equations through a dense LU inverse (:485-490).
+struct LcJob {
+    const double* W; int rows;
+    const int64_t* offsets; const int32_t* items; const double* ratings; int n_users;
+    const uint8_t* pair_mask;
+    const std::vector<std::vector<std::pair<int, int64_t>>>* by_movie;     // movie -> (user, position)
+    float* err; int32_t* kk; double* pred; int32_t* status; int32_t* lim; double* w_lim;
+    int honest;
+    std::atomic<int> next{0};
+};
+
+inline double lc_edge(const LcJob& J, int a, int b) {       // graph_loader :102-117
+    if (a == b || a >= J.rows || b >= J.rows) return 0.0;
+    const float f = (float)J.W[(size_t)a * J.rows + b];
+    return ((double)f > 0.1) ? (double)f : 0.0;
+}
+
+void local_calc_movie(LcJob& J, int m) {
+    const auto& pairs = (*J.by_movie)[m];
+    if (pairs.empty()) return;
+    std::vector<int> nodes(1, m);                            // :283-290 (ascending neighbour order, B6)
+    for (int j = 0; j < J.rows; ++j) if (lc_edge(J, m, j) != 0.0) nodes.push_back(j);
+    const int n = (int)nodes.size();
+    if (n < 3) return;                                       // :271-272
+    std::vector<int> pos(J.rows, -1);
+    for (int i = 0; i < n; ++i) pos[nodes[i]] = i;
+    std::vector<double> ww((size_t)n * n, 0.0), dd((size_t)n * n, 0.0), ll((size_t)n * n), ll2((size_t)n * n);
+    for (int i = 1; i < n; ++i) {                            // :324-335
+        for (int j = 1; j < n; ++j) if (i != j) at(ww, n, i, j) = lc_edge(J, nodes[i], nodes[j]);
+        at(ww, n, 0, i) = at(ww, n, i, 0) = lc_edge(J, m, nodes[i]);
+    }
+    for (int i = 0; i < n; ++i) {                            // :353-361
+        double count = 0;
+        for (int j = 0; j < n; ++j) count += at(ww, n, i, j);
+        at(dd, n, i, i) = count;
+    }
+    for (size_t t = 0; t < (size_t)n * n; ++t) ll[t] = dd[t] - ww[t];   // :364
+    if (J.honest) {                                          // :368-374
+        std::vector<double> tmp = dd, dd2, t1((size_t)n * n);
+        lu_inverse(n, tmp, dd2);
+        for (auto& x : dd2) x = std::sqrt(x);
+        gemm(n, dd2.data(), ll.data(), t1.data());
+        gemm(n, t1.data(), dd2.data(), ll2.data());
+    } else {
+        std::vector<double> s(n);
+        for (int i = 0; i < n; ++i) s[i] = std::sqrt(1.0 / at(dd, n, i, i));
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i) at(ll2, n, i, j) = (s[i] * at(ll, n, i, j)) * s[j];
+    }
+    std::vector<double> v((size_t)n * n), d(n), e(n);        // :378
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) at(v, n, i, j) = (i >= j) ? at(ll2, n, i, j) : at(ll2, n, j, i);
+    tridiagonalize(n, v, d, e); implicit_ql(n, v, d, e);
+    std::vector<double> rat(n);
+    std::vector<int> un, rt;
+    for (const auto& pr : pairs) {                           // :393 for each user
+        const int u = pr.first; const int64_t t0 = pr.second;
+        std::fill(rat.begin(), rat.end(), 0.0);
+        for (int64_t t = J.offsets[u]; t < J.offsets[u + 1]; ++t)
+            if (J.items[t] < J.rows && pos[J.items[t]] >= 0) rat[pos[J.items[t]]] = J.ratings[t];
+        const double rat_real = rat[0];
+        rat[0] = 0.0;                                        // :405
+        un.clear(); rt.clear();
+        for (int i = 0; i < n; ++i) (rat[i] == 0.0 ? un : rt).push_back(i);     // :406-413
+        const int nu_ = (int)un.size(), kk = (int)rt.size();
+        J.kk[t0] = kk;
+        // :417-436 smallest eigenvalue of ll2_h * ll2_h^T
+        std::vector<double> g((size_t)nu_ * nu_), gd(nu_), ge(nu_);
+        for (int a = 0; a < nu_; ++a)
+            for (int b = 0; b <= a; ++b) {
+                double acc = 0.0;
+                for (int j = 0; j < n; ++j) acc += at(ll2, n, un[a], j) * at(ll2, n, un[b], j);
+                g[(size_t)b * nu_ + a] = g[(size_t)a * nu_ + b] = acc;
+            }
+        tridiagonalize(nu_, g, gd, ge); implicit_ql(nu_, g, gd, ge);
+        const double wl = std::sqrt(gd[0]);
+        J.w_lim[t0] = wl;
+        int lim;
+        for (lim = 0; lim < n; ++lim) if (d[lim] > wl) break;                   // :443-451
+        if (lim < 2) lim = 2;
+        J.lim[t0] = lim;
+        int st = 0;
+        double p;
+        if (kk == 0) { st = 1; p = std::nan(""); }                             // 0/0 :487
+        else {
+            std::vector<double> mm((size_t)lim * lim, 0.0), inv, rhs(lim, 0.0), x(lim, 0.0);
+            double mean = 0.0;
+            for (int t = 0; t < kk; ++t) mean += rat[rt[t]];
+            mean /= kk;
+            for (int a = 0; a < lim; ++a) {
+                for (int b = 0; b < lim; ++b) {
+                    double acc = 0.0;
+                    for (int t = 0; t < kk; ++t) acc += at(v, n, rt[t], a) * at(v, n, rt[t], b);
+                    mm[(size_t)b * lim + a] = acc;                              // :484-485
+                }
+                for (int t = 0; t < kk; ++t) rhs[a] += at(v, n, rt[t], a) * (rat[rt[t]] - mean);
+            }
+            if (kk < lim) st = 2;
+            lu_inverse(lim, mm, inv);                                          // mm.inverse() :490
+            p = 0.0;
+            for (int a = 0; a < lim; ++a) {
+                double acc = 0.0;
+                for (int b = 0; b < lim; ++b) acc += inv[(size_t)b * lim + a] * rhs[b];
+                p += at(v, n, 0, a) * acc;
+            }
+            p += mean;
+        }
+        J.pred[t0] = p;
+        double pc = p;
+        if (pc > 5) pc = 5;                                                    // :494-497
+        if (pc < 1) pc = 1;
+        J.err[t0] = (float)((rat_real - pc) * (rat_real - pc));               // :499
+        J.status[t0] = st;
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+// local_calc over every movie vertex that has requested pairs; outputs [nnz] aligned with items, status 4 where the
+// reference writes no line.  n_threads workers take movie vertices from a shared counter (the GraphLab engine runs
+// vertex programs concurrently).  Returns the number of pairs computed.
+long long cpuref_local_calc(const double* W, int rows, const int64_t* offsets, const int32_t* items, const double* ratings,
+                            int n_users, const uint8_t* pair_mask, int n_threads, int honest, float* err, int32_t* kk,
+                            double* pred, int32_t* status, int32_t* lim, double* w_lim) {
+    const int64_t nnz = offsets[n_users];
+    std::vector<std::vector<std::pair<int, int64_t>>> by_movie(rows);
+    for (int64_t t = 0; t < nnz; ++t) { err[t] = 0.f; kk[t] = 0; pred[t] = 0.0; status[t] = 4; lim[t] = 0; w_lim[t] = 0.0; }
+    for (int u = 0; u < n_users; ++u)
+        for (int64_t t = offsets[u]; t < offsets[u + 1]; ++t)
+            if (items[t] >= 0 && items[t] < rows && (!pair_mask || pair_mask[t])) by_movie[items[t]].emplace_back(u, t);
+    LcJob J;
+    J.W = W; J.rows = rows; J.offsets = offsets; J.items = items; J.ratings = ratings; J.n_users = n_users;
+    J.pair_mask = pair_mask; J.by_movie = &by_movie; J.err = err; J.kk = kk; J.pred = pred; J.status = status; J.lim = lim;
+    J.w_lim = w_lim; J.honest = honest;
+    std::vector<std::thread> pool;
+    auto worker = [&]() {
+        for (;;) {
+            const int m = J.next.fetch_add(1);
+            if (m >= rows) break;
+            local_calc_movie(J, m);
+        }
+    };
+    if (n_threads < 1) n_threads = 1;
+    for (int t = 0; t < n_threads; ++t) pool.emplace_back(worker);
+    for (auto& th : pool) th.join();
+    long long done = 0;
+    for (int64_t t = 0; t < nnz; ++t) done += status[t] != 4;
+    return done;
+}
 
 // Outputs: sig_min[nnz]; k_out[n_users]; lam_out + lam_off[u]: max(n,2) slots, first k valid;
 // vec_out + vec_off[u]: max(n,2)*n slots holding the n x k row-major kept eigenvectors.

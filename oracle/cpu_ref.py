@@ -73,3 +73,29 @@ def precompute(weights: np.ndarray, offsets: np.ndarray, items: np.ndarray, user
     lams = [lam[lam_off[u]: lam_off[u] + k[u]] for u in range(nu)]
     vecs = [vec[vec_off[u]: vec_off[u] + deg[u] * k[u]].reshape(int(deg[u]), int(k[u])) for u in range(nu)]
     return dict(sig_min=sig, k=k, lam=lams, vec=vecs, seconds=dt, text_bytes=int(nbytes))
+
+
+def local_calc(weights: np.ndarray, offsets: np.ndarray, items: np.ndarray, ratings: np.ndarray, pair_mask=None,
+               n_threads: int = 1, honest: bool = True):
+    """C++ restatement of local_calc.cpp's vertex program over every requested (user, movie) pair (same arrays as
+    gsi_local_calc_host).  Returns dict err, kk, pred, status (4 = no line), lim, w_lim [nnz], seconds, pairs."""
+    lib().cpuref_local_calc.restype = ctypes.c_longlong
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    items = np.ascontiguousarray(items, dtype=np.int32)
+    ratings = np.ascontiguousarray(ratings, dtype=np.float64)
+    nnz = int(offsets[-1])
+    mask = None if pair_mask is None else np.ascontiguousarray(pair_mask, dtype=np.uint8)
+    err = np.zeros(nnz, dtype=np.float32)
+    kk = np.zeros(nnz, dtype=np.int32)
+    pred = np.zeros(nnz, dtype=np.float64)
+    status = np.zeros(nnz, dtype=np.int32)
+    lim = np.zeros(nnz, dtype=np.int32)
+    w_lim = np.zeros(nnz, dtype=np.float64)
+    t0 = time.perf_counter()
+    done = lib().cpuref_local_calc(
+        _p(w, ctypes.c_double), ctypes.c_int(w.shape[0]), _p(offsets, ctypes.c_int64), _p(items, ctypes.c_int32),
+        _p(ratings, ctypes.c_double), ctypes.c_int(len(offsets) - 1), None if mask is None else _p(mask, ctypes.c_uint8),
+        ctypes.c_int(n_threads), ctypes.c_int(int(honest)), _p(err, ctypes.c_float), _p(kk, ctypes.c_int32),
+        _p(pred, ctypes.c_double), _p(status, ctypes.c_int32), _p(lim, ctypes.c_int32), _p(w_lim, ctypes.c_double))
+    return dict(err=err, kk=kk, pred=pred, status=status, lim=lim, w_lim=w_lim, seconds=time.perf_counter() - t0, pairs=int(done))

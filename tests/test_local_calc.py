@@ -94,3 +94,56 @@ def test_asymmetric_table_is_tolerance_level():
     assert [(r[0], r[1], r[3]) for r in r0] == [(r[0], r[1], r[3]) for r in r1]
     d = [abs(a[7] - b[7]) for a, b in zip(r0, r1) if a[3] > 0]
     assert max(d) < 5e-2
+
+
+def _csr(test_rat):
+    by_user = {}
+    for m, d in test_rat.items():
+        for u, r in d.items():
+            by_user.setdefault(u, []).append((m, r))
+    users = sorted(by_user)
+    offsets, items, ratings = [0], [], []
+    for u in users:
+        for m, r in sorted(by_user[u]):
+            items.append(m)
+            ratings.append(r)
+        offsets.append(len(items))
+    return users, np.array(offsets, dtype=np.int64), np.array(items, dtype=np.int32), np.array(ratings, dtype=np.float64)
+
+
+@pytest.mark.parametrize("which,honest,threads", [("tiny_int", True, 1), ("tiny_half", False, 3), ("random", True, 2)])
+def test_cpp_restatement_agrees_with_numpy_oracle(golden_dir, which, honest, threads):
+    """Two independent restatements of local_calc.cpp (numpy/LAPACK and the C++ Householder + QL solver pair with the
+    reference's dense inverse and products) agree: emitted pairs, kk, status classes and lim exactly, w_lim to 1e-10,
+    predictions to 1e-7 on well-posed pairs whose cutoff does not split a cluster."""
+    from oracle import cpu_ref
+    if which == "random":
+        fin, test = _random_case(2, n_items=60, n_users=25, density=0.15)
+    else:
+        d = os.path.join(golden_dir, which)
+        fin = O.parse_fin(open(os.path.join(d, "out_fin_1_of_1")).read())
+        test = O.parse_rat(open(os.path.join(d, "out_test_rat_1_of_1")).read())
+    weights = O.weights_from_fin(fin)
+    users, offsets, items, ratings = _csr(test)
+    out = cpu_ref.local_calc(weights, offsets, items, ratings, n_threads=threads, honest=honest)
+    pos = {(int(items[t]), u): t for ui, u in enumerate(users) for t in range(offsets[ui], offsets[ui + 1])}
+    rows = O.local_calc(fin, test)
+    assert out["pairs"] == len(rows)
+    emitted = {(r[0], r[1]) for r in rows}
+    for key, t in pos.items():
+        assert (out["status"][t] == 4) == (key not in emitted)
+    n_cmp = 0
+    for (m, u, err, kk, pred, status, lim, w_lim, gap) in rows:
+        t = pos[(m, u)]
+        assert out["kk"][t] == kk
+        if kk == 0:
+            assert out["status"][t] == 1 and np.isnan(out["pred"][t])
+            continue
+        assert abs(out["w_lim"][t] - w_lim) <= 1e-10, (m, u, out["w_lim"][t], w_lim)
+        assert out["lim"][t] == lim
+        assert (out["status"][t] == 2) == (status == O.PRED_UNDERDETERMINED)
+        if status == O.PRED_OK and gap > 1e-6:
+            assert abs(out["pred"][t] - pred) <= 1e-7, (m, u, out["pred"][t], pred)
+            assert abs(float(out["err"][t]) - float(err)) <= 1e-5 * max(1.0, float(err))
+            n_cmp += 1
+    assert n_cmp > 50
