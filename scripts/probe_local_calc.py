@@ -5,8 +5,15 @@ ML-100K shape (943 x 1682, 100k integer ratings, seed 31413), 5-fold user split;
 stage on the train folds, the test ratings are the validation fold.  A seeded PCT % of the movie vertices is
 computed (the tool's own --pct switch, local_calc.cpp:266).  Prints one JSON line.
 
-    python scripts/probe_local_calc.py [pct] [n_oracle_movies]
+    python scripts/probe_local_calc.py [pct] [n_oracle_movies] [shape]
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/probe_local_calc.py [pct] 0 [shape]
+
+Under torchrun (WORLD_SIZE > 1) the movie vertices are dealt over the ranks (shard.shard_movies through
+Context.local_calc_shard), every rank computes the pairs of its own movies, pair counts and squared errors are
+all-reduced and the wall time is the slowest rank's; the oracle comparison runs on rank 0 over its own pairs only.
+(The multi-GPU mode has been exercised on CPU for its dealing logic only -- tests/test_shard.py.)
 """
+import os
 import json
 import sys
 import time
@@ -20,13 +27,20 @@ from oracle import gsi_oracle as O  # noqa: E402
 
 pct = float(sys.argv[1]) if len(sys.argv) > 1 else 5.0
 n_oracle = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-r = D.make_ratings("ml-100k")
+shape = sys.argv[3] if len(sys.argv) > 3 else "ml-100k"
+rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+if world > 1:
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group("nccl")
+r = D.make_ratings(shape)
 folds = D.fold_split(r, 5)
 val_idx = np.sort(folds[0])
 trn_idx = np.sort(np.concatenate(folds[1:]))
 _, v_off, v_items, v_rat = D.subset(r, val_idx)
 _, t_off, t_items, t_rat = D.subset(r, trn_idx)
-ctx = Context(0)
+ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
 a, b, w = ctx.knn_build(t_off, t_items, t_rat, r.n_items + 1, install_weights=False)
 ctx.set_weights_edges(a, b, w.astype(np.float64))
 kept = w.astype(np.float32).astype(np.float64) > 0.1
@@ -36,12 +50,29 @@ movies = np.unique(v_items)
 chosen = movies[rng.random(len(movies)) * 100.0 < pct]
 mask = np.isin(v_items, chosen).astype(np.uint8)
 ctx.local_calc(v_off, v_items, v_rat.astype(np.float64), pair_mask=np.zeros_like(mask))   # warm-up: neighbour lists only
+if world > 1:
+    dist.barrier()
 t0 = time.time()
-out = ctx.local_calc(v_off, v_items, v_rat.astype(np.float64), pair_mask=mask)
+if world > 1:
+    out = ctx.local_calc_shard(v_off, v_items, v_rat.astype(np.float64), nb + 1, rank, world, pair_mask=mask)
+else:
+    out = ctx.local_calc(v_off, v_items, v_rat.astype(np.float64), pair_mask=mask)
 wall = time.time() - t0
 done = out["status"] != 4
+if world > 1:                      # merge: slowest rank's wall time, pair counts and squared errors summed
+    okr = out["status"] == 0
+    st = torch.tensor([float(done.sum()), float(okr.sum()), float(out["err"][okr].astype(np.float64).sum())], dtype=torch.float64, device="cuda")
+    tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    dist.all_reduce(st)
+    dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps(dict(shape=shape, pct=pct, n_gpus=world, pairs=int(st[0].item()), wall_s=round(tw.item(), 3),
+                              pairs_per_s=round(st[0].item() / tw.item(), 1), rmse_ok=float(np.sqrt(st[2].item() / max(st[1].item(), 1.0))))))
+    dist.destroy_process_group()
+    ctx.close()
+    sys.exit(0)
 ok = out["status"] == 0
-res = dict(shape="ml-100k fold 0", pct=pct, movies=int(len(chosen)), pairs=int(done.sum()), wall_s=round(wall, 3),
+res = dict(shape=shape + " fold 0", pct=pct, movies=int(len(chosen)), pairs=int(done.sum()), wall_s=round(wall, 3),
            pairs_per_s=round(float(done.sum()) / wall, 1),
            local_graph_nodes=dict(mean=float(nb[chosen].mean() + 1), max=int(nb[chosen].max() + 1)),
            status=np.bincount(out["status"], minlength=5).tolist(),
