@@ -6,13 +6,22 @@
 //   -> graph_filtered_signal_1_of_1   lines `vertex value` (graph_signal_writer :140-148), ascending vertex id
 // The three GraphLab engines (degree, init values, one synchronous superstep per further coefficient, :312-375) are one
 // gsi_cheby_filter_host() call.  Vertices that only appear in the topology read a signal of 0 (uninitialised in the reference).
+#include <time.h>
+
 #include <map>
 
 #include "host_io.hpp"
 
 using namespace gsihost;
 
+static double now_s() {
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return t.tv_sec + 1e-9 * t.tv_nsec;
+}
+
 int main(int, char**) {
+    const double t_load = now_s();
     std::vector<double> coeff;
     for (const std::string& f : list_files("./", [](const std::string& n) { return n.rfind("coeff", 0) == 0; })) {
         std::string text;
@@ -64,13 +73,20 @@ int main(int, char**) {
     for (const Edge& e : edges) { const int64_t p = fill[index[e.a]]++; col[p] = index[e.b]; w[p] = e.w; }
     std::vector<double> x(nv), y(nv);
     for (int64_t i = 0; i < nv; ++i) x[i] = signal[ids[i]];
+    // the two timing lines scale2.sh greps from the reference's output (cheby.cpp:287-288, :328-334)
+    printf("Loading graph. Finished in %g\n", now_s() - t_load);
     printf("Num vertices: %lld\nNum edges: %zu\n", (long long)nv, edges.size());
     gsi_ctx* ctx = nullptr;
     const char* dev = getenv("GSI_DEVICE");
     if (gsi_create(&ctx, dev ? atoi(dev) : 0, nullptr) != GSI_OK) return fail(nullptr, "gsi_create");
     printf("Running ...\n");
+    const double t_run = now_s();
     if (gsi_cheby_filter_host(ctx, nv, row_off.data(), col.data(), w.data(), x.data(), (int)coeff.size(), coeff.data(), y.data()) != GSI_OK)
         return fail(ctx, "gsi_cheby_filter_host");
+    const double runtime = now_s() - t_run;
+    const double updates = (double)nv * (double)coeff.size();        // one vertex update per vertex and coefficient (:262-264)
+    printf("----------------------------------------------------------\nFinal Runtime (seconds):   %g\nUpdates executed: %.0f\n"
+           "Update Rate (updates/second): %g\n", runtime, updates, updates / runtime);
     gsi_destroy(ctx);
     FILE* f = fopen("graph_filtered_signal_1_of_1", "w");
     if (!f) { perror("graph_filtered_signal_1_of_1"); return EXIT_FAILURE; }

@@ -7,6 +7,8 @@ script and the RMSE step the reference leaves to the user, without hard-coded pa
                           the other folds together are u{i}.train (:46-56).  The shuffle is seeded.
   rmse_from_out_res       the step run_test_precompute.sh:19 stops before: `cat out_res_*` and average
                           column 3.  Lines are `movie user' mse kk` (local_calc_precomp.cpp:393-404).
+  mega_graph, cheby_scale mega_graph.py:27-40 and scale2.sh:5-36: seeded random graphs and the three scaling sweeps of
+                          the cheby tool (coefficients, connectivity, nodes), timing lines kept as JSON.
   run_pipeline            run_test_precompute.sh:9-20: per fold, movielens/u{i}.train + u{i}.validate,
                           then knn; knn2; precompute_local 8; local_calc_precomp --pct P;
                           cat out_res_* > out_res.{i}.  The tools are the drop-in binaries under
@@ -14,7 +16,9 @@ script and the RMSE step the reference leaves to the user, without hard-coded pa
 
 CLI:  python -m collaborative_filtering_b200.workflow fold  u.data 5 [--out cross_validation] [--seed S]
       python -m collaborative_filtering_b200.workflow rmse  out_res_1_of_1 [more files ...]
-      python -m collaborative_filtering_b200.workflow run   cross_validation workdir [--pct 20] [--folds 0,1,2,3,4]
+      python -m collaborative_filtering_b200.workflow run   cross_validation workdir [--pct 20] [--folds 0,1,2,3,4] [--variant local_calc]
+      python -m collaborative_filtering_b200.workflow mega-graph 50000 0.01 [--out DIR]
+      python -m collaborative_filtering_b200.workflow cheby-scale workdir [--nodes 50000] [--conn 0.01] [--coeffs 64]
 """
 from __future__ import annotations
 
@@ -29,6 +33,8 @@ import subprocess
 import sys
 import time
 from collections import OrderedDict
+
+import numpy as np
 
 BIN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bin")
 TOOLS = ("knn", "knn2", "precompute_local", "local_calc_precomp")
@@ -143,6 +149,79 @@ def run_pipeline(cross_dir: str, workdir: str, folds=None, pct: int = 20, seed: 
     return results
 
 
+def mega_graph(size: int, conn: float, out_dir: str = ".", seed: int = 31413) -> int:
+    """mega_graph.py:27-40 restated with a seeded generator: `graph_signal.txt` (vertex i+1, value uniform in [0, 10))
+    and `graph_topology.txt` with conn * size^2 distinct directed links (a, b), a != b, weight uniform in [0, 1) printed
+    with two decimals.  Returns the number of links."""
+    rng = np.random.default_rng(seed)
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, "graph_signal.txt"), "w") as f:
+        f.write("".join("%d %s\n" % (i + 1, repr(float(v))) for i, v in enumerate(rng.uniform(0, 10, size))))
+    n_links = int(conn * size * size)
+    if n_links > size * (size - 1):
+        raise ValueError("more links requested than a graph of %d vertices has" % size)
+    codes = np.zeros(0, dtype=np.int64)
+    while len(codes) < n_links:                               # rejection sampling of distinct off-diagonal pairs (:31-37)
+        need = n_links - len(codes)
+        a = rng.integers(0, size, size=need + need // 8 + 16, dtype=np.int64)
+        b = rng.integers(0, size, size=len(a), dtype=np.int64)
+        fresh = (a * size + b)[a != b]
+        codes = np.unique(np.concatenate([codes, fresh]))
+        if len(codes) > n_links:
+            codes = rng.permutation(codes)[:n_links]
+    wei = rng.random(len(codes))
+    with open(os.path.join(out_dir, "graph_topology.txt"), "w") as f:
+        for lo in range(0, len(codes), 1 << 20):
+            c = codes[lo: lo + (1 << 20)]
+            f.write("".join("%d %d %.2f\n" % (x // size + 1, x % size + 1, w) for x, w in zip(c.tolist(), wei[lo: lo + (1 << 20)].tolist())))
+    return int(len(codes))
+
+
+def cheby_scale(workdir: str, nodes=50000, conn=0.01, coeffs=64, sweep_coeffs=range(10, 101, 10),
+                sweep_conn=tuple(round(0.005 * i, 3) for i in range(1, 11)), sweep_nodes=range(5000, 50001, 5000),
+                seed: int = 31413, bin_dir: str = BIN_DIR, log=sys.stderr, stage_timeout=None) -> list:
+    """scale2.sh restated: three sweeps of the `cheby` tool on random graphs -- number of coefficients (:5-14), connectivity
+    (:17-26) and number of nodes (:30-38) -- each point generating its graph with mega_graph (the first sweep reuses one
+    graph), cutting the first k coefficients of a 1000-long line (`_coeff_1000.txt`, not shipped with the reference:
+    seeded uniform values here) into coeff.txt, running the tool in `workdir` and keeping the two timing lines the script
+    greps ("Finished in", "Final Runtime").  Returns one dict per point; also appended to workdir/scale_res2.jsonl."""
+    os.makedirs(workdir, exist_ok=True)
+    exe = os.path.join(bin_dir, "cheby")
+    if not os.path.exists(exe):
+        raise FileNotFoundError("%s is not built (run `make -C collaborative_filtering_b200/csrc`)" % exe)
+    all_coeff = np.random.default_rng(seed + 1).uniform(-1.0, 1.0, 1000)
+    res_path = os.path.join(workdir, "scale_res2.jsonl")
+    open(res_path, "w").close()
+    results = []
+
+    def point(n, c, k, regenerate):
+        if regenerate:
+            mega_graph(n, c, workdir, seed)
+        with open(os.path.join(workdir, "coeff.txt"), "w") as f:
+            f.write(" ".join(repr(float(x)) for x in all_coeff[:k]) + "\n")
+        t0 = time.perf_counter()
+        p = subprocess.run([exe], cwd=workdir, check=True, stdout=subprocess.PIPE, timeout=stage_timeout)
+        wall = time.perf_counter() - t0
+        rec = {"nodes": int(n), "conn": float(c), "coeffs": int(k), "wall_s": round(wall, 3)}
+        for line in p.stdout.decode().splitlines():
+            if "Finished in" in line:
+                rec["load_s"] = float(line.split()[-1])
+            elif "Final Runtime" in line:
+                rec["runtime_s"] = float(line.split()[-1])
+        with open(res_path, "a") as f:
+            f.write(json.dumps(rec) + "\n")
+        print(json.dumps(rec), file=log)
+        results.append(rec)
+
+    for i, k in enumerate(sweep_coeffs):
+        point(nodes, conn, k, regenerate=(i == 0))
+    for c in sweep_conn:
+        point(nodes, c, coeffs, regenerate=True)
+    for n in sweep_nodes:
+        point(n, conn, coeffs, regenerate=True)
+    return results
+
+
 def main(argv=None) -> int:
     ap = argparse.ArgumentParser(prog="collaborative_filtering_b200.workflow")
     sub = ap.add_subparsers(dest="cmd", required=True)
@@ -162,7 +241,26 @@ def main(argv=None) -> int:
     c.add_argument("--seed", type=int, default=31413)
     c.add_argument("--tool", default="precompute_local", choices=["precompute_local", "precompute_local_threads"])
     c.add_argument("--variant", default="precomp", choices=["precomp", "local_calc"])
+    d = sub.add_parser("mega-graph", help="random graph_signal.txt / graph_topology.txt for cheby (mega_graph.py)")
+    d.add_argument("size", type=int)
+    d.add_argument("conn", type=float)
+    d.add_argument("--out", default=".")
+    d.add_argument("--seed", type=int, default=31413)
+    e = sub.add_parser("cheby-scale", help="the three scaling sweeps of scale2.sh with the cheby tool")
+    e.add_argument("workdir")
+    e.add_argument("--nodes", type=int, default=50000)
+    e.add_argument("--conn", type=float, default=0.01)
+    e.add_argument("--coeffs", type=int, default=64)
+    e.add_argument("--seed", type=int, default=31413)
     args = ap.parse_args(argv)
+    if args.cmd == "mega-graph":
+        print(mega_graph(args.size, args.conn, args.out, args.seed))
+        return 0
+    if args.cmd == "cheby-scale":
+        res = cheby_scale(args.workdir, args.nodes, args.conn, args.coeffs,
+                          sweep_nodes=range(args.nodes // 10, args.nodes + 1, args.nodes // 10), seed=args.seed)
+        print(json.dumps(res))
+        return 0
     if args.cmd == "fold":
         print(fold_cross_validation(args.filename, args.num_div, args.out, args.seed))
     elif args.cmd == "rmse":

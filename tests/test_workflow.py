@@ -109,3 +109,45 @@ def test_pipeline_two_folds(tmp_path):
 def test_run_pipeline_rejects_unknown_variant(tmp_path):
     with pytest.raises(ValueError):
         WF.run_pipeline(str(tmp_path), str(tmp_path / "w"), folds=[0], variant="nope")
+
+
+def test_mega_graph_generator(tmp_path):
+    """mega_graph.py:27-40: conn * size^2 distinct directed links without self links, weights with two decimals, one
+    signal line per vertex; seeded, so two runs write identical files."""
+    d = str(tmp_path / "g")
+    n = WF.mega_graph(300, 0.02, d, seed=4)
+    assert n == int(0.02 * 300 * 300)
+    topo = [l.split() for l in open(os.path.join(d, "graph_topology.txt"))]
+    assert len(topo) == n and len({(a, b) for a, b, _ in topo}) == n
+    assert all(a != b and 1 <= int(a) <= 300 and 1 <= int(b) <= 300 for a, b, _ in topo)
+    assert all(len(w.split(".")[1]) == 2 and 0.0 <= float(w) <= 1.0 for _, _, w in topo)
+    sig = [l.split() for l in open(os.path.join(d, "graph_signal.txt"))]
+    assert [int(v) for v, _ in sig] == list(range(1, 301)) and all(0.0 <= float(x) < 10.0 for _, x in sig)
+    first = open(os.path.join(d, "graph_topology.txt")).read()
+    WF.mega_graph(300, 0.02, d, seed=4)
+    assert first == open(os.path.join(d, "graph_topology.txt")).read()
+    with pytest.raises(ValueError):
+        WF.mega_graph(10, 1.0, d)
+
+
+def test_cheby_scale_driver_with_a_stub_tool(tmp_path):
+    """scale2.sh:5-36: the sweep driver around the cheby tool -- checked on CPU with a stand-in executable that prints the
+    two timing lines the script greps and records the inputs it was given."""
+    bin_dir = tmp_path / "bin"
+    bin_dir.mkdir()
+    stub = bin_dir / "cheby"
+    stub.write_text("#!/bin/sh\n"
+                    "echo \"$(wc -l < graph_topology.txt) $(wc -l < graph_signal.txt) $(wc -w < coeff.txt)\" >> calls.txt\n"
+                    "echo 'Loading graph. Finished in 0.25'\n"
+                    "echo 'Final Runtime (seconds):   0.5'\n")
+    stub.chmod(0o755)
+    work = str(tmp_path / "work")
+    res = WF.cheby_scale(work, nodes=200, conn=0.01, coeffs=6, sweep_coeffs=(3, 5), sweep_conn=(0.01, 0.02),
+                         sweep_nodes=(100, 200), seed=9, bin_dir=str(bin_dir), log=open(os.devnull, "w"))
+    assert [(r["nodes"], r["conn"], r["coeffs"]) for r in res] == [(200, 0.01, 3), (200, 0.01, 5), (200, 0.01, 6), (200, 0.02, 6),
+                                                                    (100, 0.01, 6), (200, 0.01, 6)]
+    assert all(r["load_s"] == 0.25 and r["runtime_s"] == 0.5 for r in res)
+    calls = [tuple(int(x) for x in l.split()) for l in open(os.path.join(work, "calls.txt"))]
+    assert calls == [(400, 200, 3), (400, 200, 5), (400, 200, 6), (800, 200, 6), (100, 100, 6), (400, 200, 6)]
+    lines = open(os.path.join(work, "scale_res2.jsonl")).read().splitlines()
+    assert len(lines) == 6
