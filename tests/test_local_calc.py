@@ -147,3 +147,29 @@ def test_cpp_restatement_agrees_with_numpy_oracle(golden_dir, which, honest, thr
             assert abs(float(out["err"][t]) - float(err)) <= 1e-5 * max(1.0, float(err))
             n_cmp += 1
     assert n_cmp > 50
+
+
+@pytest.mark.parametrize("n,kk", [(5, 1), (9, 4), (20, 7), (33, 32)])
+def test_closed_form_cutoff_on_a_clique(n, kk):
+    """Known answer that pins the cutoff independently of any solver: a local graph that is a clique with equal weights
+    has L = a I - b J (a = n/(n-1), b = 1/(n-1)), so L_h L_h^T = a^2 I - n/(n-1)^2 J on the unrated nodes and
+    w_lim = sqrt(n kk) / (n - 1) for kk rated neighbours.  The spectrum of L is {0, a (n-1 times)}: the max(.,2) rule cuts
+    through the degenerate cluster, which the oracle reports as gap ~ 0."""
+    from oracle import cpu_ref
+    movies = list(range(1, n + 1))
+    fin = [(a, b, 0.5) for a in movies for b in movies if a != b]
+    user = O.UIMAX - 1
+    test = {1: {user: 4.0}}
+    for m in movies[1:1 + kk]:
+        test[m] = {user: 3.0}
+    rows = O.local_calc_movie(1, O.item_graph_weights(fin), test)
+    assert len(rows) == 1
+    (_, _, _, kk_o, _, status, lim, w_lim, gap) = rows[0]
+    assert kk_o == kk and lim == 2 and abs(gap) <= 1e-9
+    assert abs(w_lim - np.sqrt(n * kk) / (n - 1)) <= 1e-12
+    # the C++ restatement (Householder + QL) meets the same closed form
+    offsets = np.array([0, kk + 1], dtype=np.int64)
+    items = np.array(movies[:kk + 1], dtype=np.int32)
+    ratings = np.array([4.0] + [3.0] * kk)
+    out = cpu_ref.local_calc(O.weights_from_fin(fin), offsets, items, ratings)
+    assert abs(out["w_lim"][0] - np.sqrt(n * kk) / (n - 1)) <= 1e-10 and out["kk"][0] == kk

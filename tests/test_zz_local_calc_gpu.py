@@ -210,3 +210,23 @@ def test_workflow_variant(tmp_path):
     assert [(l.split()[0], l.split()[1], l.split()[3]) for l in lines] == [(str(x[0]), str(x[1]), str(x[3])) for x in rows]
     if all(x[8] > 1e-6 and x[5] == O.PRED_OK for x in rows):
         assert abs(res[0]["rmse"] - O.rmse_of(rows)[0]) <= 1e-4
+
+
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("n,kk", [(5, 1), (20, 7), (33, 32), (70, 30)])
+def test_closed_form_cutoff_on_a_clique(ctx, monkeypatch, n, kk, exact):
+    """Solver-independent known answer (tests/test_local_calc.py derives it): on a clique with equal weights
+    w_lim = sqrt(n kk) / (n - 1) for every pair of a user who rated kk + 1 of the n movies; the spectrum of L is
+    {0, n/(n-1) x (n-1)}, so lim is the forced 2."""
+    if exact:
+        monkeypatch.setenv("GSI_LC_EXACT", "1")
+    movies = np.arange(1, n + 1)
+    a, b = np.meshgrid(movies, movies, indexing="ij")
+    sel = a != b
+    ctx.set_weights_edges(a[sel].astype(np.int32), b[sel].astype(np.int32), np.full(int(sel.sum()), 0.5))
+    offsets = np.array([0, kk + 1], dtype=np.int64)
+    items = movies[:kk + 1].astype(np.int32)
+    ratings = np.array([4.0] + [3.0] * kk)
+    out = ctx.local_calc(offsets, items, ratings)
+    assert (out["status"] != 4).all() and (out["kk"] == kk).all() and (out["cols"] == 2).all()
+    assert np.abs(out["w_lim"] - np.sqrt(n * kk) / (n - 1)).max() <= 1e-8
