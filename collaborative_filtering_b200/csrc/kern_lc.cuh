@@ -2,9 +2,11 @@
 // movie and its out-neighbours in the thresholded item graph), its normalised Laplacian L, P = L L^T, and per
 // (movie, test user) pair the exact cutoff w_lim = sigma_min(L[unrated rows, :]) = sqrt(lambda_min(P[unrated, unrated]))
 // followed by the band-limited least-squares prediction.  The per-movie eigensolve runs on the batched Householder /
-// divide & conquer / back-transform pipeline of hh_host.cuh, the per-pair one on its tridiagonalisation stage followed
-// by a Sturm-count bracket of the smallest eigenvalue; the kernels here build the pipeline's inputs (tile-major
-// symmetric matrices) and consume its outputs.
+// divide & conquer / back-transform pipeline of hh_host.cuh.  The per-pair cutoff needs one eigenvalue only: the fast
+// path (lc_lanczos_kernel) gets it by Lanczos through the movie's P without forming the pair's matrix; the exact path
+// (fallback, GSI_LC_EXACT=1) gathers the matrix, runs the pipeline's tridiagonalisation stage and brackets the smallest
+// eigenvalue of T on the Sturm count.  The other kernels build the pipeline's inputs (tile-major symmetric matrices)
+// and consume its outputs.
 #pragma once
 #include "gsi_internal.cuh"
 #include "kern_trd.cuh"
