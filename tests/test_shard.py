@@ -182,3 +182,27 @@ def test_gloo_world2_movie_deal_and_reduce(tmp_path):
     outs = [p.communicate(timeout=300)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "OK" in outs[0]
+
+
+def test_local_calc_shard_masks_through_the_api(monkeypatch):
+    """Context.local_calc_shard without a device: the call it forwards to is replaced by a recorder; the masks of the
+    ranks partition the requested pairs, movie ids beyond the table are left out, a movie's pairs stay together."""
+    from collaborative_filtering_b200.api import Context
+    r = D.make_ratings("ml-100k", n_users=60)
+    items = r.items.copy()
+    items[::97] = r.n_items + 50                          # ids outside the weight table
+    n_nodes = (np.arange(r.n_items + 1) * 31) % 400 + 1
+    base = (np.arange(len(items)) % 3 != 0).astype(np.uint8)
+    seen = []
+    ctx = Context.__new__(Context)                         # no gsi_create: only the host-side dealing is exercised
+    monkeypatch.setattr(Context, "local_calc", lambda self, off, it, rat, pair_mask=None: seen.append(np.array(pair_mask)) or {})
+    monkeypatch.setattr(Context, "__del__", lambda self: None, raising=False)
+    for rank in range(4):
+        ctx.local_calc_shard(r.offsets, items, r.ratings.astype(np.float64), n_nodes, rank, 4, pair_mask=base)
+    total = np.sum(seen, axis=0)
+    inside = items < len(n_nodes)
+    assert np.array_equal(total[inside], base[inside]) and (total[~inside] == 0).all()
+    owner_of = {}
+    for rank, m in enumerate(seen):
+        for movie in np.unique(items[m == 1]):
+            assert owner_of.setdefault(int(movie), rank) == rank
