@@ -5,14 +5,16 @@ pair, the three smallest eigenvalues of G, the number of Lanczos steps until the
 every 8 steps) and the error against numpy.linalg.eigvalsh.  Result recorded in profiles/r01w_local_calc.md: 8-24 steps,
 error <= 1.6e-15.  CPU only; imports the oracle for the Laplacian restatement (a script, not product code).
 
-    python scripts/proto_lanczos_lc.py
+    python scripts/proto_lanczos_lc.py [shape] [n_movies]
 """
 import sys, time
 import numpy as np
 sys.path.insert(0, ".")
 from collaborative_filtering_b200 import datasets as D
 from oracle import gsi_oracle as O
-r = D.make_ratings("ml-100k"); folds = D.fold_split(r, 5)
+shape = sys.argv[1] if len(sys.argv) > 1 else "ml-100k"
+n_sample = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+r = D.make_ratings(shape); folds = D.fold_split(r, 5)
 val_idx = np.sort(folds[0]); trn_idx = np.sort(np.concatenate(folds[1:]))
 _, v_off, v_items, v_rat = D.subset(r, val_idx)
 _, t_off, t_items, t_rat = D.subset(r, trn_idx)
@@ -37,7 +39,7 @@ for ui in range(len(val_idx)):
         test.setdefault(int(v_items[t]), {})[ui] = float(v_rat[t])
 rng = np.random.default_rng(0)
 movies = [m for m in test if keep[m].sum() + 1 >= 3]
-sample = rng.choice(movies, size=12, replace=False)
+sample = rng.choice(movies, size=n_sample, replace=False)
 def lanczos_min(G, tol=1e-13, maxit=600, seed=1):
     n = G.shape[0]
     rs = np.random.default_rng(seed)
