@@ -44,3 +44,28 @@ def test_product_never_touches_the_checker():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text, "%s references oracle/" % f
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The boundary is a C ABI: include/gsi.h must compile as C99 on its own (no C++ or CUDA types in the signatures),
+    and a C translation unit that calls an entry point must link against libgsi.so."""
+    import subprocess
+    from collaborative_filtering_b200 import _lib
+    hdr = os.path.join(ROOT, "include", "gsi.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-xc", hdr])
+    src = tmp_path / "probe.c"
+    src.write_text('#include <stdio.h>\n#include "gsi.h"\n'
+                   'int main(void) { gsi_ctx* c = 0; int rc = gsi_create(&c, 0, 0);\n'
+                   '  printf("%s|%d|%s\\n", gsi_version(), rc, gsi_last_error(c));\n'
+                   '  if (c) gsi_destroy(c);\n  return 0; }\n')
+    exe = str(tmp_path / "probe")
+    if not os.path.exists(_lib.SO_PATH):
+        _lib.build()
+    libdir = os.path.dirname(_lib.SO_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", exe, str(src), "-L", libdir, "-lgsi",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "sm_100a" in out.stdout
+    import torch
+    if not torch.cuda.is_available():
+        assert "|2|" in out.stdout and "no CPU fallback" in out.stdout      # GSI_ERR_CUDA, loudly
