@@ -173,3 +173,37 @@ def test_closed_form_cutoff_on_a_clique(n, kk):
     ratings = np.array([4.0] + [3.0] * kk)
     out = cpu_ref.local_calc(O.weights_from_fin(fin), offsets, items, ratings)
     assert abs(out["w_lim"][0] - np.sqrt(n * kk) / (n - 1)) <= 1e-10 and out["kk"][0] == kk
+
+
+def test_rating_zero_means_unrated_and_masks_drop_pairs():
+    """local_calc.cpp:406-413 tests `usr_rat(i) == 0`: a stored rating of 0 is indistinguishable from "not rated" -- in both
+    restatements; a pair mask (the --pct sample, :266) removes pairs without changing the others; movie ids beyond the weight
+    table have no vertex data and no line."""
+    from oracle import cpu_ref
+    fin, test = _random_case(7, n_items=30, n_users=12, density=0.5)
+    u0 = sorted({u for d in test.values() for u in d})[0]
+    zeroed = [m for m in sorted(test) if u0 in test[m]][1:3]
+    for m in zeroed:
+        test[m][u0] = 0.0                                            # two of this user's ratings read as "not rated"
+    weights = O.weights_from_fin(fin)
+    users, offsets, items, ratings = _csr(test)
+    rows = O.local_calc(fin, test)
+    out = cpu_ref.local_calc(weights, offsets, items, ratings, honest=False)
+    pos = {(int(items[t]), u): t for ui, u in enumerate(users) for t in range(offsets[ui], offsets[ui + 1])}
+    for (m, u, err, kk, pred, status, lim, w_lim, gap) in rows:
+        assert out["kk"][pos[(m, u)]] == kk
+    n_u0 = sum(1 for m in test if u0 in test[m])
+    for (m, u, err, kk, *_rest) in rows:
+        if u == u0 and m not in zeroed:
+            assert kk <= n_u0 - 1 - len(zeroed)                      # the zeroed movies never count as known
+    mask = (items % 2 == 1).astype(np.uint8)
+    part = cpu_ref.local_calc(weights, offsets, items, ratings, pair_mask=mask, honest=False)
+    assert (part["status"][mask == 0] == 4).all()
+    sel = mask == 1
+    for k in ("kk", "status", "lim"):
+        assert np.array_equal(part[k][sel], out[k][sel])
+    assert np.array_equal(part["w_lim"][sel], out["w_lim"][sel], equal_nan=True)
+    items2 = items.copy()
+    items2[0] = weights.shape[0] + 5                                 # outside the table: no vertex, no line
+    out2 = cpu_ref.local_calc(weights, offsets, items2, ratings, honest=False)
+    assert out2["status"][0] == 4
