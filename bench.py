@@ -2,17 +2,21 @@
 """bench.py -- users/s of the precompute hot path (gather + normalised Laplacian + full symmetric
 eigensolve + sig_min + cutoff) on ML-10M shaped synthetic data.
 
-Workload (per GPU, per step): one 1/8 shard of the ML-10M shape (71,567 users x 10,681 items,
-10.0M ratings; SURVEY.md 8d recipe, seed 31413), the shard a rank holds when the data set is
-user-sharded over an 8-GPU box by the n^3 cost model (LPT).  Weak scaling: rank r processes shard
-r, so --gpus 8 is exactly the whole ML-10M shape per step.  The item-similarity table W
-((N+1)^2 fp64, 913 MB) is generated on rank 0 and replicated with an NCCL broadcast.
+Workload (per step): the WHOLE ML-10M shape (71,567 users x 10,681 items, 10.0M ratings; SURVEY.md 8d
+recipe, seed 31413 -- BASELINE.json configs[2], the configuration the metric is quoted on), user-sharded
+over the N GPUs of the run by the n^3 cost model (LPT, shard.py): rank r processes shard r of N, so every N
+solves the same data set per step (strong scaling; at N = 1 one GPU takes all 71,567 users in
+workspace-sized chunks).  The item-similarity table W ((N+1)^2 fp64, 913 MB) is generated on rank 0 and
+replicated with an NCCL broadcast.  There is no data-path collective.
 
   value    users/s, device resident: CSR ids in HBM -> records (sig_min, k, lam, U) in HBM
   e2e      users/s through the host-facing C ABI (gsi_precompute_stream): pinned host CSR in,
            records out in pinned host memory, H2D / D2H copies inside the timed region
-  roofline the eigensolve kernels (the dominant device time) against the FP64 FMA peak measured
-           live (MEASURED_PEAKS.json has no FP64 number), algorithmic flops = 9 n^3 per user
+  roofline the eigensolve kernel group (trd + dc + dc_gemm + bt: the dominant device time) against the FP64
+           peak measured live (MEASURED_PEAKS.json has no FP64 number), algorithmic flops = 9 n^3 per user
+           (SURVEY.md 8d); the HBM view of trd_kernel and of the Laplacian stage are `secondary`
+  parity   after the timed region: the 3 largest and 20 random users of rank 0's shard against the oracle
+  predict  predictions/s, RMSE and RMSE delta vs the oracle on fold 0 of the ML-1M shape (configs[1])
   cpu_baseline  oracle/cpu_ref (C++ restatement of precompute_local_threads.cpp, all host threads)
            timed on a bounded stratified sample and extrapolated by the n^3 cost model
 
@@ -38,21 +42,30 @@ from collaborative_filtering_b200 import shard as SH  # noqa: E402
 
 METRIC = "users/sec Laplacian+eigensolve at ML-10M shape"
 UNIT = "users/s"
-N_SHARDS = 8
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def build_workload(shape: str, rank: int):
-    """Ratings of `shape`, LPT-sharded into 8 by n^3; returns the CSR of shard (rank mod 8)."""
+def bench_config(shape: str) -> dict:
+    """The workload description, identical in both arms (`--impl gsi` and `--impl reference`) and at every N."""
+    users, items, nnz = D.SHAPES[shape][:3]
+    return {"workload": "%s shape: %d users x %d items, %d ratings (SURVEY.md 8d recipe, seed %d), the WHOLE data set per step, "
+                        "user-sharded over the GPUs of the run by LPT on n^3; synthetic symmetric W, density 0.9, fp64 (N+1)^2 table"
+                        % (shape, users, items, nnz, D.SEED),
+            "users_per_step": int(users), "items": int(items),
+            "l2": "256 MiB flush write between steps; working set per step >> 126 MB L2"}
+
+
+def build_workload(shape: str, rank: int, world: int):
+    """Ratings of `shape`, LPT-sharded into `world` by n^3; returns (ratings, CSR of shard `rank`, the shard's user indices)."""
     r = D.make_ratings(shape)
-    deg = r.degrees()
-    owners = SH.lpt_assign(deg, N_SHARDS)
-    idx = np.nonzero(owners == (rank % N_SHARDS))[0]
+    if world == 1:
+        return r, r.offsets, r.items, np.arange(r.n_users)
+    idx = SH.shard_users(r.degrees(), rank, world)
     _, offsets, items, _ = D.subset(r, idx)
-    return r, offsets, items
+    return r, offsets, items, idx
 
 
 class ClockSampler(threading.Thread):
@@ -135,6 +148,7 @@ def cpu_reference_rate(weights, offsets, items, budget_s: float = 15.0, threads:
     est_total = 0.0
     last_coef = None
     measured_s = 0.0
+    n3_measured = 0.0
     for s in sorted(per_stratum):
         us = per_stratum[s]
         off = np.zeros(len(us) + 1, dtype=np.int64)
@@ -145,19 +159,22 @@ def cpu_reference_rate(weights, offsets, items, budget_s: float = 15.0, threads:
         c3 = out["seconds"] / float((deg[us].astype(np.float64) ** 3).sum())
         last_coef = c3
         all_in = np.array([u for u in strata[s] if deg[u] <= n_cap])
+        n3_measured += float((deg[all_in].astype(np.float64) ** 3).sum())
         est_total += c3 * float((deg[all_in].astype(np.float64) ** 3).sum())
     heavy = deg[deg > n_cap].astype(np.float64)
     est_total += (last_coef or coef / cores) * float((heavy ** 3).sum())
-    desc = ("%d of %d users (stratified by log2 n, n <= %d) timed in %.1f s on %d threads with text formatting; "
-            "%d heavier users extrapolated by the n^3 coefficient of the largest stratum"
-            % (len(picked), len(deg), n_cap, measured_s, cores, len(heavy)))
+    n3_all = float((deg.astype(np.float64) ** 3).sum())
+    desc = ("%d of %d users (stratified by log2 n, n <= %d) timed in %.1f s on %d threads with text formatting; the %d heavier users "
+            "(%.0f %% of sum n^3) are extrapolated by the n^3 coefficient of the largest timed stratum; the workload would take "
+            "%.0f s on this host" % (len(picked), len(deg), n_cap, measured_s, cores, len(heavy),
+                                     100.0 * (1.0 - n3_measured / n3_all), est_total))
     return len(deg) / est_total, desc, cores
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    r, offsets, items = build_workload(args.shape, 0)
+    r, offsets, items, _ = build_workload(args.shape, 0, 1)      # the CPU arm runs the whole data set on the host cores at every N
     w = D.make_weights(r.n_items)
     for _ in range(args.warmup):
         cpu_reference_rate(w, offsets, items, budget_s=1.0)
@@ -170,57 +187,64 @@ def run_reference(args, rank, world):
     v = float(np.mean(rates))
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s shape, 1/8 user shard per GPU (LPT by n^3), synthetic W density 0.9" % args.shape,
-                   "users_per_step": int(len(offsets) - 1)},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "config": bench_config(args.shape),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                         "note": "ms_per_step is the time of the bounded sample; value describes the whole workload (users / estimated seconds)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------
-# auxiliary: predictions/s of the local_calc_precomp stage on a bounded sample (second half of
-# BASELINE.json's metric string).  ML-100K shape, item graph built by the knn2 stage itself (cosine
-# weights), users with n <= 256, one prediction per (user, rated movie) pair.
+# predictions/s + RMSE + RMSE delta (second and third term of BASELINE.json's metric) on configs[1]:
+# ML-1M shape, 5-fold user split (fold_cross_validation.py:11-56), fold 0 = validation, the item graph from
+# the knn2 stage on the four train folds, one prediction per (validation user, rated movie) pair.
 # ---------------------------------------------------------------------------------------------
-def deal_users(deg, nmax, rank, world):
-    """Users with n <= nmax, dealt round robin over the ranks by descending n (users are independent units)."""
-    sel_all = np.nonzero(deg <= nmax)[0]
-    sel_all = sel_all[np.argsort(-deg[sel_all], kind="stable")]
-    return sel_all, np.sort(sel_all[rank::world])
-
-
-def reduce_predict_stats(npairs, flop, se_ok, n_ok, kernel_ms, wall, device):
-    """all-reduce of (pair count, flops, sum of squared errors, well-posed count) and the slowest rank's times."""
+def reduce_predict_stats(vals, maxes, device):
+    """all-reduce of the sums (pair count, flops, squared errors, ...) and the slowest rank's times."""
     import torch
     import torch.distributed as dist
-    sums = torch.tensor([npairs, flop, se_ok, n_ok], dtype=torch.float64, device=device)
-    mx = torch.tensor([kernel_ms, wall], dtype=torch.float64, device=device)
+    sums = torch.tensor(vals, dtype=torch.float64, device=device)
+    mx = torch.tensor(maxes, dtype=torch.float64, device=device)
     dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-    return int(sums[0].item()), float(sums[1].item()), float(sums[2].item()), int(sums[3].item()), float(mx[0].item()), float(mx[1].item())
+    return [float(x) for x in sums.tolist()], [float(x) for x in mx.tolist()]
 
 
-def predict_sample(local_rank, rank=0, world=1, nmax=256):
-    """Collective over the ranks: every rank builds the (replicated) item graph, predicts the pairs of its share of the
-    users (users are independent: dealt round robin by descending n), and the counts / squared errors / slowest kernel
-    time are all-reduced.  The returned numbers are whole-job."""
+def deal_users(deg, rank, world):
+    """Users dealt round robin over the ranks by descending n (users are independent units; all predictions of a user
+    stay next to its U)."""
+    order = np.argsort(-deg, kind="stable")
+    return np.sort(order[rank::world])
+
+
+def predict_fold(local_rank, rank=0, world=1, shape="ml-1m", fold=0, oracle_pairs=1500, nmax_oracle=400):
+    """Collective over the ranks.  Returns the whole-job block printed as "predict" (rank 0 adds the oracle comparison)."""
     from collaborative_filtering_b200.api import Context
-    r = D.make_ratings("ml-100k")
+    r = D.make_ratings(shape)
+    folds = D.fold_split(r, 5)
+    val_idx = np.sort(folds[fold])
+    trn_idx = np.sort(np.concatenate([f for i, f in enumerate(folds) if i != fold]))
+    _, t_off, t_items, t_rat = D.subset(r, trn_idx)
     c2 = Context(local_rank)
     try:
-        c2.knn_build(r.offsets, r.items, r.ratings, r.n_items + 1, install_weights=True)
-        deg = np.diff(r.offsets)
-        sel_all, sel = deal_users(deg, nmax, rank, world)
-        _, s_off, s_items, s_rat = D.subset(r, sel)
-        recs = c2.precompute(s_off, s_items)
-        c2.predict(recs, s_rat.astype(np.float64))                       # warm-up
         c2.timing_enable(True)
         c2.timing_reset()
         t0 = time.perf_counter()
-        out = c2.predict(recs, s_rat.astype(np.float64))
+        a, b, w = c2.knn_build(t_off, t_items, t_rat, r.n_items + 1, install_weights=True)     # every rank builds the (replicated) graph
+        knn_wall = time.perf_counter() - t0
+        knn_ms = c2.timing()["knn"]["ms"]
+        deg_val = r.degrees()[val_idx]
+        mine = val_idx[deal_users(deg_val, rank, world)]
+        _, s_off, s_items, s_rat = D.subset(r, mine)
+        recs = c2.precompute(s_off, s_items)
+        rat64 = s_rat.astype(np.float64)
+        c2.predict(recs, rat64)                                                                 # warm-up
+        c2.timing_reset()
+        t0 = time.perf_counter()
+        out = c2.predict(recs, rat64)
         wall = time.perf_counter() - t0
         tm = c2.timing()["predict"]
         npairs = int(s_off[-1])
@@ -228,23 +252,79 @@ def predict_sample(local_rank, rank=0, world=1, nmax=256):
         kk_ok, c_ok = out["kk"][ok].astype(np.float64), out["cols"][ok].astype(np.float64)
         # algorithmic flops of the reference's per-pair solve: Gram + inverse + products
         flop = float((2 * kk_ok * c_ok ** 2 + (2.0 / 3.0) * c_ok ** 3 + 2 * kk_ok * c_ok + 2 * c_ok ** 2).sum())
-        kernel_ms, se_ok, n_ok = tm["ms"], float(out["err"][ok].astype(np.float64).sum()), int(ok.sum())
-        if world > 1:                                     # whole-job numbers: sums over the ranks, time of the slowest rank
+        se_ok, n_ok = float(out["err"][ok].astype(np.float64).sum()), int(ok.sum())
+        # every pair the reference would print (kk > 0): the clamp makes NaN-free errors for all of them
+        se_all = float(np.nan_to_num(out["err"].astype(np.float64)).sum())
+        kernel_ms = tm["ms"]
+        sums, maxes = [npairs, flop, se_ok, n_ok, se_all], [kernel_ms, wall]
+        if world > 1:
             import torch
-            npairs, flop, se_ok, n_ok, kernel_ms, wall = reduce_predict_stats(
-                npairs, flop, se_ok, n_ok, kernel_ms, wall, torch.device("cuda", local_rank))
-        tf = flop / (kernel_ms * 1e-3) / 1e12 / world       # per-GPU rate against the per-GPU peak
+            sums, maxes = reduce_predict_stats(sums, maxes, torch.device("cuda", local_rank))
+        npairs_all, flop_all, se_ok_all, n_ok_all, se_all_all = sums
+        kernel_ms_all, wall_all = maxes
+        tf = flop_all / (kernel_ms_all * 1e-3) / 1e12 / world              # per-GPU rate against the per-GPU peak
         peak = c2.measure_fp64_tflops(True)
-        tm = dict(tm, ms=kernel_ms)
-        return {"value": npairs / (tm["ms"] * 1e-3), "unit": "predictions/s", "e2e_value": npairs / wall, "n_gpus": world,
-                "roofline": {"kernel": "predict2_kernel (bordered Gram + blocked Cholesky, FP64 MMA)", "bound": "fp64 tensor",
-                             "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak if peak else None,
-                             "algorithmic_flop": flop, "peak_source": "DMMA m8n8k4 probe measured live (gsi_measure_fp64_tflops)"},
-                "pairs": npairs, "well_posed_fraction": n_ok / max(1, npairs), "kernel_ms": tm["ms"], "launches": tm["launches"],
-                "rmse_well_posed": float(np.sqrt(se_ok / n_ok)) if n_ok else None,
-                "sample": "ml-100k shape, knn2-built item graph, %d users with n <= %d dealt over %d rank(s), every (user, rated "
-                          "movie) pair; value = kernel time (CUDA events, slowest rank), e2e_value = gsi_predict_host wall time "
-                          "with host buffers; counts and squared errors all-reduced" % (len(sel_all), nmax, world)}
+        block = {
+            "value": npairs_all / (kernel_ms_all * 1e-3), "unit": "predictions/s", "e2e_value": npairs_all / wall_all, "n_gpus": world,
+            "config": "%s shape, fold %d of the 5-fold user split as validation (%d users, max n %d), item graph = knn2 weights of the "
+                      "four train folds, every (validation user, rated movie) pair" % (shape, fold, len(val_idx), int(deg_val.max())),
+            "pairs": int(npairs_all), "well_posed_fraction": n_ok_all / max(1.0, npairs_all), "kernel_ms": kernel_ms_all,
+            "e2e_s": wall_all, "launches": tm["launches"],
+            "rmse_well_posed": float(np.sqrt(se_ok_all / n_ok_all)) if n_ok_all else None,
+            "rmse_all_pairs": float(np.sqrt(se_all_all / npairs_all)) if npairs_all else None,
+            "roofline": {"kernel": "predict2_kernel (bordered Gram + blocked Cholesky, FP64 MMA)", "bound": "fp64 tensor",
+                         "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak if peak else None,
+                         "algorithmic_flop": flop_all, "peak_source": "DMMA m8n8k4 probe measured live (gsi_measure_fp64_tflops)"},
+            "knn": {"what": "knn2 stage on the four train folds (%d users, %d ratings): co-rater accumulation + cosine finalise + edge "
+                            "compaction, bit-exact float sums" % (len(trn_idx), int(t_off[-1])),
+                    "kernel_ms": knn_ms, "wall_s": knn_wall, "edges": int(len(w)),
+                    "pair_updates_per_s": float(((np.diff(t_off).astype(np.float64) ** 2 - np.diff(t_off)) / 2).sum() / (knn_ms * 1e-3)) if knn_ms else None},
+            "value_is": "kernel time (CUDA events, slowest rank); e2e_value = gsi_predict_host wall time with host buffers",
+        }
+        if rank == 0 and oracle_pairs > 0:
+            # ---- RMSE delta: the oracle's predictor (numpy restatement of local_calc_precomp.cpp:217-380) on the SAME records
+            # (stage-wise protocol) over a seeded sample of this rank's pairs from users with n <= nmax_oracle
+            from oracle import gsi_oracle as O
+            graph = O.item_graph([(int(x), int(y), float(z)) for x, y, z in zip(a, b, w)])
+            rng = np.random.default_rng(D.SEED + 7)
+            deg_s = np.diff(s_off)
+            cand = np.nonzero(deg_s <= nmax_oracle)[0]
+            pairs = []
+            for ui in cand:
+                pairs.extend((int(ui), j) for j in range(int(deg_s[ui])))
+            pick = rng.choice(len(pairs), size=min(oracle_pairs, len(pairs)), replace=False)
+            t0 = time.perf_counter()
+            se_g = se_o = 0.0
+            n_cmp = mism = 0
+            dpred = 0.0
+            cache = {}
+            for pi in pick:
+                ui, j = pairs[pi]
+                if ui not in cache:
+                    its = s_items[s_off[ui]: s_off[ui + 1]]
+                    cache[ui] = (dict(items=its.astype(np.int64), row_of={int(m): q for q, m in enumerate(its)},
+                                      sigs_min=recs.sig_of(ui), lam=recs.lam_of(ui), vec=recs.vec_of(ui)),
+                                 {int(m): float(s_rat[s_off[ui] + q]) for q, m in enumerate(its)})
+                ud, ur = cache[ui]
+                m = int(ud["items"][j])
+                err, kk, pred, status, c = O.predict_pair(ud, m, graph.get(m, set()), ur, ur[m])
+                g = s_off[ui] + j
+                ok_g, ok_o = out["status"][g] == 0, status == O.PRED_OK
+                if ok_g != ok_o:
+                    mism += 1
+                if ok_g and ok_o:
+                    n_cmp += 1
+                    se_g += float(out["err"][g])
+                    se_o += float(err)
+                    dpred = max(dpred, abs(float(out["pred"][g]) - float(pred)))
+            rg = float(np.sqrt(se_g / n_cmp)) if n_cmp else None
+            ro = float(np.sqrt(se_o / n_cmp)) if n_cmp else None
+            block["rmse_parity"] = {
+                "rmse_gpu": rg, "rmse_oracle": ro, "rmse_delta": abs(rg - ro) if n_cmp else None, "bar": 1e-4,
+                "pairs_compared": n_cmp, "status_mismatches": mism, "max_abs_pred_diff": dpred,
+                "sample": "%d seeded pairs of rank 0's users with n <= %d, oracle predictor on the same records (%.1f s of numpy)"
+                          % (len(pick), nmax_oracle, time.perf_counter() - t0)}
+        return block
     finally:
         c2.close()
 
@@ -255,7 +335,7 @@ def predict_sample(local_rank, rank=0, world=1, nmax=256):
 
 def bind_to_gpu_numa_node(local_rank):
     """One process per GPU: run (and therefore allocate the pinned record staging) on the CPUs of the NUMA node the GPU
-    hangs off, so that the 4 GB of records a rank copies back per step do not cross the socket interconnect.  Returns
+    hangs off, so that the records a rank copies back per step do not cross the socket interconnect.  Returns
     the node, or None when the topology is not exposed (single socket, container without /sys)."""
     try:
         import torch
@@ -277,6 +357,31 @@ def bind_to_gpu_numa_node(local_rank):
     return None
 
 
+def parity_block(offsets, items, w_host, d_sig, d_k, d_lo, d_vo, d_lam, d_vec, n_random=20, n_largest=3):
+    """after the timed region, the records of the last timed step -- the shard's largest users and a
+    seeded random sample -- against the oracle (oracle/light_check.py).  The oracle is the checker here, nothing else."""
+    from oracle.light_check import check_record, summarise
+    deg = np.diff(offsets)
+    rng = np.random.default_rng(D.SEED + 5)
+    largest = np.argsort(-deg, kind="stable")[:n_largest]
+    rest = np.setdiff1d(np.arange(len(deg)), largest)
+    users = list(largest) + list(rng.choice(rest, size=min(n_random, len(rest)), replace=False))
+    k = d_k.cpu().numpy()
+    lo = d_lo.cpu().numpy()
+    vo = d_vo.cpu().numpy()
+    rows, t0 = [], time.perf_counter()
+    for u in users:
+        n, ku = int(deg[u]), int(k[u])
+        lam = d_lam[int(lo[u]): int(lo[u]) + ku].cpu().numpy()
+        vec = d_vec[int(vo[u]): int(vo[u]) + n * ku].cpu().numpy()
+        sig = d_sig[int(offsets[u]): int(offsets[u + 1])].cpu().numpy()
+        rows.append(check_record(items[offsets[u]: offsets[u + 1]], w_host, sig, ku, lam, vec))
+    s = summarise(rows)
+    s["what"] = "records of the last timed step on rank 0: its %d largest users and %d seeded random ones" % (len(largest), len(users) - len(largest))
+    s["seconds"] = time.perf_counter() - t0
+    return s
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -288,7 +393,7 @@ def run_gpu(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     t_gen = time.time()
-    r, offsets, items = build_workload(args.shape, rank)
+    r, offsets, items, _ = build_workload(args.shape, rank, world)
     nu = len(offsets) - 1
     deg = np.diff(offsets)
     log("[rank %d] shard: %d users, nnz %d, max n %d, sum 9n^3 = %.3g flop (gen %.1fs)"
@@ -311,11 +416,13 @@ def run_gpu(args, rank, world, local_rank):
     if world > 1:
         dist.broadcast(d_w, src=0)
     torch.cuda.synchronize()
+    torch.cuda.empty_cache()
 
     stream = torch.cuda.current_stream()
     ctx = Context(local_rank, stream=stream.cuda_stream)
     ctx.set_workspace_limit(args.workspace_gb << 30)
     ctx.set_weights(d_w)
+    small_max = ctx.small_max
     fp64_peak = ctx.measure_fp64_tflops(False)
     dmma_peak = ctx.measure_fp64_tflops(True)
 
@@ -359,11 +466,22 @@ def run_gpu(args, rank, world, local_rank):
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_rank = ms_total
     ms_total = float(t.item())
     users_total = torch.tensor([nu], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(users_total, op=dist.ReduceOp.SUM)
     value = float(users_total.item()) * args.steps / (ms_total * 1e-3)
+
+    # ---- parity of what was just timed (rank 0's shard) ----
+    parity = None
+    w_host = None
+    if rank == 0 and not args.no_parity:
+        w_host = d_w.cpu().numpy()
+        parity = parity_block(offsets, items, w_host, d_sig, d_k, d_lo, d_vo, d_lam, d_vec)
+        log("[parity]", json.dumps(parity))
+    del d_lam, d_vec                                   # the host path below stages its own records
+    torch.cuda.empty_cache()
 
     # ---- e2e through the host-facing C ABI: pinned CSR in, records out in pinned staging ----
     h_off = offsets
@@ -390,89 +508,98 @@ def run_gpu(args, rank, world, local_rank):
     e2e_value = float(users_total.item()) * args.e2e_steps / float(t.item())
     h2d_bytes = int(items.nbytes)
     d2h_bytes = d2h[0] // max(1, args.e2e_steps)
+    io = torch.tensor([h2d_bytes, d2h_bytes], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(io, op=dist.ReduceOp.SUM)
+    h2d_bytes, d2h_bytes = int(io[0].item()), int(io[1].item())
+    ctx.close()
+    del ctx
+    torch.cuda.empty_cache()
 
-    # ---- auxiliary predictions/s sample: a collective over the ranks (users dealt over the GPUs, sums all-reduced) ----
+    # ---- predictions/s, RMSE, RMSE delta on the ML-1M fold: a collective over the ranks ----
     predict_aux = None
     if not args.no_predict:
-        predict_aux = predict_sample(local_rank, rank, world)
+        predict_aux = predict_fold(local_rank, rank, world)
 
     if rank == 0:
-        # ---- roofline of the dominant kernel group (live CUDA-event times of the timed region) ----
+        # ---- roofline (live CUDA-event times of the timed region; every class is timed on every launch) ----
         def est_ms(name):
             v = timing[name]
             return v["ms"] * (v["launches"] / v["samples"]) if v["samples"] else 0.0
-        small = deg[deg <= ctx.small_max].astype(np.float64)
-        large = deg[deg > ctx.small_max].astype(np.float64)
+        large = deg[deg > small_max].astype(np.float64)
         n3_large = float((large ** 3).sum())
+        n3_all = float((deg.astype(np.float64) ** 3).sum())
         kernels = {k: {"ms_per_step": est_ms(k) / args.steps, "launches_per_step": timing[k]["launches"] / args.steps,
                        "avg_launch_us": (1e3 * timing[k]["ms"] / timing[k]["samples"]) if timing[k]["samples"] else None}
                    for k in timing if timing[k]["launches"]}
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
-        # ---- dominant kernel: trd_kernel, ONE persistent launch per step over every user with n > 160.
-        # Algorithmic bytes per user: the symmetric half of the trailing matrix is streamed
-        # once per column, 8 (n-j)^2 / 2 bytes -> (4/3) n^3, plus read+write of it once per 64-column panel for the
-        # rank-128 trailing update -> n^3 / 24:   B_trd(n) = 1.375 n^3 bytes.
-        use_bj = timing["bj_update"]["launches"] > 0
-        trd_ms = est_ms("trd") / max(1, timing["trd"]["launches"])             # average launch duration, live CUDA events
-        trd_bytes = 1.375 * n3_large * args.steps / max(1, timing["trd"]["launches"])   # per launch
-        trd_gbs = trd_bytes / (trd_ms * 1e-3) / 1e9 if trd_ms > 0 else 0.0
-        # ---- the whole eigensolve group against the FP64 peak: 9 n^3 flop per user
-        grp = ["bj_gram", "bj_inner", "bj_update"] if use_bj else ["trd", "dc", "dc_gemm", "bt"]
+        # ---- headline: the whole eigensolve group against the FP64 peak, 9 n^3 flop per user ----
+        grp = [k for k in ("trd", "sbr", "dc", "dc_gemm", "bt") if k in timing and timing[k]["launches"]]
         grp_ms = sum(est_ms(k) for k in grp) / args.steps
         eig_tf = 9.0 * n3_large / (grp_ms * 1e-3) / 1e12 if grp_ms > 0 else 0.0
+        # ---- secondary: the HBM view of the one-stage tridiagonalisation and of the Laplacian stage ----
+        # trd_kernel streams the symmetric half of the trailing matrix once per column, 8 (n-j)^2 / 2 bytes -> (4/3) n^3, plus
+        # read+write of it once per 64-column panel for the rank-128 trailing update -> n^3 / 24:  B_trd(n) = 1.375 n^3 bytes.
+        trd_ms = est_ms("trd") / args.steps
+        trd_bytes = 1.375 * n3_large
+        trd_gbs = trd_bytes / (trd_ms * 1e-3) / 1e9 if trd_ms > 0 else 0.0
         lap_bytes = float((8.0 * large ** 2 + 12.0 * large).sum())          # 8n^2 (fp64 table) + ids + sig_min
         lap_ms = est_ms("lap") / args.steps
         roofline = {
-            "kernel": "trd_kernel (blocked Householder tridiagonalisation, persistent team kernel, n > %d)" % ctx.small_max,
-            "bound": "hbm", "achieved": trd_gbs, "peak": hbm_peak, "unit": "GB/s",
-            "frac": trd_gbs / hbm_peak if hbm_peak else None,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture of this same
-            # workload (profiles/r01d_prof_trd_raw.csv): 1.841 TB + 67.2 GB per launch
-            "traffic": 1.908e12 if (args.shape == "ml-10m" and not use_bj and ctx.small_max <= 80) else None,
-            "peak_source": hbm_src,
-            "algorithmic_bytes_per_launch": trd_bytes, "avg_launch_ms": trd_ms,
-            "algorithmic_bytes_per_unit": "1.375 n^3 per user (4/3 n^3 half-matrix symv stream + n^3/24 trailing update)",
-            "share_of_step": (est_ms("trd") / args.steps) / (ms_total / args.steps) if ms_total > 0 else None,
-            "eigensolve_fp64": {
-                "kernels": "+".join(grp), "bound": "fp64", "achieved": eig_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": eig_tf / fp64_peak if fp64_peak else None, "algorithmic_flop_per_step": 9.0 * n3_large,
-                "peak_source": "FP64 FMA peak measured live by gsi_measure_fp64_tflops (MEASURED_PEAKS.json has no FP64 figure); "
-                               "DMMA m8n8k4 probe %.1f TF/s" % dmma_peak,
-                "executed_vs_algorithmic": "9 n^3 per user is credited (SURVEY.md 8d); Householder + D&C executes ~4-5 n^3 "
-                                           "(4/3 n^3 tridiagonalisation, ~1-2 n^3 merges, 2 n^2 k back-transform)"},
-            "secondary": {"kernel": "lap_* (gather+Laplacian+sig_min, n>%d)" % ctx.small_max, "bound": "hbm",
-                          "achieved": (lap_bytes / (lap_ms * 1e-3) / 1e9) if lap_ms > 0 else None, "peak": hbm_peak,
-                          "unit": "GB/s", "frac": (lap_bytes / (lap_ms * 1e-3) / 1e9 / hbm_peak) if lap_ms > 0 else None,
-                          "peak_source": hbm_src},
+            "kernel": "eigensolve group (%s) of the users with n > %d: Householder tridiagonalisation, divide & conquer, back-transform"
+                      % ("+".join(grp), small_max),
+            "bound": "fp64", "achieved": eig_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": eig_tf / fp64_peak if fp64_peak else None,
+            "traffic": None,
+            "algorithmic_flop_per_step": 9.0 * n3_large, "group_ms_per_step": grp_ms,
+            "algorithmic_flop_per_unit": "9 n^3 per user (SURVEY.md 8d: 4/3 n^3 tridiagonalisation + 4/3 n^3 Q + ~6 n^3 QR iterations)",
+            "peak_source": "FP64 FMA peak measured live by gsi_measure_fp64_tflops (MEASURED_PEAKS.json has no FP64 figure); "
+                           "DMMA m8n8k4 probe %.1f TF/s" % dmma_peak,
+            "executed_vs_algorithmic": "9 n^3 per user is credited; Householder + D&C executes ~4-5 n^3 (4/3 n^3 tridiagonalisation, "
+                                       "~1-2 n^3 merges, 2 n^2 k back-transform)",
+            "share_of_step": grp_ms / (ms_rank / args.steps) if ms_rank > 0 else None,
+            "secondary": [
+                {"kernel": "trd_kernel (one-stage blocked Householder tridiagonalisation, persistent team kernel)", "bound": "hbm",
+                 "achieved": trd_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": trd_gbs / hbm_peak if hbm_peak else None,
+                 "algorithmic_bytes_per_step": trd_bytes, "ms_per_step": trd_ms, "peak_source": hbm_src,
+                 "algorithmic_bytes_per_unit": "1.375 n^3 per user (4/3 n^3 half-matrix symv stream + n^3/24 trailing update); builder's "
+                                               "model of the one-stage algorithm, not SURVEY.md 8d's 4n^2 + 4(k+nk)",
+                 "traffic_note": "ncu --set full of this kernel on the 1/8 shard (profiles/r01k_prof_trd_raw.csv): 1.908 TB per launch = "
+                                 "1.13 x the model"},
+                {"kernel": "lap_fused_gather + lap_fused_transform (gather + Laplacian + sig_min, n > %d)" % small_max, "bound": "hbm",
+                 "achieved": (lap_bytes / (lap_ms * 1e-3) / 1e9) if lap_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
+                 "frac": (lap_bytes / (lap_ms * 1e-3) / 1e9 / hbm_peak) if lap_ms > 0 else None, "peak_source": hbm_src,
+                 "algorithmic_bytes_per_unit": "8 n^2 + 12 n per user (fp64 table gather + ids + sig_min; SURVEY.md 8d with the fp64 table)"},
+            ],
         }
         launches = int(sum(v["launches"] for v in timing.values()) // args.steps)
         # ---- CPU baseline on this box's host cores (bounded sample) ----
         cpu = None
         if not args.no_cpu and world == 1:               # reported baseline: rank 0 at N = 1 only
-            w_host = d_w.cpu().numpy()
+            if w_host is None:
+                w_host = d_w.cpu().numpy()
             rate, desc, cores = cpu_reference_rate(w_host, offsets, items, budget_s=args.cpu_budget)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s shape, 1/8 user shard per GPU (LPT by n^3), synthetic W density 0.9" % args.shape,
-                       "users_per_step_per_gpu": nu, "nnz_per_step_per_gpu": int(offsets[-1]), "max_n": int(deg.max()),
-                       "l2": "256 MiB flush write between steps; working set per step >> 126 MB L2",
-                       "outputs_doubles_per_step": list(used), "numa_node_of_rank0": numa},
+            "config": bench_config(args.shape),
+            "shard_of_rank0": {"users": nu, "nnz": int(offsets[-1]), "max_n": int(deg.max()), "sum_n3": n3_all,
+                               "outputs_doubles_per_step": list(used), "numa_node": numa, "workspace_gb": args.workspace_gb},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "steps": args.e2e_steps},
             "gpu_launches": launches,
             "roofline": roofline,
             "kernels": kernels,
+            "parity": parity,
             "cpu_baseline": cpu,
             "predict": predict_aux,
+            "rmse_delta": (predict_aux or {}).get("rmse_parity", {}).get("rmse_delta") if predict_aux else None,
         }
         print(json.dumps(line), flush=True)
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -484,10 +611,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gsi", choices=["gsi", "reference"])
     ap.add_argument("--shape", default="ml-10m", choices=sorted(D.SHAPES))
-    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-predict", action="store_true", help="skip the auxiliary predictions/s sample")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-timed parity block")
+    ap.add_argument("--no-predict", action="store_true", help="skip the predictions/s + RMSE block (ML-1M fold)")
     ap.add_argument("--workspace-gb", type=int, default=64)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -62,6 +62,18 @@ SYMBOLS = {
                                             ctypes.c_void_p]),
     "gsi_knn3_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 6),
     "gsi_cheby_filter_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 4 + [ctypes.c_int] + [ctypes.c_void_p] * 2),
+    "gsi_group_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p]),
+    "gsi_group_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "gsi_group_size": (ctypes.c_int, [ctypes.c_void_p]),
+    "gsi_group_ctx": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int]),
+    "gsi_group_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "gsi_group_broadcast_path": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "gsi_group_set_workspace_limit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
+    "gsi_group_set_weights_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "gsi_group_precompute_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                                   RECORD_SINK, ctypes.c_void_p]),
+    "gsi_group_predict_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 8 + [ctypes.c_int64, ctypes.c_void_p,
+                                              ctypes.c_int64] + [ctypes.c_void_p] * 6),
     "gsi_timing_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "gsi_timing_reset": (ctypes.c_int, [ctypes.c_void_p]),
     "gsi_timing_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

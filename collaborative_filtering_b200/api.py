@@ -61,6 +61,129 @@ def upper_bounds(offsets: np.ndarray):
     return int(m.sum()), int((n * m).sum())
 
 
+def _predict_args(recs: "Records") -> dict:
+    """The record arrays in the dtypes / layout the C ABI reads (copies only where needed)."""
+    return dict(offsets=np.ascontiguousarray(recs.offsets, dtype=np.int64), items=np.ascontiguousarray(recs.items, dtype=np.int32),
+                k=np.ascontiguousarray(recs.k, dtype=np.int32), lam_off=np.ascontiguousarray(recs.lam_off, dtype=np.int64),
+                vec_off=np.ascontiguousarray(recs.vec_off, dtype=np.int64), lam=np.ascontiguousarray(recs.lam, dtype=np.float64),
+                vec=np.ascontiguousarray(recs.vec, dtype=np.float64))
+
+
+def _collect_records(offsets, items, call):
+    """Runs a streaming precompute (``call(cb)``) and gathers the chunks into one Records (host arrays)."""
+    nu = len(offsets) - 1
+    lam_cap, vec_cap = upper_bounds(offsets)
+    sig = np.zeros(int(offsets[-1]), dtype=np.float64)
+    k = np.zeros(nu, dtype=np.int32)
+    lam_off = np.zeros(nu, dtype=np.int64)
+    vec_off = np.zeros(nu, dtype=np.int64)
+    lam = np.zeros(lam_cap, dtype=np.float64)
+    vec = np.zeros(vec_cap, dtype=np.float64)
+    used = [0, 0]
+
+    def sink(ch):
+        nr = ch.n_records
+        ui = np.ctypeslib.as_array(ch.user_index, shape=(nr,))
+        nn = np.ctypeslib.as_array(ch.n, shape=(nr,))
+        kk = np.ctypeslib.as_array(ch.k, shape=(nr,))
+        lo = np.ctypeslib.as_array(ch.lam_off, shape=(nr,))
+        vo = np.ctypeslib.as_array(ch.vec_off, shape=(nr,))
+        for j in range(nr):
+            u, n, kj = int(ui[j]), int(nn[j]), int(kk[j])
+            k[u] = kj
+            lam_off[u], vec_off[u] = used
+            lam[used[0]: used[0] + kj] = np.ctypeslib.as_array(ctypes.cast(ctypes.addressof(ch.lam.contents) + 8 * int(lo[j]), c_f64p), shape=(kj,))
+            vec[used[1]: used[1] + n * kj] = np.ctypeslib.as_array(ctypes.cast(ctypes.addressof(ch.vec.contents) + 8 * int(vo[j]), c_f64p), shape=(n * kj,))
+            o = int(offsets[u])
+            sig[o: o + n] = np.ctypeslib.as_array(ctypes.cast(ctypes.addressof(ch.sig_min.contents) + 8 * o, c_f64p), shape=(n,))
+            used[0] += kj
+            used[1] += n * kj
+        return 0
+
+    call(sink)
+    return Records(offsets, items, sig, k, lam_off, vec_off, lam[: used[0]], vec[: used[1]])
+
+
+c_f64p = ctypes.POINTER(ctypes.c_double)
+
+
+class Group:
+    """Every GPU of the box behind one call (gsi_group_*): the analogue of the reference's thread pool over all workers
+    (precompute_local_threads.cpp:300-314).  ``devices=None`` takes every visible device."""
+
+    def __init__(self, devices=None):
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        if devices is None:
+            rc = self._lib.gsi_group_create(ctypes.byref(h), 0, None)
+        else:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            rc = self._lib.gsi_group_create(ctypes.byref(h), len(devices), ctypes.cast(arr, ctypes.c_void_p))
+        if rc != 0:
+            raise GsiError(rc, (self._lib.gsi_last_error(None) or b"").decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gsi_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise GsiError(rc, (self._lib.gsi_group_last_error(self._h) or b"").decode())
+
+    @property
+    def size(self) -> int:
+        return int(self._lib.gsi_group_size(self._h))
+
+    @property
+    def broadcast_path(self) -> str:
+        return self._lib.gsi_group_broadcast_path(self._h).decode()
+
+    def set_workspace_limit(self, nbytes: int):
+        self._check(self._lib.gsi_group_set_workspace_limit(self._h, nbytes))
+
+    def set_weights(self, w: np.ndarray):
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        assert w.ndim == 2 and w.shape[0] == w.shape[1]
+        self._check(self._lib.gsi_group_set_weights_host(self._h, _ptr(w), w.shape[0]))
+
+    def precompute(self, offsets, items) -> Records:
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        items = np.ascontiguousarray(items, dtype=np.int32)
+
+        def call(sink):
+            def _cb(_opaque, chunk_p):
+                return int(sink(chunk_p.contents) or 0)
+            cb = _lib.RECORD_SINK(_cb)
+            self._check(self._lib.gsi_group_precompute_stream(self._h, len(offsets) - 1, _ptr(offsets), _ptr(items), cb, None))
+
+        return _collect_records(offsets, items, call)
+
+    def predict(self, recs: Records, ratings, w_lim=None, pair_mask=None) -> dict:
+        nnz = int(recs.offsets[-1])
+        ratings = np.ascontiguousarray(ratings, dtype=np.float64)
+        w_lim = np.ascontiguousarray(recs.sig_min if w_lim is None else w_lim, dtype=np.float64)
+        mask = None if pair_mask is None else np.ascontiguousarray(pair_mask, dtype=np.uint8)
+        err = np.zeros(nnz, dtype=np.float32)
+        kk = np.zeros(nnz, dtype=np.int32)
+        pred = np.zeros(nnz, dtype=np.float64)
+        status = np.zeros(nnz, dtype=np.int32)
+        cols = np.zeros(nnz, dtype=np.int32)
+        a = _predict_args(recs)
+        self._check(self._lib.gsi_group_predict_host(
+            self._h, len(a["offsets"]) - 1, _ptr(a["offsets"]), _ptr(a["items"]), _ptr(w_lim), _ptr(ratings),
+            _ptr(a["k"]), _ptr(a["lam_off"]), _ptr(a["vec_off"]), _ptr(a["lam"]), len(a["lam"]), _ptr(a["vec"]), len(a["vec"]),
+            _ptr(mask), _ptr(err), _ptr(kk), _ptr(pred), _ptr(status), _ptr(cols)))
+        return dict(err=err, kk=kk, pred=pred, status=status, cols=cols)
+
+
 class Context:
     """One per GPU (gsi_create).  ``stream``: a raw cudaStream_t handle (e.g.
     ``torch.cuda.current_stream().cuda_stream``) or None for a private stream."""
@@ -181,12 +304,10 @@ class Context:
         pred = np.zeros(nnz, dtype=np.float64)
         status = np.zeros(nnz, dtype=np.int32)
         cols = np.zeros(nnz, dtype=np.int32)
-        lam = np.ascontiguousarray(recs.lam, dtype=np.float64)
-        vec = np.ascontiguousarray(recs.vec, dtype=np.float64)
+        a = _predict_args(recs)          # converted arrays stay referenced until the call returns
         self._check(self._lib.gsi_predict_host(
-            self._h, len(recs.offsets) - 1, _ptr(recs.offsets), _ptr(recs.items), _ptr(w_lim), _ptr(ratings),
-            _ptr(np.ascontiguousarray(recs.k, dtype=np.int32)), _ptr(np.ascontiguousarray(recs.lam_off, dtype=np.int64)),
-            _ptr(np.ascontiguousarray(recs.vec_off, dtype=np.int64)), _ptr(lam), len(lam), _ptr(vec), len(vec),
+            self._h, len(a["offsets"]) - 1, _ptr(a["offsets"]), _ptr(a["items"]), _ptr(w_lim), _ptr(ratings),
+            _ptr(a["k"]), _ptr(a["lam_off"]), _ptr(a["vec_off"]), _ptr(a["lam"]), len(a["lam"]), _ptr(a["vec"]), len(a["vec"]),
             _ptr(mask), _ptr(err), _ptr(kk), _ptr(pred), _ptr(status), _ptr(cols)))
         return dict(err=err, kk=kk, pred=pred, status=status, cols=cols)
 

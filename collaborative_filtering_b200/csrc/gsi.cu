@@ -1140,3 +1140,5 @@ extern "C" int gsi_measure_fp64_tflops(gsi_ctx* ctx, int use_dmma, double* tflop
     *tflops = flop / (best * 1e-3) / 1e12;
     return GSI_OK;
 }
+
+#include "group_host.cuh"

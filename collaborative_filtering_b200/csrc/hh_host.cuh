@@ -168,12 +168,8 @@ static int hh_trd(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_tea
         static const int small_cap = getenv("GSI_TRD_SMALL_MAX") ? std::min(TRD_SMALL_MAX, atoi(getenv("GSI_TRD_SMALL_MAX"))) : TRD_SMALL_MAX;
         int nj_big = nj;
         if (forced_team <= 0) while (nj_big > 0 && pl.jobs[nj_big - 1].n <= small_cap) --nj_big;
-        {   // next to big users the small ones are free filler for the persistent kernel (its length is the biggest user's
-            // chain): they only move when they are a real share of the chunk's work
-            double w_small = 0, w_all = 0;
-            for (int j = 0; j < nj; ++j) { const double c3 = (double)pl.jobs[j].n * pl.jobs[j].n * pl.jobs[j].n; w_all += c3; if (j >= nj_big) w_small += c3; }
-            if (nj_big > 0 && w_small < 0.05 * w_all && !getenv("GSI_TRD_SMALL_MAX")) nj_big = nj;
-        }
+        // (The route of a user depends on its own n only -- never on what else is in the chunk -- so that a user's record
+        // is bit-identical however the users are sharded over chunks, ranks or GPUs: SURVEY.md section 7 test (h).)
         if (nj_big < nj) {
             const size_t ssm = trd_small_smem_bytes(pl.jobs[nj_big].n);
             GSI_CUDA(ctx, cudaFuncSetAttribute(trd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));

@@ -151,23 +151,28 @@ int main(int argc, char** argv) {
     }
     if (skipped_users) fprintf(stderr, "warning: %zu test ratings of users without an out_eigen_ record skipped\n", skipped_users);
     // ---- GPU ----
-    gsi_ctx* ctx = nullptr;
-    const char* dev = getenv("GSI_DEVICE");
-    if (gsi_create(&ctx, dev ? atoi(dev) : 0, nullptr) != GSI_OK) return fail(nullptr, "gsi_create");
-    if (gsi_set_weights_host(ctx, table.data(), wrows) != GSI_OK) return fail(ctx, "gsi_set_weights_host");
+    // every visible device (GSI_DEVICE / GSI_DEVICES restrict them): users with all their pairs are dealt over the GPUs
+    gsi_group* grp = nullptr;
+    std::vector<int> devs;
+    if (const char* one = getenv("GSI_DEVICE")) devs.push_back(atoi(one));
+    else if (const char* list = getenv("GSI_DEVICES"))
+        for (const char* p = list; *p;) { char* q; const long v = strtol(p, &q, 10); if (q == p) break; devs.push_back((int)v); p = (*q == ',') ? q + 1 : q; }
+    if (gsi_group_create(&grp, (int)devs.size(), devs.empty() ? nullptr : devs.data()) != GSI_OK) return fail(nullptr, "gsi_group_create");
+    auto group_fail = [&](const char* what) { fprintf(stderr, "%s: %s\n", what, gsi_group_last_error(grp)); gsi_group_destroy(grp); return EXIT_FAILURE; };
+    if (gsi_group_set_weights_host(grp, table.data(), wrows) != GSI_OK) return group_fail("gsi_group_set_weights_host");
     std::vector<double>().swap(table);
     std::vector<float> err(nnz);
     std::vector<int32_t> kk(nnz), status(nnz), cols(nnz);
     std::vector<double> pred(nnz);
-    printf("Running ...\n");
+    printf("Running on %d device(s) ...\n", gsi_group_size(grp));
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
-    if (gsi_predict_host(ctx, nu, offsets.data(), items.data(), w_lim.data(), ratings.data(), kvec.data(), lam_off.data(),
-                         vec_off.data(), lam.data(), (int64_t)lam.size(), vec.data(), (int64_t)vec.size(), mask.data(), err.data(),
-                         kk.data(), pred.data(), status.data(), cols.data()) != GSI_OK)
-        return fail(ctx, "gsi_predict_host");
+    if (gsi_group_predict_host(grp, nu, offsets.data(), items.data(), w_lim.data(), ratings.data(), kvec.data(), lam_off.data(),
+                               vec_off.data(), lam.data(), (int64_t)lam.size(), vec.data(), (int64_t)vec.size(), mask.data(), err.data(),
+                               kk.data(), pred.data(), status.data(), cols.data()) != GSI_OK)
+        return group_fail("gsi_group_predict_host");
     clock_gettime(CLOCK_MONOTONIC, &t1);
-    gsi_destroy(ctx);
+    gsi_group_destroy(grp);
     // ---- out_res: "movie user' mse kk\n", ascending movie then user' ----
     struct Row { unsigned movie, user; float mse; int kk, status; };
     std::vector<Row> rowsv;

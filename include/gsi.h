@@ -47,7 +47,7 @@ const char* gsi_version(void);
 /* Device workspace budget in bytes for one chunk of users (default 8 GiB). */
 int gsi_set_workspace_limit(gsi_ctx* ctx, int64_t bytes);
 /* Largest n that takes the CTA-resident (shared-memory Jacobi) kernel; larger users take the Householder /
- * divide-and-conquer path.  Default 80 (measured crossover), GSI_SMALL_MAX=32..160 overrides it. */
+ * divide-and-conquer path.  Default 44 (measured crossover), GSI_SMALL_MAX=32..160 overrides it. */
 int gsi_small_max(const gsi_ctx* ctx);
 /* Synchronise the context's stream. */
 int gsi_sync(gsi_ctx* ctx);
@@ -224,6 +224,44 @@ int gsi_knn3_host(gsi_ctx* ctx, int64_t n_users, const int64_t* offsets, const i
  * after c1.  All pointers are host memory; y receives nv values. */
 int gsi_cheby_filter_host(gsi_ctx* ctx, int64_t nv, const int64_t* row_off, const int32_t* col, const double* w,
                           const double* x, int ncoef, const double* coef, double* y);
+
+/* ---- device group: every GPU of the box behind ONE call  (replaces the thread pool of
+ *      precompute_local_threads.cpp:300-314, which spreads the users over all workers of the box by itself, and the
+ *      engine threads that run apply() in local_calc_precomp.cpp:566-572) ------------------------------------------ *
+ *
+ * A group owns one context per device and one host thread per device while a call runs.  Users are independent units
+ * (each compute_eigens() task reads only the shared read-only weights, precompute_local_threads.cpp:25,120-123): they
+ * are dealt over the devices by longest-processing-time-first on the cost n^3 + 64 n^2 (deterministic), every device
+ * runs gsi_precompute_stream on its share, and there is no data-path collective.  The weight table is copied to the
+ * first device once and replicated to the others over NVLink: ncclBroadcast when an NCCL library can be loaded
+ * (libnccl.so.2, resolved at run time), otherwise a tree of peer copies (gsi_group_broadcast_path says which).
+ * Records of a user are bit-identical to what a single context computes (the route of a user depends on its n only).
+ */
+typedef struct gsi_group gsi_group;
+/* `devices` = n_devices CUDA ordinals; n_devices <= 0 (or devices == NULL) takes every visible device. */
+int gsi_group_create(gsi_group** out, int n_devices, const int* devices);
+int gsi_group_destroy(gsi_group* g);
+int gsi_group_size(const gsi_group* g);
+/* Context of member i (for per-device calls: timing, workspace limit, ...); owned by the group. */
+gsi_ctx* gsi_group_ctx(gsi_group* g, int i);
+const char* gsi_group_last_error(const gsi_group* g);
+/* "single", "nccl" or "peer": how the last gsi_group_set_weights_host replicated the table. */
+const char* gsi_group_broadcast_path(const gsi_group* g);
+int gsi_group_set_workspace_limit(gsi_group* g, int64_t bytes);
+/* gsi_set_weights_host on member 0, then replication to every other member (device to device). */
+int gsi_group_set_weights_host(gsi_group* g, const double* w, int rows);
+/* gsi_precompute_stream over all devices.  The sink is called from the device threads, one call at a time (serialised
+ * by the group); user_index refers to the caller's CSR, sig_min to the caller's offsets, exactly as for one context.
+ * The order in which chunks arrive depends on timing; the records themselves do not. */
+int gsi_group_precompute_stream(gsi_group* g, int64_t n_users, const int64_t* offsets, const int32_t* items,
+                                gsi_record_sink sink, void* opaque);
+/* gsi_predict_host over all devices: users (with all their pairs, next to their U -- SURVEY.md 8e) are dealt by
+ * longest-processing-time-first on the cost pairs * n * k^2; outputs land in the caller's [nnz] arrays. */
+int gsi_group_predict_host(gsi_group* g, int64_t n_users, const int64_t* offsets, const int32_t* items,
+                           const double* w_lim, const double* ratings, const int32_t* k,
+                           const int64_t* lam_off, const int64_t* vec_off, const double* lam,
+                           int64_t lam_len, const double* vec, int64_t vec_len, const uint8_t* pair_mask,
+                           float* err, int32_t* kk, double* pred, int32_t* status, int32_t* cols);
 
 /* ---- measurement helpers ------------------------------------------------------------------- */
 

@@ -22,10 +22,13 @@ def test_reference_arm_prints_one_contract_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"].startswith("users/sec") and d["unit"] == "users/s"
-    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert d["higher_is_better"] is True and d["scaling"] == "strong" and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert d["steps"] == 1 and d["warmup"] == 0 and d["n_gpus"] == 1 and d["vs_baseline"] is None
     assert d["value"] > 0 and d["ms_per_step"] > 0
     assert "workload" in d["config"] and "model" not in d["config"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.bench_config("ml-10m")          # both arms print the same config dict (vs_reference.same_config)
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["unit"] == "users/s" and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
