@@ -103,7 +103,7 @@ struct Workspace {
     DevBuf k_off, k_items, k_rat, k_cnt, k_num, k_S, k_ecnt, k_eoff, k_ea, k_eb, k_ew, k_co, k_err, k_mcnt, k_has;
     DevBuf c_off, c_col, c_w, c_wn, c_vec;          // Chebyshev filter: CSR, normalised weights, 5 vertex vectors
     int64_t knn_edges = 0;
-    DevBuf pred_meta, pred_work, p_off, p_items, p_wlim, p_rat, p_k, p_lamoff, p_vecoff, p_lam, p_vec, p_err, p_kk, p_pred, p_status, p_cols;
+    DevBuf pred_meta, pred_work, p_off, p_items, p_wlim, p_rat, p_k, p_lamoff, p_vecoff, p_lam, p_vec, p_err, p_kk, p_pred, p_status, p_cols, p_gsum, p_hsum, p_sumoff, p_exact, p_lim, p_mask;
     DevBuf meta, vec_pad, lam_pad, G, rows, cols, perm, hpart, q, totals, items, sig, outk, outlam, outvec, stage_vec, stage_lam, probe;
     DevBuf hhA, hhQa, hhQb, hhS, hhvec, hhivec, trd_acol, trd_ypart, trd_part, trd_panels;
     PinBuf h_meta, h_stage_vec, h_stage_lam, h_small, h_k, h_lamoff, h_vecoff, h_sig;
@@ -170,7 +170,8 @@ extern "C" int gsi_destroy(gsi_ctx* c) {
                    &w.sig, &w.outk, &w.outlam, &w.outvec, &w.stage_vec, &w.stage_lam, &w.probe};
     for (auto b : d) b->release();
     DevBuf* d2[] = {&w.pred_meta, &w.pred_work, &w.p_off, &w.p_items, &w.p_wlim, &w.p_rat, &w.p_k, &w.p_lamoff, &w.p_vecoff,
-                    &w.p_lam, &w.p_vec, &w.p_err, &w.p_kk, &w.p_pred, &w.p_status, &w.p_cols};
+                    &w.p_lam, &w.p_vec, &w.p_err, &w.p_kk, &w.p_pred, &w.p_status, &w.p_cols, &w.p_gsum, &w.p_hsum, &w.p_sumoff,
+                    &w.p_exact, &w.p_lim, &w.p_mask};
     for (auto b : d2) b->release();
     DevBuf* d3[] = {&w.k_off, &w.k_items, &w.k_rat, &w.k_cnt, &w.k_num, &w.k_S, &w.k_ecnt, &w.k_eoff, &w.k_ea, &w.k_eb, &w.k_ew,
                     &w.k_co, &w.k_err, &w.k_mcnt, &w.k_has, &w.c_off, &w.c_col, &w.c_w, &w.c_wn, &w.c_vec};
@@ -756,60 +757,96 @@ extern "C" int gsi_predict_device(gsi_ctx* ctx, int64_t nu, const int64_t* h_off
         GSI_CUDA(ctx, cudaMemsetAsync(d_cols, 0, nnz * 4, ctx->stream));
         GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    // classes by the user's kept-eigenpair count (upper bound of the columns a pair can use)
-    // (records with k <= 192 run on the tensor-core kernel with everything in shared memory, the rest on the scalar one)
+    // ---- per-user sums (complement-row form) and the per-pair plan (kk, lim) ----
+    int rc;
+    std::vector<int64_t> sum_off((size_t)nu + 1, 0);
+    for (int64_t u = 0; u < nu; ++u) sum_off[u + 1] = sum_off[u] + h_k[u];
+    if ((rc = ws.p_gsum.ensure(ctx, std::max<int64_t>(1, sum_off[nu]) * 8)) != GSI_OK) return rc;
+    if ((rc = ws.p_hsum.ensure(ctx, std::max<int64_t>(1, sum_off[nu]) * 8)) != GSI_OK) return rc;
+    if ((rc = ws.p_sumoff.ensure(ctx, (size_t)(nu + 1) * 8)) != GSI_OK) return rc;
+    if ((rc = ws.p_exact.ensure(ctx, std::max<int64_t>(1, nu))) != GSI_OK) return rc;
+    if ((rc = ws.p_lim.ensure(ctx, std::max<int64_t>(1, nnz) * 4)) != GSI_OK) return rc;
+    if ((rc = ws.p_mask.ensure(ctx, std::max<int64_t>(1, nnz))) != GSI_OK) return rc;
+    PredParams P;
+    memset(&P, 0, sizeof P);
+    P.W = ctx->d_w; P.w_rows = ctx->w_rows; P.items = d_items; P.offsets = d_off; P.w_lim = d_w_lim; P.ratings = d_ratings;
+    P.k = d_k; P.lam_off = d_lam_off; P.vec_off = d_vec_off; P.lam = d_lam; P.vec = d_vec;
+    P.err = d_err; P.kk = d_kk; P.pred = d_pred; P.status = d_status; P.cols_used = d_cols;
+    P.gsum = ws.p_gsum.as<double>(); P.hsum = ws.p_hsum.as<double>(); P.sum_off = ws.p_sumoff.as<int64_t>();
+    P.user_exact = ws.p_exact.as<uint8_t>(); P.plan_lim = ws.p_lim.as<int32_t>();
+    P.pair_mask_dev = nullptr;
+    std::vector<int32_t> h_kk((size_t)nnz), h_lim((size_t)nnz);
+    std::vector<uint8_t> h_exact((size_t)nu);
+    if (nnz) {
+        GSI_CUDA(ctx, cudaMemcpyAsync(ws.p_sumoff.p, sum_off.data(), (size_t)(nu + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (pair_mask) {
+            GSI_CUDA(ctx, cudaMemcpyAsync(ws.p_mask.p, pair_mask, (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+            P.pair_mask_dev = ws.p_mask.as<uint8_t>();
+        }
+        GsiSpan sp(ctx, GSI_T_PREDICT, 2);
+        {
+            HhTrace tr(ctx, "predict: per-user sums + per-pair plan");
+            pred_user_sums_kernel<<<(unsigned)nu, 256, 0, ctx->stream>>>(P, ws.p_gsum.as<double>(), ws.p_hsum.as<double>(), ws.p_exact.as<uint8_t>(), (int)nu);
+            pred_plan_kernel<<<(unsigned)nu, 256, 0, ctx->stream>>>(P, (int)nu);
+        }
+        sp.end();
+        GSI_CUDA(ctx, cudaGetLastError());
+        GSI_CUDA(ctx, cudaMemcpyAsync(h_kk.data(), d_kk, (size_t)nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        GSI_CUDA(ctx, cudaMemcpyAsync(h_lim.data(), ws.p_lim.p, (size_t)nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        GSI_CUDA(ctx, cudaMemcpyAsync(h_exact.data(), ws.p_exact.p, (size_t)nu, cudaMemcpyDeviceToHost, ctx->stream));
+        GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    const bool no_wood = getenv("GSI_PRED_DIRECT") && atoi(getenv("GSI_PRED_DIRECT")) != 0;   // probe / test: direct form only
+    if (no_wood) P.user_exact = nullptr;
+    // classes by the ORDER of the pair's solve: min(lim, n - kk) when the complement-row form applies, else lim
+    // (pairs up to order 192 keep everything in shared memory, bigger ones use a per-CTA scratch in L2)
     static const int kClassC[] = {16, 32, 48, 64, 96, 128, 160, 192};
     const int n_smem_classes = 8;
-    std::vector<std::vector<PredTask>> cls(n_smem_classes + 1);
+    struct ClassAcc { std::vector<PredTask> tasks; int nmax = 0, kmax = 0; };
+    std::vector<ClassAcc> cls(n_smem_classes + 1);
     for (int64_t u = 0; u < nu; ++u) {
         const int n = (int)(h_off[u + 1] - h_off[u]);
-        const int k = h_k[u];
-        int c = 0;
-        while (c < n_smem_classes && (k > kClassC[c] || predict2_smem_bytes(kClassC[c], n, true) > 226 * 1024)) ++c;
         for (int i = 0; i < n; ++i) {
             const int64_t pair = h_off[u] + i;
             if (pair_mask && !pair_mask[pair]) continue;
-            cls[c].push_back({pair, (int32_t)u, k, n});
+            const int lim = h_lim[pair], nr = n - h_kk[pair];
+            const int dim = (!no_wood && h_exact[u] && nr < lim) ? nr : lim;
+            int c = 0;
+            while (c < n_smem_classes && (dim > kClassC[c] || predict2_smem_bytes(kClassC[c], n, true, P2_R, lim) > 226 * 1024)) ++c;
+            cls[c].tasks.push_back({pair, (int32_t)u, dim, n});
+            cls[c].nmax = std::max(cls[c].nmax, n); cls[c].kmax = std::max(cls[c].kmax, lim);
         }
     }
     int64_t done = 0;
     for (int c = 0; c <= n_smem_classes; ++c) {
-        std::vector<PredTask>& tasks = cls[c];
+        std::vector<PredTask>& tasks = cls[c].tasks;
         if (tasks.empty()) continue;
         const bool in_smem = c < n_smem_classes;
-        // big-k tasks: descending k so that a wave has similar cost
+        // big tasks: descending order so that a wave has similar cost
         if (!in_smem) std::stable_sort(tasks.begin(), tasks.end(), [](const PredTask& a, const PredTask& b) { return a.k > b.k; });
         std::vector<int64_t> t_pair(tasks.size());
         std::vector<int32_t> t_user(tasks.size());
-        int nmax = 0, kmax = 0;
-        for (size_t t = 0; t < tasks.size(); ++t) {
-            t_pair[t] = tasks[t].pair; t_user[t] = tasks[t].user;
-            nmax = std::max(nmax, tasks[t].n); kmax = std::max(kmax, tasks[t].k);
-        }
+        const int nmax = cls[c].nmax, kmax = std::max(cls[c].kmax, 2);
+        for (size_t t = 0; t < tasks.size(); ++t) { t_pair[t] = tasks[t].pair; t_user[t] = tasks[t].user; }
         MetaBuilder mb;
         const size_t o_pair = mb.add(t_pair), o_user = mb.add(t_user);
-        int rc;
         if ((rc = ws.pred_meta.ensure(ctx, mb.host.size())) != GSI_OK) return rc;
         GSI_CUDA(ctx, cudaMemcpyAsync(ws.pred_meta.p, mb.host.data(), mb.host.size(), cudaMemcpyHostToDevice, ctx->stream));
         GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        PredParams P;
-        P.W = ctx->d_w; P.w_rows = ctx->w_rows; P.items = d_items; P.offsets = d_off; P.w_lim = d_w_lim; P.ratings = d_ratings;
-        P.k = d_k; P.lam_off = d_lam_off; P.vec_off = d_vec_off; P.lam = d_lam; P.vec = d_vec;
         P.task_pair = (const int64_t*)(ws.pred_meta.as<char>() + o_pair);
         P.task_user = (const int32_t*)(ws.pred_meta.as<char>() + o_user);
-        P.err = d_err; P.kk = d_kk; P.pred = d_pred; P.status = d_status; P.cols_used = d_cols;
-        P.work = nullptr; P.work_stride = 0; P.nmax = nmax; P.m_in_smem = in_smem ? 1 : 0;
+        P.work = nullptr; P.work_stride = 0; P.nmax = nmax; P.kmax = kmax; P.m_in_smem = in_smem ? 1 : 0;
         if (in_smem) {
             P.cmax = kClassC[c];
             P.chunk_rows = P2_R;
-            const size_t smem = predict2_smem_bytes(P.cmax, nmax, true);
+            const size_t smem = predict2_smem_bytes(P.cmax, nmax, true, P2_R, kmax);
             GSI_CUDA(ctx, cudaFuncSetAttribute(predict2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
             const int64_t wave = 1 << 20;
             for (int64_t b = 0; b < (int64_t)tasks.size(); b += wave) {
                 const int cnt = (int)std::min<int64_t>(wave, tasks.size() - b);
                 P.task_base = (int)b;
-                char label[96];
-                snprintf(label, sizeof label, "predict2 class c<=%d: %d pairs, nmax %d, %zu B smem", P.cmax, cnt, nmax, smem);
+                char label[112];
+                snprintf(label, sizeof label, "predict2 order<=%d: %d pairs, nmax %d, kmax %d, %zu B smem", P.cmax, cnt, nmax, kmax, smem);
                 HhTrace tr(ctx, label);
                 GsiSpan sp(ctx, GSI_T_PREDICT, 1);
                 predict2_kernel<<<cnt, 256, smem, ctx->stream>>>(P);
@@ -817,10 +854,10 @@ extern "C" int gsi_predict_device(gsi_ctx* ctx, int64_t nu, const int64_t* h_off
                 GSI_CUDA(ctx, cudaGetLastError());
             }
         } else {
-            // waves of CTAs, each with a private kmax^2 scratch in global memory
+            // waves of CTAs, each with a private scratch for its matrix in global memory
             size_t b = 0;
             while (b < tasks.size()) {
-                const int kwave = tasks[b].k;                       // largest k of this wave (sorted)
+                const int kwave = tasks[b].k;                       // largest order of this wave (sorted)
                 const int64_t stride = (int64_t)predict2_tiles_dbl(kwave);
                 int64_t wave = std::max<int64_t>(1, std::min<int64_t>(4 * ctx->sm_count, (ctx->ws_limit / 2) / (stride * 8)));
                 wave = std::min<int64_t>(wave, tasks.size() - b);
@@ -828,12 +865,12 @@ extern "C" int gsi_predict_device(gsi_ctx* ctx, int64_t nu, const int64_t* h_off
                 P.cmax = kwave; P.work = ws.pred_work.as<double>(); P.work_stride = stride; P.task_base = (int)b;
                 P.chunk_rows = 64;                                  // as many staged rows as fit beside the index arrays
                 static const size_t stage_cap = getenv("GSI_PRED_STAGE_KB") ? (size_t)atoi(getenv("GSI_PRED_STAGE_KB")) * 1024 : 110 * 1024;   // two CTAs per SM
-                while (P.chunk_rows > 8 && predict2_smem_bytes(P.cmax, nmax, false, P.chunk_rows) > stage_cap) P.chunk_rows /= 2;
-                const size_t smem = predict2_smem_bytes(P.cmax, nmax, false, P.chunk_rows);
-                if (smem > 226 * 1024) return gsi_fail(ctx, GSI_ERR_INVALID, "predict: user too large for the staging buffers (n=%d, k=%d)", nmax, kwave);
+                while (P.chunk_rows > 8 && predict2_smem_bytes(P.cmax, nmax, false, P.chunk_rows, kmax) > stage_cap) P.chunk_rows /= 2;
+                const size_t smem = predict2_smem_bytes(P.cmax, nmax, false, P.chunk_rows, kmax);
+                if (smem > 226 * 1024) return gsi_fail(ctx, GSI_ERR_INVALID, "predict: user too large for the staging buffers (n=%d, order=%d)", nmax, kwave);
                 GSI_CUDA(ctx, cudaFuncSetAttribute(predict2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-                char label[96];
-                snprintf(label, sizeof label, "predict2 (M in L2) c<=%d: %d pairs, nmax %d, %zu B smem", P.cmax, (int)wave, nmax, smem);
+                char label[112];
+                snprintf(label, sizeof label, "predict2 (M in L2) order<=%d: %d pairs, nmax %d, %zu B smem", P.cmax, (int)wave, nmax, smem);
                 HhTrace tr(ctx, label);
                 GsiSpan sp(ctx, GSI_T_PREDICT, 1);
                 predict2_kernel<<<(int)wave, 256, smem, ctx->stream>>>(P);

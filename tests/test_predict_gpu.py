@@ -125,4 +125,17 @@ def test_ml100k_precompute_then_predict_vs_oracle(ctx):
             rows.append((m, u, err, kk, pred, status, c))
     n_ok = _compare(users, recs, out, rows)
     assert n_ok >= 20
-    assert (recs.k > 192).any()                                   # L2-scratch class exercised
+    # the same pairs through the DIRECT form only (GSI_PRED_DIRECT=1: c x c Gram over the K rows, the reference's own
+    # formulation; it also exercises the class with M in the L2 scratch, k > 192): the complement-row (Woodbury) form that
+    # ran above must agree with it pair by pair
+    os.environ["GSI_PRED_DIRECT"] = "1"
+    try:
+        direct = ctx.predict(recs, rat.astype(np.float64))
+    finally:
+        del os.environ["GSI_PRED_DIRECT"]
+    _compare(users, recs, direct, rows)
+    assert (recs.k > 192).any()
+    assert np.array_equal(out["kk"], direct["kk"]) and np.array_equal(out["cols"], direct["cols"])
+    assert np.array_equal(out["status"], direct["status"])
+    ok = out["status"] == 0
+    assert ok.sum() > 1000 and np.abs(out["pred"][ok] - direct["pred"][ok]).max() <= 1e-7
