@@ -15,7 +15,7 @@ SO_PATH = os.path.join(_HERE, "libgsi.so")
 
 GSI_OK, GSI_ERR_INVALID, GSI_ERR_CUDA, GSI_ERR_NOMEM, GSI_ERR_STATE, GSI_ERR_CAPACITY, GSI_ERR_SINK = range(7)
 T_NAMES = ["eig_cta", "lap", "bj_gram", "bj_inner", "bj_update", "finalize", "compact", "predict", "knn",
-           "trd", "dc", "dc_gemm", "bt", "cheby"]
+           "trd", "dc", "dc_gemm", "bt", "cheby", "sbr", "bt2"]
 
 c_i64p = ctypes.POINTER(ctypes.c_int64)
 c_i32p = ctypes.POINTER(ctypes.c_int32)
@@ -78,6 +78,7 @@ SYMBOLS = {
     "gsi_timing_reset": (ctypes.c_int, [ctypes.c_void_p]),
     "gsi_timing_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "gsi_measure_fp64_tflops": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_f64p]),
+    "gsi_debug_band": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 4),
     "gsi_debug_eigh": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_float, ctypes.c_int] +
                        [ctypes.c_void_p] * 7),
 }

@@ -442,3 +442,17 @@ class Context:
                                              _ptr(v), _ptr(lam), _ptr(u), ctypes.byref(k)))
         kk = int(k.value)
         return dict(d=d, e=e[:n - 1], tau=tau[:n - 1], v=v, lam=lam, u=u[:, :kk], k=kk)
+
+    def debug_band(self, a: np.ndarray, chase: bool = True):
+        """Two-stage test hook (gsi_debug_band): returns dict(band = dense symmetric band matrix after stage 1, d, e)."""
+        a = np.asfortranarray(a, dtype=np.float64)
+        n = a.shape[0]
+        ab = np.zeros((n, 128))
+        d = np.zeros(n); e = np.zeros(max(n - 1, 1))
+        self._check(self._lib.gsi_debug_band(self._h, n, _ptr(a), _ptr(ab), _ptr(d) if chase else None, _ptr(e) if chase else None))
+        band = np.zeros((n, n))
+        for dd in range(65):
+            v = ab[: n - dd, dd]
+            band[np.arange(dd, n), np.arange(0, n - dd)] = v
+            band[np.arange(0, n - dd), np.arange(dd, n)] = v
+        return dict(band=band, ab=ab, d=d, e=e[: n - 1])

@@ -19,6 +19,7 @@
 #include "kern_trd.cuh"
 #include "kern_dc.cuh"
 #include "kern_bt.cuh"
+#include "kern_sbr.cuh"
 #include "kern_cheby.cuh"
 #include "kern_lc.cuh"
 
@@ -106,6 +107,7 @@ struct Workspace {
     DevBuf pred_meta, pred_work, p_off, p_items, p_wlim, p_rat, p_k, p_lamoff, p_vecoff, p_lam, p_vec, p_err, p_kk, p_pred, p_status, p_cols, p_gsum, p_hsum, p_sumoff, p_exact, p_lim, p_mask;
     DevBuf meta, vec_pad, lam_pad, G, rows, cols, perm, hpart, q, totals, items, sig, outk, outlam, outvec, stage_vec, stage_lam, probe;
     DevBuf hhA, hhQa, hhQb, hhS, hhvec, hhivec, trd_acol, trd_ypart, trd_part, trd_panels;
+    DevBuf sbr_panels, sbr_small, sbr_band, sbr_v2, sbr_prog, sbr_list;
     PinBuf h_meta, h_stage_vec, h_stage_lam, h_small, h_k, h_lamoff, h_vecoff, h_sig;
 };
 
@@ -176,7 +178,8 @@ extern "C" int gsi_destroy(gsi_ctx* c) {
     DevBuf* d3[] = {&w.k_off, &w.k_items, &w.k_rat, &w.k_cnt, &w.k_num, &w.k_S, &w.k_ecnt, &w.k_eoff, &w.k_ea, &w.k_eb, &w.k_ew,
                     &w.k_co, &w.k_err, &w.k_mcnt, &w.k_has, &w.c_off, &w.c_col, &w.c_w, &w.c_wn, &w.c_vec};
     for (auto b : d3) b->release();
-    DevBuf* d4[] = {&w.hhA, &w.hhQa, &w.hhQb, &w.hhS, &w.hhvec, &w.hhivec, &w.trd_acol, &w.trd_ypart, &w.trd_part, &w.trd_panels};
+    DevBuf* d4[] = {&w.hhA, &w.hhQa, &w.hhQb, &w.hhS, &w.hhvec, &w.hhivec, &w.trd_acol, &w.trd_ypart, &w.trd_part, &w.trd_panels,
+                    &w.sbr_panels, &w.sbr_small, &w.sbr_band, &w.sbr_v2, &w.sbr_prog, &w.sbr_list};
     for (auto b : d4) b->release();
     PinBuf* p[] = {&w.h_meta, &w.h_stage_vec, &w.h_stage_lam, &w.h_small, &w.h_k, &w.h_lamoff, &w.h_vecoff, &w.h_sig};
     for (auto b : p) b->release();

@@ -73,6 +73,7 @@ struct HhDev {           // device views of one chunk
     int64_t* roff_arr; int64_t* voff_arr; int64_t* loff_arr;
 };
 
+
 #define HH_CTL_INTS 12288      // [0..8) trd level queues, [8] bt queue, [64 + 256 l ..) slots, [2048 + 256 l ..) barriers, [3840..) trace
 
 static int hh_alloc(gsi_ctx* ctx, const HhPlan& pl, const Job* jobs, HhDev& D) {
@@ -140,17 +141,30 @@ struct HhTrace {
     }
 };
 
+#include "sbr_host.cuh"
+
+struct HhSbrState { SbrDev dev; SbrStage2 st2; int nu = 0; };     // two-stage users of the chunk in flight (a prefix of its jobs)
+
 // size class of a user on the tridiagonalisation levels.  Every CTA of a team pays the per-column
 // synchronisation latency, so teams are kept as small as the tail allows: the biggest users start first
 // and everything smaller fills the other SMs behind them.
 static int hh_level_of(int np) { return np > 4096 ? 0 : (np > 2048 ? 1 : (np > 1024 ? 2 : 3)); }
 
 // tridiagonalisation only (uses D.jobs, D.A, D.d, D.e, D.tau, D.ctl): A = Q T Q^T, T in (d, e), reflectors in A / tau
-static int hh_trd(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_team) {
+static int hh_trd(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_team, HhSbrState& SB) {
     Workspace& ws = WS(ctx);
     cudaStream_t st = ctx->stream;
     const int nj = pl.nj;
     int rc;
+    // ---------------- the big users: two-stage reduction (kern_sbr.cuh); jobs are sorted by n descending
+    SB.nu = 0;
+    if (forced_team <= 0 && sbr_min_n() > 0) while (SB.nu < nj && pl.jobs[SB.nu].n >= sbr_min_n()) ++SB.nu;
+    if (SB.nu > 0) {
+        if ((rc = sbr_alloc(ctx, pl, SB.nu, SB.dev)) != GSI_OK) return rc;
+        { HhTrace tr(ctx, "sbr stage 1 (dense -> band)"); if ((rc = sbr_stage1(ctx, pl, D, SB.dev)) != GSI_OK) return rc; }
+        if ((rc = sbr_stage2(ctx, pl, D, SB.dev, SB.st2)) != GSI_OK) return rc;
+    }
+    const int first_one_stage = SB.nu;
     // ---------------- tridiagonalisation: ONE persistent launch, levels of nested teams (kern_trd.cuh)
     {
         const int sms = ctx->sm_count;
@@ -163,11 +177,11 @@ static int hh_trd(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_tea
         P.jobs = D.jobs; P.A = D.A; P.d = D.d; P.e = D.e; P.tau = D.tau;
         P.nlevels = 0;
         size_t smem = 0;
-        int b = 0;
+        int b = first_one_stage;
         // users whose matrix fits in shared memory go to the CTA-resident kernel (jobs are sorted by n descending: the tail)
         static const int small_cap = getenv("GSI_TRD_SMALL_MAX") ? std::min(TRD_SMALL_MAX, atoi(getenv("GSI_TRD_SMALL_MAX"))) : TRD_SMALL_MAX;
         int nj_big = nj;
-        if (forced_team <= 0) while (nj_big > 0 && pl.jobs[nj_big - 1].n <= small_cap) --nj_big;
+        if (forced_team <= 0) while (nj_big > first_one_stage && pl.jobs[nj_big - 1].n <= small_cap) --nj_big;
         // (The route of a user depends on its own n only -- never on what else is in the chunk -- so that a user's record
         // is bit-identical however the users are sharded over chunks, ranks or GPUs: SURVEY.md section 7 test (h).)
         if (nj_big < nj) {
@@ -282,7 +296,8 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
     cudaStream_t st = ctx->stream;
     const int nj = pl.nj;
     int rc;
-    if ((rc = hh_trd(ctx, pl, D, forced_team)) != GSI_OK) return rc;
+    HhSbrState SB;
+    if ((rc = hh_trd(ctx, pl, D, forced_team, SB)) != GSI_OK) return rc;
     // ---------------- divide & conquer
     DcParams P;
     P.jobs = D.jobs; P.nodes = D.nodes; P.state = D.state; P.Qa = D.Qa; P.Qb = D.Qb; P.S = D.S; P.lamA = D.lamA; P.lamB = D.lamB;
@@ -331,7 +346,8 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
         }
         GSI_CUDA(ctx, cudaGetLastError());
     }
-    // ---------------- back-transformation
+    // ---------------- back-transformation: Q2 (bulge-chasing reflectors) for the two-stage users first, then Q1 / Q for everybody
+    if (SB.nu > 0 && (rc = sbr_bt2(ctx, D, SB.st2)) != GSI_OK) return rc;
     BtParams B;
     B.jobs = D.jobs; B.njobs = nj; B.A = D.A; B.tau = D.tau; B.S = D.S; B.Qa = D.Qa; B.Qb = D.Qb; B.kuser = D.kuser;
     B.items = D.bt_items; B.nitems = (int)pl.bt_items.size(); B.queue = D.ctl + 8;
@@ -525,5 +541,38 @@ extern "C" int gsi_debug_eigh(gsi_ctx* ctx, int n, const double* a, float thr, i
     const bool in_b = pl.jobs[0].levels & 1;
     if (lam) GSI_CUDA(ctx, cudaMemcpy(lam, in_b ? D.lamB : D.lamA, (size_t)n * 8, cudaMemcpyDeviceToHost));
     if (u && kk > 0) GSI_CUDA(ctx, cudaMemcpy2D(u, (size_t)n * 8, in_b ? D.Qb : D.Qa, (size_t)np * 8, (size_t)n * 8, kk, cudaMemcpyDeviceToHost));
+    return GSI_OK;
+}
+
+// ---- stage-wise test hook of the two-stage path: the band after stage 1 ------------------------------------------------
+extern "C" int gsi_debug_band(gsi_ctx* ctx, int n, const double* a, double* ab /* [n * 128] */, double* d, double* e) {
+    if (!ctx) return gsi_fail(nullptr, GSI_ERR_INVALID, "null context");
+    if (!a || !ab || n < 130 || n > 17664) return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_debug_band: need a matrix with 130 <= n <= 17664");
+    GSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    Job job{0, n, 0};
+    HhPlan pl;
+    hh_build_plan(&job, 1, pl);
+    HhDev D;
+    int rc;
+    if ((rc = hh_alloc(ctx, pl, &job, D)) != GSI_OK) return rc;
+    const int np = pl.jobs[0].np, NT = np >> 6;
+    std::vector<double> tiled((size_t)np * np, 0.0);
+    for (int cc = 0; cc < n; ++cc)
+        for (int r = 0; r < n; ++r) tiled[hh_tidx(r, cc, NT)] = a[(size_t)cc * n + r];
+    GSI_CUDA(ctx, cudaMemcpyAsync(D.A, tiled.data(), tiled.size() * 8, cudaMemcpyHostToDevice, st));
+    GSI_CUDA(ctx, cudaStreamSynchronize(st));
+    HhSbrState SB;
+    SB.nu = 1;
+    if ((rc = sbr_alloc(ctx, pl, 1, SB.dev)) != GSI_OK) return rc;
+    if ((rc = sbr_stage1(ctx, pl, D, SB.dev)) != GSI_OK) return rc;
+    GSI_CUDA(ctx, cudaMemcpyAsync(ab, SB.dev.AB, (size_t)n * SBR_LDB * 8, cudaMemcpyDeviceToHost, st));
+    GSI_CUDA(ctx, cudaStreamSynchronize(st));
+    if (d || e) {
+        if ((rc = sbr_stage2(ctx, pl, D, SB.dev, SB.st2)) != GSI_OK) return rc;
+        if (d) GSI_CUDA(ctx, cudaMemcpyAsync(d, D.d, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        if (e) GSI_CUDA(ctx, cudaMemcpyAsync(e, D.e, (size_t)(n - 1) * 8, cudaMemcpyDeviceToHost, st));
+        GSI_CUDA(ctx, cudaStreamSynchronize(st));
+    }
     return GSI_OK;
 }

@@ -280,7 +280,7 @@ extern "C" int gsi_local_calc_host(gsi_ctx* ctx, int64_t nu, const int64_t* offs
                 const int NT = pl.npmax >> 6;
                 lc_fill_kernel<<<dim3(np_, NT * NT), 256, 0, st>>>(D.jobs, d_fills, D.A);
                 GSI_CUDA(ctx, cudaGetLastError());
-                if ((rc = hh_trd(ctx, pl, D, 0)) != GSI_OK) return rc;
+                { HhSbrState sb; if ((rc = hh_trd(ctx, pl, D, 0, sb)) != GSI_OK) return rc; }
                 lc_tmin_kernel<<<(np_ + 3) / 4, 128, 0, st>>>(D.jobs, np_, D.d, D.e, d_wl);
                 GSI_CUDA(ctx, cudaGetLastError());
             }

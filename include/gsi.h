@@ -282,7 +282,9 @@ enum {
     GSI_T_DC_GEMM = 11,    /* divide & conquer merge GEMMs (DMMA)                                 */
     GSI_T_BT = 12,         /* back-transformation of the kept eigenvectors (DMMA) + emit          */
     GSI_T_CHEBY = 13,      /* Chebyshev graph filter supersteps                                   */
-    GSI_T_COUNT = 14
+    GSI_T_SBR = 14,        /* two-stage tridiagonalisation: dense -> band (DMMA), bulge chasing   */
+    GSI_T_BT2 = 15,        /* back-transformation through the bulge-chasing reflectors (DMMA)     */
+    GSI_T_COUNT = 16
 };
 int gsi_timing_enable(gsi_ctx* ctx, int on);
 int gsi_timing_reset(gsi_ctx* ctx);
@@ -308,6 +310,12 @@ int gsi_measure_fp64_tflops(gsi_ctx* ctx, int use_dmma, double* tflops);
  * pointer may be NULL. */
 int gsi_debug_eigh(gsi_ctx* ctx, int n, const double* a, float thr, int team, double* d, double* e,
                    double* tau, double* v, double* lam, double* u, int32_t* k);
+
+/* Test hook of the two-stage tridiagonalisation (users with n >= 1024, GSI_SBR_MIN overrides): stage 1 (dense -> band of
+ * half-width 64) on ONE dense symmetric matrix (host, column-major, n >= 130).  ab[j * 128 + dd] = B(j + dd, j), dd = 0 .. 64
+ * (zero beyond); B is orthogonally similar to A.  With d / e non-NULL stage 2 (bulge chasing) runs as well and the tridiagonal
+ * comes back. */
+int gsi_debug_band(gsi_ctx* ctx, int n, const double* a, double* ab, double* d, double* e);
 
 #ifdef __cplusplus
 }
