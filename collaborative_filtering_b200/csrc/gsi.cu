@@ -268,8 +268,14 @@ struct Chunk { bool large; int begin, end; bool bj = false; };   // [begin, end)
 static inline int64_t pad_slots(int n) { return (int64_t)n * std::max(n, 2); }
 static inline int ld_of(int n) { return (n + 7) & ~7; }
 static inline int hh_np(int n) { return (n + 63) & ~63; }
-// workspace of one user on the Householder path: A, Qa, Qb, S (np^2 each) + vectors
-static inline int64_t hh_ws_doubles(int n) { const int64_t np = hh_np(n); return 4 * np * np + 32 * np; }
+static int sbr_min_n();
+// workspace of one user on the Householder path: A, Qa, Qb, S (np^2 each) + vectors; two-stage users add the reflector
+// blocks of the bulge chase (~np^2), the compact band and the panel buffers
+static inline int64_t hh_ws_doubles(int n) {
+    const int64_t np = hh_np(n);
+    const bool two_stage = sbr_min_n() > 0 && n >= sbr_min_n();
+    return two_stage ? 5 * np * np + 1024 * np : 4 * np * np + 32 * np;
+}
 static inline int nb_of(int n, int B) { int nb = (n + B - 1) / B; return nb + (nb & 1); }
 
 static int plan(gsi_ctx* ctx, int64_t nu, const int64_t* off, std::vector<Job>& small, std::vector<Job>& large,
@@ -292,7 +298,8 @@ static int plan(gsi_ctx* ctx, int64_t nu, const int64_t* off, std::vector<Job>& 
     int n_bj_first = (int)large.size();                                         // large[0 .. n_bj_first) -> block Jacobi
     if (!ctx->large_bj) {
         n_bj_first = 0;
-        while (n_bj_first < (int)large.size() && large[n_bj_first].n > GSI_HH_MAX_N) ++n_bj_first;   // sorted descending
+        // (the two-stage reduction has no such limit: with it -- the default -- nobody takes the block-Jacobi path)
+        while (sbr_min_n() == 0 && n_bj_first < (int)large.size() && large[n_bj_first].n > GSI_HH_MAX_N) ++n_bj_first;   // sorted descending
     }
     b = n_bj_first;
     while (b < (int)large.size() && !ctx->large_bj) {

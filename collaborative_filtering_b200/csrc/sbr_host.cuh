@@ -50,6 +50,9 @@ static int sbr_stage1(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, const SbrD
     GSI_CUDA(ctx, cudaFuncSetAttribute(sbr_panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbr_qr_smem_bytes()));
     GSI_CUDA(ctx, cudaFuncSetAttribute(sbr_symm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbr_symm_smem_bytes()));
     GSI_CUDA(ctx, cudaFuncSetAttribute(sbr_syr2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbr_syr2k_smem_bytes()));
+    GSI_CUDA(ctx, cudaFuncSetAttribute(sbr_w1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbr_w_smem_bytes()));
+    GSI_CUDA(ctx, cudaFuncSetAttribute(sbr_w2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbr_w_smem_bytes()));
+    GSI_CUDA(ctx, cudaFuncSetAttribute(sbr_w3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbr_w_smem_bytes()));
     SbrParams P;
     memset(&P, 0, sizeof P);
     P.jobs = D.jobs; P.A = D.A; P.tau = D.tau; P.Vp = S.Vp; P.Wp = S.Wp; P.Xp = S.Xp; P.Yp = S.Yp; P.Sp = S.Sp; P.T1 = S.T1; P.TS = S.TS;
