@@ -86,15 +86,16 @@ rank = int(os.environ["RANK"])
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["PORT"], rank=rank, world_size=2)
 r = D.make_ratings("ml-100k", n_users=120)
 deg = np.diff(r.offsets)
-sel_all, mine = bench.deal_users(deg, 200, rank, 2)
-other = bench.deal_users(deg, 200, 1 - rank, 2)[1]
-assert len(np.intersect1d(mine, other)) == 0 and np.array_equal(np.sort(np.concatenate([mine, other])), np.sort(sel_all))
-assert abs(int(deg[mine].sum()) - int(deg[other].sum())) <= int(deg[sel_all].max())          # dealt by descending n: balanced
+mine = bench.deal_users(deg, rank, 2)
+other = bench.deal_users(deg, 1 - rank, 2)
+assert len(np.intersect1d(mine, other)) == 0 and np.array_equal(np.sort(np.concatenate([mine, other])), np.arange(len(deg)))
+assert abs(int(deg[mine].sum()) - int(deg[other].sum())) <= int(deg.max())          # dealt by descending n: balanced
 pairs = int(deg[mine].sum())
-out = bench.reduce_predict_stats(pairs, 2.0 * pairs, 0.5 * pairs, pairs - rank, 10.0 + rank, 0.1 * (rank + 1), torch.device("cpu"))
-tot = int(deg[sel_all].sum())
-assert out[0] == tot and out[1] == 2.0 * tot and abs(out[2] - 0.5 * tot) < 1e-9 and out[3] == tot - 1
-assert out[4] == 11.0 and abs(out[5] - 0.2) < 1e-12                                          # the slowest rank's times
+sums, maxes = bench.reduce_predict_stats([pairs, 2.0 * pairs, 0.5 * pairs, pairs - rank], [10.0 + rank, 0.1 * (rank + 1)], torch.device("cpu"))
+tot = int(deg.sum())
+assert sums[0] == tot and sums[1] == 2.0 * tot and abs(sums[2] - 0.5 * tot) < 1e-9 and sums[3] == tot - 1
+assert maxes[0] == 11.0 and abs(maxes[1] - 0.2) < 1e-12                                          # the slowest rank's times
+out = sums
 print("OK", out[0])
 dist.destroy_process_group()
 """ % ROOT
