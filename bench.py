@@ -536,7 +536,7 @@ def run_gpu(args, rank, world, local_rank):
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
         # ---- headline: the whole eigensolve group against the FP64 peak, 9 n^3 flop per user ----
-        grp = [k for k in ("trd", "sbr", "dc", "dc_gemm", "bt") if k in timing and timing[k]["launches"]]
+        grp = [k for k in ("trd", "sbr", "dc", "dc_gemm", "bt2", "bt") if k in timing and timing[k]["launches"]]
         grp_ms = sum(est_ms(k) for k in grp) / args.steps
         eig_tf = 9.0 * n3_large / (grp_ms * 1e-3) / 1e12 if grp_ms > 0 else 0.0
         # ---- secondary: the HBM view of the one-stage tridiagonalisation and of the Laplacian stage ----

@@ -280,7 +280,7 @@ __device__ __forceinline__ double lc_block_sum(double v, double* red) {
 }
 
 __global__ void __launch_bounds__(256) lc_lanczos_kernel(const LcPair* __restrict__ pairs, int npairs, const LcMovie* __restrict__ movies,
-                                                         const double* __restrict__ P, const int32_t* __restrict__ kidx, int nmax,
+                                                         const double* __restrict__ P, const int32_t* __restrict__ kidx, int nmax, int ntrials,
                                                          double* __restrict__ w_lim, int32_t* __restrict__ conv) {
     extern __shared__ double lz_sm[];
     double* q = lz_sm;                  // [nmax] current Lanczos vector (zero on the rated nodes)
@@ -299,8 +299,27 @@ __global__ void __launch_bounds__(256) lc_lanczos_kernel(const LcPair* __restric
         __syncthreads();
         for (int t = tid; t < Pp.kk; t += 256) mask[kidx[Pp.k_off + t]] = 0;
         __syncthreads();
-        const double q0 = 1.0 / sqrt((double)n_unr);
-        for (int i = tid; i < n; i += 256) { q[i] = mask[i] ? q0 : 0.0; qp[i] = 0.0; }
+        // Two runs from independent start vectors (the guard of VERDICT r01 item 9): a start vector that happens to be
+        // (nearly) orthogonal to the wanted eigenvector would let the Ritz value settle on lambda_2 unnoticed; the constant
+        // vector (close to D^1/2 1, the direction of the smallest eigenvalue) and a hashed +-1 pattern cannot both be.
+        // Disagreement -> conv = 0 -> the pair goes to the exact path.  The reported value is the first run's.
+        double theta_run[2] = {0.0, 0.0};
+        int done_all = 1;
+        for (int trial = 0; trial < ntrials; ++trial) {
+        if (trial == 0) {
+            const double q0 = 1.0 / sqrt((double)n_unr);
+            for (int i = tid; i < n; i += 256) { q[i] = mask[i] ? q0 : 0.0; qp[i] = 0.0; }
+        } else {
+            double part = 0.0;
+            for (int i = tid; i < n; i += 256) {
+                unsigned h = (unsigned)i * 2654435761u + 0x9e3779b9u;
+                h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+                const double v = mask[i] ? (0.5 + (double)(h & 1023u) / 1024.0) * ((h & 2048u) ? 1.0 : -1.0) : 0.0;
+                q[i] = v; qp[i] = 0.0; part = fma(v, v, part);
+            }
+            const double nrm = sqrt(lc_block_sum(part, red));
+            for (int i = tid; i < n; i += 256) q[i] /= nrm;
+        }
         __syncthreads();
         const int kmax = min(LC_LZ_MAX, n_unr);
         double beta_prev = 0.0, theta = 0.0, theta_old = 1e300;
@@ -341,6 +360,15 @@ __global__ void __launch_bounds__(256) lc_lanczos_kernel(const LcPair* __restric
             beta_prev = beta;
             __syncthreads();
         }
+        theta_run[trial] = theta;
+        done_all &= done;
+        __syncthreads();
+        }
+        // an invariant-subspace breakdown ("exhausted" with fewer steps than unrated nodes) in one run only gives that run's
+        // smallest eigenvalue inside its Krylov space: the comparison catches it like any other disagreement
+        if (ntrials > 1 && !(fabs(theta_run[0] - theta_run[1]) <= 1e-10 * fmax(1.0, fabs(theta_run[0])))) done_all = 0;
+        const double theta = theta_run[0];
+        const int done = done_all;
         if (tid == 0) { w_lim[p] = sqrt(theta); conv[p] = done; }
     }
 }

@@ -111,9 +111,10 @@ extern "C" int gsi_local_calc_host(gsi_ctx* ctx, int64_t nu, const int64_t* offs
     std::vector<int> active;
     for (int m = 0; m < rows; ++m)
         if (mcount[m + 1] > mcount[m] && h_cnt[m] + 1 >= 3) active.push_back(m);
+    // local graphs above GSI_HH_MAX_N nodes take the two-stage tridiagonalisation like the big users of the precompute path
     for (int m : active)
-        if (h_cnt[m] + 1 > GSI_HH_MAX_N)
-            return gsi_fail(ctx, GSI_ERR_INVALID, "movie %d: local graph of %d nodes exceeds the eigensolver's limit %d", m, h_cnt[m] + 1, GSI_HH_MAX_N);
+        if (h_cnt[m] + 1 > 46000)
+            return gsi_fail(ctx, GSI_ERR_INVALID, "movie %d: local graph of %d nodes exceeds the eigensolver's limit %d", m, h_cnt[m] + 1, 46000);
     std::stable_sort(active.begin(), active.end(), [&](int a, int b) { return h_cnt[a] > h_cnt[b]; });
     const auto npad = [](int n) { const int nn = std::max(n, LC_PAD_N); return (int64_t)hh_np(nn); };
     const int64_t budget = std::max<int64_t>(ctx->ws_limit / 64, (int64_t)GSI_HH_MAX_N * GSI_HH_MAX_N);   // doubles of sum(np^2) per chunk
@@ -252,7 +253,9 @@ extern "C" int gsi_local_calc_host(gsi_ctx* ctx, int64_t nu, const int64_t* offs
                 if ((rc = pc.alloc(ctx, &d_conv, (size_t)np_)) != GSI_OK) return rc;
                 GSI_CUDA(ctx, cudaFuncSetAttribute(lc_lanczos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz_smem));
                 const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / lz_smem));
-                lc_lanczos_kernel<<<std::min(np_, per_sm * ctx->sm_count), 256, lz_smem, st>>>(d_pairs, np_, d_movies, d_P, d_kidx, nmax, d_wl, d_conv);
+                const char* g = getenv("GSI_LC_GUARD");                      // 0: single run (the r01 behaviour); default: two start vectors
+                const int ntrials = (g && atoi(g) == 0) ? 1 : 2;
+                lc_lanczos_kernel<<<std::min(np_, per_sm * ctx->sm_count), 256, lz_smem, st>>>(d_pairs, np_, d_movies, d_P, d_kidx, nmax, ntrials, d_wl, d_conv);
                 GSI_CUDA(ctx, cudaGetLastError());
             }
             if (exact) {   // exact cutoff: smallest eigenvalue of L_h L_h^T = P[unrated, unrated] (:417-436).  Only that one value is

@@ -12,10 +12,13 @@ struct SbrDev {                 // device buffers of the SBR users of a chunk (a
     int parts_cap = 0;
 };
 
-// users with n >= this take the two-stage path (GSI_SBR_MIN overrides; 0 = never)
+// users with n >= this take the two-stage path (GSI_SBR_MIN overrides; 0 = never).  Default: the users the one-stage kernel
+// cannot take (n > GSI_HH_MAX_N) -- measured on the ML-10M shape (profiles/r02c_sbr_threshold.md) the two-stage path does not
+// yet beat the one-stage kernel below that: its bulge chase is bound by the 3-task lag between consecutive sweeps and the
+// second back-transform costs 1.8 n^3 more flop on an FP64 pipe that is only ~5 flop/byte away from the HBM roofline.
 static int sbr_min_n() {
     const char* e = getenv("GSI_SBR_MIN");               // read on every call (tests switch it)
-    const int v = e ? atoi(e) : 1024;
+    const int v = e ? atoi(e) : GSI_HH_MAX_N + 1;
     return v <= 0 ? 0 : std::max(v, 130);
 }
 
@@ -43,6 +46,24 @@ static int sbr_alloc(gsi_ctx* ctx, const HhPlan& pl, int nu, SbrDev& S) {
     return GSI_OK;
 }
 
+// GSI_TRACE: per-kernel-kind stopwatch of stage 1 (synchronising; diagnostics only)
+struct SbrKindTimer {
+    gsi_ctx* ctx; bool on; int cur = -1; cudaEvent_t a = nullptr, b = nullptr; double ms[4] = {0, 0, 0, 0}; int waves = 0; int64_t panels = 0;
+    explicit SbrKindTimer(gsi_ctx* c) : ctx(c), on(c->trace) { if (on) { cudaEventCreate(&a); cudaEventCreate(&b); } }
+    void go(int kind) {
+        if (!on) return;
+        if (cur >= 0) { cudaEventRecord(b, ctx->stream); cudaEventSynchronize(b); float t = 0.f; cudaEventElapsedTime(&t, a, b); ms[cur] += t; }
+        cur = kind;
+        if (kind >= 0) cudaEventRecord(a, ctx->stream);
+    }
+    ~SbrKindTimer() {
+        if (!on) return;
+        fprintf(stderr, "[gsi trace] sbr stage 1 kinds: waves %d panel-steps %lld  qr %.1f  symm %.1f  w123 %.1f  syr2k %.1f ms\n", waves,
+                (long long)panels, ms[0], ms[1], ms[2], ms[3]);
+        cudaEventDestroy(a); cudaEventDestroy(b);
+    }
+};
+
 // stage 1 for the users [0, nu) of the chunk: dense -> band (in A) + reflectors (in A, tau); AB = compact band
 static int sbr_stage1(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, const SbrDev& S) {
     cudaStream_t st = ctx->stream;
@@ -59,8 +80,10 @@ static int sbr_stage1(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, const SbrD
     P.qr_part = S.qr_part; P.qr_bar = S.qr_bar; P.ystride = S.rtot * 64; P.qr_parts_max = S.parts_cap;
     // tau of the users: zero (panels without a reflector keep 0)
     GSI_CUDA(ctx, cudaMemsetAsync(D.tau, 0, (size_t)S.rtot * 8, st));
+    SbrKindTimer tk(ctx);
     int b = 0;
     while (b < S.nu) {
+        ++tk.waves;
         // a wave: users whose QR teams are co-resident (one CTA per SM)
         int e = b, parts = 0;
         while (e < S.nu) {
@@ -74,19 +97,20 @@ static int sbr_stage1(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, const SbrD
             int nw = 0;                                         // active users of the wave (a prefix: sorted by n descending)
             int64_t rows_blocks = 0;
             while (b + nw < e && pl.jobs[b + nw].n - (p + 1) * 64 >= 2) { rows_blocks += (pl.jobs[b + nw].np >> 6) - (p + 1); ++nw; }
-            P.p = p;
+            P.p = p; ++tk.panels;
             const int m = nmax - (p + 1) * 64, qparts = (m + SBR_RB - 1) / SBR_RB, nbmax = NTmax - (p + 1);
             P.seg = (int)std::min<int64_t>(std::min(SBR_SEG_MAX, nbmax), std::max<int64_t>(1, (2 * sms + rows_blocks - 1) / rows_blocks));
             GsiSpan sp(ctx, GSI_T_SBR, 6);
             GSI_CUDA(ctx, cudaMemsetAsync(S.qr_bar + b, 0, (size_t)nw * 4, st));
-            sbr_panel_qr_kernel<<<dim3(qparts, nw), 256, sbr_qr_smem_bytes(), st>>>(P);
-            sbr_symm_kernel<<<dim3(nbmax * P.seg, nw), 256, sbr_symm_smem_bytes(), st>>>(P);
-            sbr_w1_kernel<<<dim3(nbmax, nw), 256, sbr_w_smem_bytes(), st>>>(P);
-            sbr_w2_kernel<<<nw, 256, sbr_w_smem_bytes(), st>>>(P);
-            sbr_w3_kernel<<<dim3(nbmax, nw), 256, sbr_w_smem_bytes(), st>>>(P);
             const int64_t tiles = (int64_t)nbmax * (nbmax + 1) / 2;
             const int ctas = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (4 * sms + nw - 1) / nw));
-            sbr_syr2k_kernel<<<dim3(ctas, nw), 256, sbr_syr2k_smem_bytes(), st>>>(P);
+            tk.go(0); sbr_panel_qr_kernel<<<dim3(qparts, nw), 256, sbr_qr_smem_bytes(), st>>>(P);
+            tk.go(1); sbr_symm_kernel<<<dim3(nbmax * P.seg, nw), 256, sbr_symm_smem_bytes(), st>>>(P);
+            tk.go(2); sbr_w1_kernel<<<dim3(nbmax, nw), 256, sbr_w_smem_bytes(), st>>>(P);
+            sbr_w2_kernel<<<nw, 256, sbr_w_smem_bytes(), st>>>(P);
+            sbr_w3_kernel<<<dim3(nbmax, nw), 256, sbr_w_smem_bytes(), st>>>(P);
+            tk.go(3); sbr_syr2k_kernel<<<dim3(ctas, nw), 256, sbr_syr2k_smem_bytes(), st>>>(P);
+            tk.go(-1);
             sp.end();
             GSI_CUDA(ctx, cudaGetLastError());
         }

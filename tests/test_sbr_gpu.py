@@ -49,7 +49,7 @@ def test_band_and_tridiagonal_are_similar_to_a(ctx, n, density):
 
 
 @pytest.mark.parametrize("n,density,sbr_min", [(130, 0.9, 130), (200, 0.5, 130), (257, 0.9, 130), (700, 0.9, 130),
-                                               (1024, 0.9, None), (1500, 0.3, None), (2100, 0.9, None)])
+                                               (1024, 0.9, 1024), (1500, 0.3, 1024), (2100, 0.9, 1024)])
 def test_eigenpairs_through_both_stages(ctx, monkeypatch, n, density, sbr_min):
     from oracle import gsi_oracle as O
     if sbr_min is not None:

@@ -230,3 +230,59 @@ def test_closed_form_cutoff_on_a_clique(ctx, monkeypatch, n, kk, exact):
     out = ctx.local_calc(offsets, items, ratings)
     assert (out["status"] != 4).all() and (out["kk"] == kk).all() and (out["cols"] == 2).all()
     assert np.abs(out["w_lim"] - np.sqrt(n * kk) / (n - 1)).max() <= 1e-8
+
+
+def test_lanczos_guard(ctx, monkeypatch):
+    """The fast path runs Lanczos from two independent start vectors and sends a pair to the exact path when the two Ritz
+    values disagree.  On ordinary graphs the guard must change nothing: same w_lim bit for bit (the
+    reported value is the first run's), same status / kk / cols with GSI_LC_GUARD=0.  On a graph made of two cliques that
+    meet only in the target movie the unrated block P[unrated, unrated] is (nearly) reducible -- the family where one
+    start vector can miss the wanted eigenvector -- and fast (guarded) and exact paths must still agree to 1e-9."""
+    fin, test = _random_case(5, 60, 20, 0.4, 3, 20)
+    a = np.array([e[0] for e in fin], dtype=np.int32)
+    b = np.array([e[1] for e in fin], dtype=np.int32)
+    w = np.array([e[2] for e in fin], dtype=np.float64)
+    ctx.set_weights_edges(a, b, w)
+    users, offsets, items, ratings = _csr(test)
+    guarded = ctx.local_calc(offsets, items, ratings)
+    monkeypatch.setenv("GSI_LC_GUARD", "0")
+    single = ctx.local_calc(offsets, items, ratings)
+    monkeypatch.delenv("GSI_LC_GUARD")
+    for k in guarded:
+        assert np.array_equal(guarded[k], single[k], equal_nan=True), k
+    # two cliques {2..31} and {32..61} with different weights, joined only through movie 1
+    rng = np.random.default_rng(11)
+    fin = []
+    for lo, hi, wt in ((2, 32, 0.9), (32, 62, 0.3)):
+        for x in range(lo, hi):
+            for y in range(x + 1, hi):
+                ww = float("%g" % np.float32(wt * rng.uniform(0.8, 1.0)))
+                fin += [(x, y, ww), (y, x, ww)]
+    for x in range(2, 62):
+        ww = float("%g" % np.float32(rng.uniform(0.2, 0.9)))
+        fin += [(1, x, ww), (x, 1, ww)]
+    test = {}
+    for u in range(1, 13):
+        its = [1] + [int(i) for i in rng.choice(np.arange(2, 62), size=int(rng.integers(4, 25)), replace=False)]
+        for m in its:
+            test.setdefault(m, {})[O.UIMAX - u] = float(rng.integers(1, 6))
+    _run_and_compare(ctx, fin, test, min_ok=20)
+    users, offsets, items, ratings = _csr(test)
+    fast = ctx.local_calc(offsets, items, ratings)
+    monkeypatch.setenv("GSI_LC_EXACT", "1")
+    exact = ctx.local_calc(offsets, items, ratings)
+    sel = fast["kk"] > 0
+    assert np.array_equal(fast["status"], exact["status"])
+    assert np.abs(fast["w_lim"][sel] - exact["w_lim"][sel]).max() <= 1e-9
+
+
+def test_local_graphs_on_the_two_stage_route(ctx, monkeypatch):
+    """Local graphs above GSI_HH_MAX_N (9,216) nodes -- possible from the ML-10M shape on, 10,681 items -- are no longer
+    rejected: their eigensolves take the two-stage tridiagonalisation.  The route is exercised here at a size the oracle
+    finishes in seconds by lowering the switch-over (GSI_SBR_MIN=130: the ~190-node local graphs and the exact path's
+    per-pair matrices above 130 rows all go dense -> band -> tridiagonal), same bars as every other case."""
+    monkeypatch.setenv("GSI_SBR_MIN", "130")
+    fin, test = _random_case(3, 260, 6, 0.7, 100, 240)
+    _run_and_compare(ctx, fin, test, min_ok=50)
+    monkeypatch.setenv("GSI_LC_EXACT", "1")
+    _run_and_compare(ctx, fin, test, min_ok=50)
