@@ -220,6 +220,46 @@ def deal_users(deg, rank, world):
     return np.sort(order[rank::world])
 
 
+def knn_block(local_rank, r, legacy_too=True):
+    """knn2 stage (north_star kernel (4), knn2.cpp:127-164) over ALL ratings of the benchmarked shape as train set: item-major
+    transpose, per-(item, column tile) accumulation in shared memory, cosine weights, edge compaction.  Kernel time by CUDA
+    events (class `knn`), the r01 scatter with global atomics timed beside it (GSI_KNN_LEGACY=1) on the same input."""
+    from collaborative_filtering_b200.api import Context
+    c = Context(local_rank)
+    try:
+        c.timing_enable(True)
+        deg = r.degrees().astype(np.float64)
+        pair_updates = float((deg * (deg - 1)).sum())                      # ordered pairs: every (a, b) row entry is owned once
+        out = {}
+        for name, env in (("item_stationary", None), ("legacy_global_atomics", "1")):
+            if env is None:
+                os.environ.pop("GSI_KNN_LEGACY", None)
+            elif not legacy_too:
+                continue
+            else:
+                os.environ["GSI_KNN_LEGACY"] = env
+            c.knn_build(r.offsets, r.items, r.ratings, r.n_items + 1, install_weights=False)      # warm-up (allocations)
+            c.timing_reset()
+            t0 = time.perf_counter()
+            a, _, w = c.knn_build(r.offsets, r.items, r.ratings, r.n_items + 1, install_weights=False)
+            wall = time.perf_counter() - t0
+            ms = c.timing()["knn"]["ms"]
+            upd = pair_updates if env is None else pair_updates / 2                             # the scatter visits a < b once
+            out[name] = {"kernel_ms": ms, "wall_s": wall, "edges": int(len(w)), "pair_updates_per_s": upd / (ms * 1e-3),
+                         "atomic_lane_ops_per_s": 4 * upd / (ms * 1e-3), "edge_checksum": float(np.float64(w).sum())}
+        os.environ.pop("GSI_KNN_LEGACY", None)
+        res = {"what": "knn2 stage on the whole shape as train set (%d users, %d items, %d ratings)" % (r.n_users, r.n_items, r.nnz),
+               "bound": "shared-memory integer atomics (ATOMS.ADD), 4 per ordered rated pair; no DRAM stream of comparable size",
+               **out}
+        if "legacy_global_atomics" in out:
+            res["speedup_vs_legacy"] = out["legacy_global_atomics"]["kernel_ms"] / out["item_stationary"]["kernel_ms"]
+            res["identical_edges"] = (out["legacy_global_atomics"]["edges"] == out["item_stationary"]["edges"]
+                                      and out["legacy_global_atomics"]["edge_checksum"] == out["item_stationary"]["edge_checksum"])
+        return res
+    finally:
+        c.close()
+
+
 def predict_fold(local_rank, rank=0, world=1, shape="ml-1m", fold=0, oracle_pairs=1500, nmax_oracle=400):
     """Collective over the ranks.  Returns the whole-job block printed as "predict" (rank 0 adds the oracle comparison)."""
     from collaborative_filtering_b200.api import Context
@@ -520,6 +560,9 @@ def run_gpu(args, rank, world, local_rank):
     predict_aux = None
     if not args.no_predict:
         predict_aux = predict_fold(local_rank, rank, world)
+    knn_aux = None
+    if not args.no_knn and rank == 0:
+        knn_aux = knn_block(local_rank, r)
 
     if rank == 0:
         # ---- roofline (live CUDA-event times of the timed region; every class is timed on every launch) ----
@@ -597,6 +640,7 @@ def run_gpu(args, rank, world, local_rank):
             "parity": parity,
             "cpu_baseline": cpu,
             "predict": predict_aux,
+            "knn": knn_aux,
             "rmse_delta": (predict_aux or {}).get("rmse_parity", {}).get("rmse_delta") if predict_aux else None,
         }
         print(json.dumps(line), flush=True)
@@ -616,6 +660,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the post-timed parity block")
     ap.add_argument("--no-predict", action="store_true", help="skip the predictions/s + RMSE block (ML-1M fold)")
+    ap.add_argument("--no-knn", action="store_true", help="skip the knn2 stage timing on the benchmarked shape")
     ap.add_argument("--workspace-gb", type=int, default=64)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -79,6 +79,9 @@ SYMBOLS = {
     "gsi_timing_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "gsi_measure_fp64_tflops": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_f64p]),
     "gsi_debug_band": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 4),
+    "gsi_debug_tc_gemm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                         ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_void_p, ctypes.c_void_p]),
     "gsi_debug_eigh": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_float, ctypes.c_int] +
                        [ctypes.c_void_p] * 7),
 }

@@ -443,6 +443,19 @@ class Context:
         kk = int(k.value)
         return dict(d=d, e=e[:n - 1], tau=tau[:n - 1], v=v, lam=lam, u=u[:, :kk], k=kk)
 
+    def debug_tc_gemm(self, a: np.ndarray, b: np.ndarray, slices: int = 8, reps: int = 1):
+        """C = A @ B through the tcgen05 INT8-slice engine (gsi_debug_tc_gemm).  Returns (C, ms_slice, ms_gemm)."""
+        a = np.asfortranarray(a, dtype=np.float64)
+        b = np.asfortranarray(b, dtype=np.float64)
+        m, k = a.shape
+        k2, n = b.shape
+        assert k == k2
+        c = np.zeros((m, n), order="F")
+        ms_s, ms_g = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        self._check(self._lib.gsi_debug_tc_gemm(self._h, m, n, k, _ptr(a), max(m, 1), _ptr(b), max(k, 1), _ptr(c), max(m, 1), slices, reps,
+                                                ctypes.byref(ms_s), ctypes.byref(ms_g)))
+        return c, ms_s.value, ms_g.value
+
     def debug_band(self, a: np.ndarray, chase: bool = True):
         """Two-stage test hook (gsi_debug_band): returns dict(band = dense symmetric band matrix after stage 1, d, e)."""
         a = np.asfortranarray(a, dtype=np.float64)

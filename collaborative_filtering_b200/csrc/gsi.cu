@@ -22,6 +22,7 @@
 #include "kern_sbr.cuh"
 #include "kern_cheby.cuh"
 #include "kern_lc.cuh"
+#include "tc_gemm.cuh"
 
 static thread_local std::string g_tls_err;
 
@@ -102,6 +103,7 @@ struct PinBuf {
 
 struct Workspace {
     DevBuf k_off, k_items, k_rat, k_cnt, k_num, k_S, k_ecnt, k_eoff, k_ea, k_eb, k_ew, k_co, k_err, k_mcnt, k_has;
+    DevBuf k_coff, k_cur, k_cuser, k_crat, k_useg;     // item-major transpose of the knn CSR (knn_row_kernel)
     DevBuf c_off, c_col, c_w, c_wn, c_vec;          // Chebyshev filter: CSR, normalised weights, 5 vertex vectors
     int64_t knn_edges = 0;
     DevBuf pred_meta, pred_work, p_off, p_items, p_wlim, p_rat, p_k, p_lamoff, p_vecoff, p_lam, p_vec, p_err, p_kk, p_pred, p_status, p_cols, p_gsum, p_hsum, p_sumoff, p_exact, p_lim, p_mask;
@@ -176,7 +178,7 @@ extern "C" int gsi_destroy(gsi_ctx* c) {
                     &w.p_exact, &w.p_lim, &w.p_mask};
     for (auto b : d2) b->release();
     DevBuf* d3[] = {&w.k_off, &w.k_items, &w.k_rat, &w.k_cnt, &w.k_num, &w.k_S, &w.k_ecnt, &w.k_eoff, &w.k_ea, &w.k_eb, &w.k_ew,
-                    &w.k_co, &w.k_err, &w.k_mcnt, &w.k_has, &w.c_off, &w.c_col, &w.c_w, &w.c_wn, &w.c_vec};
+                    &w.k_co, &w.k_err, &w.k_mcnt, &w.k_has, &w.k_coff, &w.k_cur, &w.k_cuser, &w.k_crat, &w.k_useg, &w.c_off, &w.c_col, &w.c_w, &w.c_wn, &w.c_vec};
     for (auto b : d3) b->release();
     DevBuf* d4[] = {&w.hhA, &w.hhQa, &w.hhQb, &w.hhS, &w.hhvec, &w.hhivec, &w.trd_acol, &w.trd_ypart, &w.trd_part, &w.trd_panels,
                     &w.sbr_panels, &w.sbr_small, &w.sbr_band, &w.sbr_v2, &w.sbr_prog, &w.sbr_list};
@@ -965,6 +967,60 @@ static int knn_upload_csr(gsi_ctx* ctx, int64_t nu, const int64_t* off, const in
     return GSI_OK;
 }
 
+
+// ---- test / measurement hook of the tcgen05 FP64-equivalent GEMM (tc_gemm.cu) ----------------------------------------
+extern "C" int gsi_debug_tc_gemm(gsi_ctx* ctx, int m, int n, int k, const double* a, int64_t lda, const double* b, int64_t ldb,
+                                 double* c, int64_t ldc, int slices, int reps, double* ms_slice, double* ms_gemm) {
+    if (!ctx) return gsi_fail(nullptr, GSI_ERR_INVALID, "null context");
+    if (m < 1 || n < 1 || k < 1 || !a || !b || !c || lda < m || ldb < k || ldc < m || slices < 6 || slices > 8 || reps < 1)
+        return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_debug_tc_gemm: bad argument");
+    GSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    double *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    int8_t *Ap = nullptr, *Bp = nullptr;
+    int32_t *ea = nullptr, *eb = nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    int rc = GSI_OK;
+    auto fin = [&]() {
+        cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(Ap); cudaFree(Bp); cudaFree(ea); cudaFree(eb);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+    };
+#define TCG(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fin(); return gsi_fail(ctx, GSI_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
+    TCG(cudaMalloc((void**)&dA, (size_t)lda * k * 8));
+    TCG(cudaMalloc((void**)&dB, (size_t)ldb * n * 8));
+    TCG(cudaMalloc((void**)&dC, (size_t)ldc * n * 8));
+    TCG(cudaMalloc((void**)&Ap, tc_gemm_plane_bytes_a(m, k, slices)));
+    TCG(cudaMalloc((void**)&Bp, tc_gemm_plane_bytes_b(k, n, slices)));
+    TCG(cudaMalloc((void**)&ea, (size_t)m * 4));
+    TCG(cudaMalloc((void**)&eb, (size_t)n * 4));
+    for (auto& e : ev) TCG(cudaEventCreate(&e));
+    TCG(cudaMemcpyAsync(dA, a, (size_t)lda * k * 8, cudaMemcpyHostToDevice, st));
+    TCG(cudaMemcpyAsync(dB, b, (size_t)ldb * n * 8, cudaMemcpyHostToDevice, st));
+    TCG(cudaMemsetAsync(dC, 0, (size_t)ldc * n * 8, st));
+    TcGemmArgs A;
+    memset(&A, 0, sizeof A);
+    A.A = dA; A.lda = lda; A.B = dB; A.ldb = ldb; A.C = dC; A.ldc = ldc; A.M = m; A.N = n; A.K = k; A.S = slices;
+    A.Ap = Ap; A.Bp = Bp; A.ea = ea; A.eb = eb;
+    float t_slice = 0.f, t_gemm = 0.f;
+    for (int r = 0; r < reps; ++r) {
+        TCG(cudaEventRecord(ev[0], st));
+        TCG(tc_gemm_slice_only(A, st));
+        TCG(cudaEventRecord(ev[1], st));
+        TCG(tc_gemm_mma_only(A, st, ctx->sm_count));
+        TCG(cudaEventRecord(ev[2], st));
+    }
+    TCG(cudaStreamSynchronize(st));
+    TCG(cudaEventElapsedTime(&t_slice, ev[0], ev[1]));
+    TCG(cudaEventElapsedTime(&t_gemm, ev[1], ev[2]));
+    TCG(cudaMemcpyAsync(c, dC, (size_t)ldc * n * 8, cudaMemcpyDeviceToHost, st));
+    TCG(cudaStreamSynchronize(st));
+#undef TCG
+    if (ms_slice) *ms_slice = t_slice;
+    if (ms_gemm) *ms_gemm = t_gemm;
+    fin();
+    return rc;
+}
+
 extern "C" int gsi_knn_build_host(gsi_ctx* ctx, int64_t nu, const int64_t* off, const int32_t* items, const float* ratings,
                                   int rows, int install_weights, int64_t* n_edges) {
     if (!ctx) return gsi_fail(nullptr, GSI_ERR_INVALID, "null context");
@@ -974,22 +1030,62 @@ extern "C" int gsi_knn_build_host(gsi_ctx* ctx, int64_t nu, const int64_t* off, 
     int rc, nmax = 0;
     if ((rc = knn_upload_csr(ctx, nu, off, items, ratings, &nmax)) != GSI_OK) return rc;
     const size_t nn = (size_t)rows * rows;
-    if ((rc = ws.k_cnt.ensure(ctx, nn * 4)) != GSI_OK) return rc;
+    const char* lg = getenv("GSI_KNN_LEGACY");
+    bool legacy = lg && atoi(lg) != 0;                         // 1: the r01 scatter with global atomics (kept for before / after timings)
+    for (int64_t t = 0, e = off[nu]; t < e && !legacy; ++t) {  // the item-stationary kernel counts in quarter units: half-star grid only
+        const float r2 = ratings[t] * 2.f;
+        if (!(r2 >= 0.f && r2 <= 255.f) || r2 != (float)(int)r2) legacy = true;
+    }
     if ((rc = ws.k_num.ensure(ctx, nn * 4)) != GSI_OK) return rc;
-    if ((rc = ws.k_S.ensure(ctx, nn * 4)) != GSI_OK) return rc;
+    if (legacy) {
+        if ((rc = ws.k_cnt.ensure(ctx, nn * 4)) != GSI_OK) return rc;
+        if ((rc = ws.k_S.ensure(ctx, nn * 4)) != GSI_OK) return rc;
+    }
     if ((rc = ws.k_ecnt.ensure(ctx, (size_t)(rows + 1) * 8)) != GSI_OK) return rc;
     if ((rc = ws.k_eoff.ensure(ctx, (size_t)(rows + 1) * 8)) != GSI_OK) return rc;
     if ((rc = ws.h_small.ensure(ctx, 64)) != GSI_OK) return rc;
     cudaStream_t st = ctx->stream;
-    GSI_CUDA(ctx, cudaMemsetAsync(ws.k_cnt.p, 0, nn * 4, st));
-    GSI_CUDA(ctx, cudaMemsetAsync(ws.k_num.p, 0, nn * 4, st));
-    GSI_CUDA(ctx, cudaMemsetAsync(ws.k_S.p, 0, nn * 4, st));
-    GsiSpan sp(ctx, GSI_T_KNN, 4);
-    if (nu > 0 && nmax > 1)
-        knn_accumulate_kernel<<<dim3((unsigned)nu, (nmax + 127) / 128), 128, 0, st>>>(ws.k_off.as<int64_t>(), ws.k_items.as<int32_t>(), ws.k_rat.as<float>(),
-                                                                               rows, ws.k_cnt.as<int>(), ws.k_num.as<float>(), ws.k_S.as<float>());
-    knn_finalize_kernel<<<rows, 256, 0, st>>>(rows, ws.k_cnt.as<int>(), ws.k_num.as<float>(), ws.k_S.as<float>(), 0, ws.k_ecnt.as<int64_t>(),
-                                               nullptr, nullptr, nullptr, nullptr, nullptr);
+    double* Wd = nullptr;
+    if (install_weights) {
+        drop_weights(ctx);
+        GSI_CUDA(ctx, cudaMalloc((void**)&ctx->d_w, nn * sizeof(double)));
+        ctx->own_w = true; ctx->w_rows = rows;
+        if (legacy) GSI_CUDA(ctx, cudaMemsetAsync(ctx->d_w, 0, nn * sizeof(double), st));
+        Wd = ctx->d_w;
+    }
+    const int64_t nnz = off[nu];
+    GsiSpan sp(ctx, GSI_T_KNN, legacy ? 4 : 7);
+    if (legacy) {
+        GSI_CUDA(ctx, cudaMemsetAsync(ws.k_cnt.p, 0, nn * 4, st));
+        GSI_CUDA(ctx, cudaMemsetAsync(ws.k_num.p, 0, nn * 4, st));
+        GSI_CUDA(ctx, cudaMemsetAsync(ws.k_S.p, 0, nn * 4, st));
+        if (nu > 0 && nmax > 1)
+            knn_accumulate_kernel<<<dim3((unsigned)nu, (nmax + 127) / 128), 128, 0, st>>>(ws.k_off.as<int64_t>(), ws.k_items.as<int32_t>(), ws.k_rat.as<float>(),
+                                                                                   rows, ws.k_cnt.as<int>(), ws.k_num.as<float>(), ws.k_S.as<float>());
+        knn_finalize_kernel<<<rows, 256, 0, st>>>(rows, ws.k_cnt.as<int>(), ws.k_num.as<float>(), ws.k_S.as<float>(), 0, ws.k_ecnt.as<int64_t>(),
+                                                   nullptr, nullptr, nullptr, nullptr, nullptr);
+    } else {
+        // item-major transpose + per-(user, tile) slice starts, then one CTA per (item, column tile): kern_knn.cuh
+        const int ntile = (rows + KNN_CT - 1) / KNN_CT;
+        if (ntile + 1 > 128) return gsi_fail(ctx, GSI_ERR_INVALID, "gsi_knn_build_host: %d items exceed the tile table", rows);
+        if ((rc = ws.k_coff.ensure(ctx, (size_t)(rows + 1) * 8)) != GSI_OK) return rc;
+        if ((rc = ws.k_cur.ensure(ctx, (size_t)(rows + 1) * 8)) != GSI_OK) return rc;
+        if ((rc = ws.k_cuser.ensure(ctx, (size_t)std::max<int64_t>(nnz, 1) * 4)) != GSI_OK) return rc;
+        if ((rc = ws.k_crat.ensure(ctx, (size_t)std::max<int64_t>(nnz, 1) * 4)) != GSI_OK) return rc;
+        if ((rc = ws.k_useg.ensure(ctx, (size_t)std::max<int64_t>(nu, 1) * (ntile + 1) * 4)) != GSI_OK) return rc;
+        GSI_CUDA(ctx, cudaMemsetAsync(ws.k_cur.p, 0, (size_t)(rows + 1) * 8, st));
+        if (nnz > 0) knn_csc_count_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, ws.k_items.as<int32_t>(), rows, ws.k_cur.as<unsigned long long>());
+        knn_scan_kernel<<<1, 1024, 0, st>>>(rows, ws.k_cur.as<int64_t>(), ws.k_coff.as<int64_t>());
+        GSI_CUDA(ctx, cudaMemsetAsync(ws.k_cur.p, 0, (size_t)(rows + 1) * 8, st));
+        if (nu > 0)
+            knn_csc_fill_kernel<<<dim3((unsigned)nu, std::max(1, (nmax + 127) / 128)), 128, 0, st>>>(
+                ws.k_off.as<int64_t>(), ws.k_items.as<int32_t>(), ws.k_rat.as<float>(), rows, ntile, ws.k_coff.as<int64_t>(),
+                ws.k_cur.as<unsigned long long>(), ws.k_cuser.as<int32_t>(), ws.k_crat.as<float>(), ws.k_useg.as<int32_t>());
+        knn_row_kernel<<<dim3(rows, ntile), 256, 0, st>>>(ws.k_off.as<int64_t>(), ws.k_items.as<int32_t>(), ws.k_rat.as<float>(), ws.k_coff.as<int64_t>(),
+                                                          ws.k_cuser.as<int32_t>(), ws.k_crat.as<float>(), ws.k_useg.as<int32_t>(), rows, ntile,
+                                                          ws.k_num.as<float>(), Wd);
+        knn_compact_kernel<<<rows, 256, 0, st>>>(rows, ws.k_num.as<float>(), 0, ws.k_ecnt.as<int64_t>(), nullptr, nullptr, nullptr, nullptr);
+    }
     knn_scan_kernel<<<1, 1024, 0, st>>>(rows, ws.k_ecnt.as<int64_t>(), ws.k_eoff.as<int64_t>());
     GSI_CUDA(ctx, cudaGetLastError());
     int64_t* h_ne = (int64_t*)(ws.h_small.as<char>() + 48);
@@ -1000,16 +1096,12 @@ extern "C" int gsi_knn_build_host(gsi_ctx* ctx, int64_t nu, const int64_t* off, 
     if ((rc = ws.k_ea.ensure(ctx, std::max<int64_t>(ne, 1) * 4)) != GSI_OK) return rc;
     if ((rc = ws.k_eb.ensure(ctx, std::max<int64_t>(ne, 1) * 4)) != GSI_OK) return rc;
     if ((rc = ws.k_ew.ensure(ctx, std::max<int64_t>(ne, 1) * 4)) != GSI_OK) return rc;
-    double* Wd = nullptr;
-    if (install_weights) {
-        drop_weights(ctx);
-        GSI_CUDA(ctx, cudaMalloc((void**)&ctx->d_w, nn * sizeof(double)));
-        ctx->own_w = true; ctx->w_rows = rows;
-        GSI_CUDA(ctx, cudaMemsetAsync(ctx->d_w, 0, nn * sizeof(double), st));
-        Wd = ctx->d_w;
-    }
-    knn_finalize_kernel<<<rows, 256, 0, st>>>(rows, ws.k_cnt.as<int>(), ws.k_num.as<float>(), ws.k_S.as<float>(), 1, ws.k_ecnt.as<int64_t>(),
-                                               ws.k_eoff.as<int64_t>(), ws.k_ea.as<int32_t>(), ws.k_eb.as<int32_t>(), ws.k_ew.as<float>(), Wd);
+    if (legacy)
+        knn_finalize_kernel<<<rows, 256, 0, st>>>(rows, ws.k_cnt.as<int>(), ws.k_num.as<float>(), ws.k_S.as<float>(), 1, ws.k_ecnt.as<int64_t>(),
+                                                   ws.k_eoff.as<int64_t>(), ws.k_ea.as<int32_t>(), ws.k_eb.as<int32_t>(), ws.k_ew.as<float>(), Wd);
+    else
+        knn_compact_kernel<<<rows, 256, 0, st>>>(rows, ws.k_num.as<float>(), 1, ws.k_ecnt.as<int64_t>(), ws.k_eoff.as<int64_t>(),
+                                                  ws.k_ea.as<int32_t>(), ws.k_eb.as<int32_t>(), ws.k_ew.as<float>());
     sp.end();
     GSI_CUDA(ctx, cudaGetLastError());
     GSI_CUDA(ctx, cudaStreamSynchronize(st));

@@ -311,11 +311,19 @@ int gsi_measure_fp64_tflops(gsi_ctx* ctx, int use_dmma, double* tflops);
 int gsi_debug_eigh(gsi_ctx* ctx, int n, const double* a, float thr, int team, double* d, double* e,
                    double* tau, double* v, double* lam, double* u, int32_t* k);
 
-/* Test hook of the two-stage tridiagonalisation (users with n >= 1024, GSI_SBR_MIN overrides): stage 1 (dense -> band of
+/* Test hook of the two-stage tridiagonalisation (by default the route of users with n > 9,216; GSI_SBR_MIN overrides): stage 1 (dense -> band of
  * half-width 64) on ONE dense symmetric matrix (host, column-major, n >= 130).  ab[j * 128 + dd] = B(j + dd, j), dd = 0 .. 64
  * (zero beyond); B is orthogonally similar to A.  With d / e non-NULL stage 2 (bulge chasing) runs as well and the tridiagonal
  * comes back. */
 int gsi_debug_band(gsi_ctx* ctx, int n, const double* a, double* ab, double* d, double* e);
+
+/* Test / measurement hook of the FP64-equivalent tensor-core GEMM (csrc/tc_gemm.cu: INT8 slices on tcgen05.mma.kind::i8,
+ * INT32 accumulators in tensor memory; the engine behind the divide-and-conquer merges that replace the QR-iteration half of
+ * precompute_local.cpp:231).  C (m x n) = A (m x k) * B (k x n), host buffers, column-major with the given leading dimensions.
+ * slices = 6, 7 or 8 digits of 7 bits per operand entry.  The device part runs `reps` times (>= 1); ms_slice / ms_gemm return
+ * the CUDA-event time of ONE repetition of the slicing kernels and of the tcgen05 kernel (either may be NULL). */
+int gsi_debug_tc_gemm(gsi_ctx* ctx, int m, int n, int k, const double* a, int64_t lda, const double* b, int64_t ldb,
+                      double* c, int64_t ldc, int slices, int reps, double* ms_slice, double* ms_gemm);
 
 #ifdef __cplusplus
 }
