@@ -979,10 +979,11 @@ extern "C" int gsi_debug_tc_gemm(gsi_ctx* ctx, int m, int n, int k, const double
     double *dA = nullptr, *dB = nullptr, *dC = nullptr;
     int8_t *Ap = nullptr, *Bp = nullptr;
     int32_t *ea = nullptr, *eb = nullptr;
+    TcTask* dT = nullptr;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     int rc = GSI_OK;
     auto fin = [&]() {
-        cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(Ap); cudaFree(Bp); cudaFree(ea); cudaFree(eb);
+        cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(Ap); cudaFree(Bp); cudaFree(ea); cudaFree(eb); cudaFree(dT);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
     };
 #define TCG(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fin(); return gsi_fail(ctx, GSI_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
@@ -997,16 +998,20 @@ extern "C" int gsi_debug_tc_gemm(gsi_ctx* ctx, int m, int n, int k, const double
     TCG(cudaMemcpyAsync(dA, a, (size_t)lda * k * 8, cudaMemcpyHostToDevice, st));
     TCG(cudaMemcpyAsync(dB, b, (size_t)ldb * n * 8, cudaMemcpyHostToDevice, st));
     TCG(cudaMemsetAsync(dC, 0, (size_t)ldc * n * 8, st));
-    TcGemmArgs A;
-    memset(&A, 0, sizeof A);
-    A.A = dA; A.lda = lda; A.B = dB; A.ldb = ldb; A.C = dC; A.ldc = ldc; A.M = m; A.N = n; A.K = k; A.S = slices;
-    A.Ap = Ap; A.Bp = Bp; A.ea = ea; A.eb = eb;
+    TcTask h[2];
+    memset(h, 0, sizeof h);
+    h[0].A = dA; h[0].lda = lda; h[0].B = dB; h[0].ldb = ldb; h[0].C = dC; h[0].ldc = ldc; h[0].M = m; h[0].N = n; h[0].K = k;
+    h[0].Ap = Ap; h[0].Bp = Bp; h[0].ea = ea; h[0].eb = eb;
+    TCG(cudaMalloc((void**)&dT, sizeof h));
+    TCG(cudaMemcpyAsync(dT, h, sizeof h, cudaMemcpyHostToDevice, st));
+    TcBatch A;
+    A.tasks = dT; A.ntasks = 1; A.Mmax = m; A.Nmax = n; A.Kmax = k; A.S = slices;
     float t_slice = 0.f, t_gemm = 0.f;
     for (int r = 0; r < reps; ++r) {
         TCG(cudaEventRecord(ev[0], st));
-        TCG(tc_gemm_slice_only(A, st));
+        TCG(tc_gemm_slice(A, st));
         TCG(cudaEventRecord(ev[1], st));
-        TCG(tc_gemm_mma_only(A, st, ctx->sm_count));
+        TCG(tc_gemm_mma(A, st, ctx->sm_count));
         TCG(cudaEventRecord(ev[2], st));
     }
     TCG(cudaStreamSynchronize(st));

@@ -322,9 +322,10 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
             if (ctx->trace) fprintf(stderr, "[gsi trace] dc level %d: %d nodes, mmax %d\n", l, P.nnodes, mmax);
             {
                 HhTrace tr(ctx, "  deflate");
-                const size_t dsm = dc_deflate_smem_bytes(mmax);
+                const int in_global = mmax > DC_DEFLATE_SMEM_MAX_M;
+                const size_t dsm = in_global ? 64 : dc_deflate_smem_bytes(mmax);
                 GSI_CUDA(ctx, cudaFuncSetAttribute(dc_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(dsm, 48 * 1024)));
-                dc_deflate_kernel<<<P.nnodes, 256, dsm, st>>>(P);
+                dc_deflate_kernel<<<P.nnodes, 256, dsm, st>>>(P, in_global);
             }
             {
                 HhTrace tr(ctx, "  secular");       // lanes per root grow with the merge size (few, big merges near the top)

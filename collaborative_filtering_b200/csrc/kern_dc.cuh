@@ -140,7 +140,8 @@ __global__ void __launch_bounds__(128) dc_leaf_kernel(const HJob* __restrict__ j
 // dynamic shared memory: the merged pole list (d, z, source index, type) of the node -- the deflation scan and the map
 // construction are serial chains over it (one thread), which must not run on global-memory latency
 static inline size_t dc_deflate_smem_bytes(int mmax) { return (size_t)mmax * (8 + 8 + 4 + 4) + 64; }
-__global__ void __launch_bounds__(256) dc_deflate_kernel(DcParams P) {
+#define DC_DEFLATE_SMEM_MAX_M 9600        // merges above this many poles (the Netflix tail: users up to 17,653 items) keep the lists in global memory
+__global__ void __launch_bounds__(256) dc_deflate_kernel(DcParams P, int lists_in_global) {
     extern __shared__ __align__(16) unsigned char dfl_smem[];
     const DcNode nd = P.nodes[P.node0 + blockIdx.x];
     DcState& st = P.state[P.node0 + blockIdx.x];
@@ -150,10 +151,12 @@ __global__ void __launch_bounds__(256) dc_deflate_kernel(DcParams P) {
     double* Qin = (P.in_b ? P.Qb : P.Qa) + jb.m_off + (size_t)off * ld + off;      // block (off, off)
     const double* lamIn = (P.in_b ? P.lamB : P.lamA) + vb;
     double* ds = P.ds + vb; double* zs = P.zs + vb; int32_t* src = P.src + vb;
-    double* s_ds = (double*)dfl_smem;                   // [m]
-    double* s_zs = s_ds + m;                            // [m]
-    int32_t* s_src = (int32_t*)(s_zs + m);              // [m]
-    int32_t* s_type = s_src + m;                        // [m] 1 top, 2 dense, 3 bottom
+    // lists_in_global: the node's own global arrays serve as the working copy (pos_df, written by dc_rank later, holds the types);
+    // the serial scans then run through L1 / L2 -- a few ms on the one or two merges of a level that are this big
+    double* s_ds = lists_in_global ? ds : (double*)dfl_smem;                                   // [m]
+    double* s_zs = lists_in_global ? zs : s_ds + m;                                            // [m]
+    int32_t* s_src = lists_in_global ? src : (int32_t*)(s_zs + m);                             // [m]
+    int32_t* s_type = lists_in_global ? P.pos_df + vb : s_src + m;                             // [m] 1 top, 2 dense, 3 bottom
     const double beta = P.e[jb.r_off + off + n1 - 1];
     const double sgn = beta >= 0.0 ? 1.0 : -1.0;
     const double rho = 2.0 * fabs(beta);
@@ -221,7 +224,8 @@ __global__ void __launch_bounds__(256) dc_deflate_kernel(DcParams P) {
         nrot_s = nrot;
     }
     __syncthreads();
-    for (int i = tid; i < m; i += 256) { ds[i] = s_ds[i]; zs[i] = s_zs[i]; }       // the global copies other kernels read
+    if (!lists_in_global)
+        for (int i = tid; i < m; i += 256) { ds[i] = s_ds[i]; zs[i] = s_zs[i]; }   // the global copies other kernels read
     // (c) apply the rotations to the columns of Qin, in order
     const int nrot = nrot_s;
     for (int r = 0; r < nrot; ++r) {

@@ -93,39 +93,54 @@ __device__ __forceinline__ int tc_exponent(double amax) {
     return e + 1;
 }
 
-// grid (lines), block 256: max |x| over a line of length K.  A: line = row i (elements A[i + k lda]); B: line = column j
-// (elements B[k + j ldb]).  With `gather` the k-th element of a row of A is column gather[k] (the D&C's column selection).
-__global__ void __launch_bounds__(256) tc_line_exp_kernel(const double* __restrict__ X, int64_t ld, int lines, int K, int a_side,
-                                                          const int32_t* __restrict__ gather, int32_t* __restrict__ expo) {
-    __shared__ double red[8];
-    const int line = blockIdx.x;
-    double m = 0.0;
-    for (int k = threadIdx.x; k < K; k += 256) {
-        const int kk = gather ? gather[k] : k;
-        const double v = a_side ? X[(size_t)kk * ld + line] : X[(size_t)line * ld + kk];
-        m = fmax(m, fabs(v));
-    }
-    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w) m = fmax(m, red[w]);
-        expo[line] = tc_exponent(m);
-    }
+// Every kernel works on a device-resident list of TcTask (tc_gemm.cuh): blockIdx.z (or a tile prefix sum for the GEMM) picks the
+// task, whose sizes may have been written by an earlier kernel of the same stream (the D&C's deflation counts).  Grids are sized by
+// host-side upper bounds; blocks beyond a task's real extent leave at once.
+
+// The exponent of a line is the largest element exponent (frexp is monotone in |x|), so the scan is an integer atomicMax over
+// coalesced tiles.  ea / eb start at TC_EXP_NONE (tc_exp_init_kernel); a line of zeros keeps it and is treated as e = 0.
+#define TC_EXP_NONE (-100000)
+__device__ __forceinline__ int tc_elem_exp(double x) {
+    if (!(fabs(x) > 0.0)) return TC_EXP_NONE;
+    int e;
+    frexp(x, &e);
+    return e + 1;
+}
+__device__ __forceinline__ int tc_line_exp(int e) { return e == TC_EXP_NONE ? 0 : e; }
+
+// grid (ceil((Mmax + Nmax) / 256), 1, tasks)
+__global__ void __launch_bounds__(256) tc_exp_init_kernel(const TcTask* __restrict__ tasks) {
+    const TcTask T = tasks[blockIdx.z];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < T.M) T.ea[i] = TC_EXP_NONE;
+    else if (i - T.M < T.N) T.eb[i - T.M] = TC_EXP_NONE;
 }
 
-// A side row maxima need a strided walk per row; for big matrices a tiled version keeps the reads coalesced:
-// grid (ceil(M / 256)), block 256: thread = row, loop over k (reads of a warp are 32 consecutive rows of one column)
-__global__ void __launch_bounds__(256) tc_row_exp_kernel(const double* __restrict__ A, int64_t lda, int M, int K,
-                                                         const int32_t* __restrict__ gather, int32_t* __restrict__ expo) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= M) return;
-    double m = 0.0;
-    for (int k = 0; k < K; ++k) {
-        const int kk = gather ? gather[k] : k;
-        m = fmax(m, fabs(A[(size_t)kk * lda + i]));
+// grid (k blocks max, m tiles max, tasks), block 256: thread = (row r = tid & 127, k half), 32 k's each
+__global__ void __launch_bounds__(256) tc_row_exp_kernel(const TcTask* __restrict__ tasks) {
+    const TcTask T = tasks[blockIdx.z];
+    const int kb = blockIdx.x, i = blockIdx.y * 128 + (threadIdx.x & 127), half = threadIdx.x >> 7;
+    if (kb * 64 >= T.K || i >= T.M) return;
+    int e = TC_EXP_NONE;
+    for (int q = 0; q < 32; ++q) {
+        const int k = kb * 64 + half * 32 + q;
+        if (k < T.K) e = max(e, tc_elem_exp(T.A[(size_t)(T.gather ? T.gather[k] : k) * T.lda + i]));
     }
-    expo[i] = tc_exponent(m);
+    if (e != TC_EXP_NONE) atomicMax(T.ea + i, e);
+}
+
+// grid (k blocks max, n tiles max, tasks), block 256: thread = (k chunk = tid >> 6, column = tid & 63), 16 consecutive k
+__global__ void __launch_bounds__(256) tc_col_exp_kernel(const TcTask* __restrict__ tasks) {
+    const TcTask T = tasks[blockIdx.z];
+    const int kb = blockIdx.x, j = blockIdx.y * 64 + (threadIdx.x & 63), chunk = threadIdx.x >> 6;
+    if (kb * 64 >= T.K || j >= T.N) return;
+    int e = TC_EXP_NONE;
+    const double* col = T.B + (size_t)j * T.ldb;
+    for (int q = 0; q < 16; ++q) {
+        const int k = kb * 64 + chunk * 16 + q;
+        if (k < T.K) e = max(e, tc_elem_exp(col[k]));
+    }
+    if (e != TC_EXP_NONE) atomicMax(T.eb + j, e);
 }
 
 template <int S>
@@ -143,16 +158,16 @@ __device__ __forceinline__ void tc_digits(double x, int e, int8_t (&d)[S]) {
     d[0] = (int8_t)X;                                          // what is left: |X| <= 65
 }
 
-// grid (k blocks, m tiles), block 256: one (128 x 64) block of A -> S planes of 8 KB.  Thread = (row r = tid & 127, k half);
-// every thread handles 32 k's of its row; reads are coalesced over rows.
+// grid (k blocks max, m tiles max, tasks), block 256: one (128 x 64) block of A -> S planes of 8 KB.  Thread = (row r = tid & 127,
+// k half); every thread handles 32 k's of its row; reads are coalesced over rows.
 template <int S>
-__global__ void __launch_bounds__(256) tc_slice_a_kernel(const double* __restrict__ A, int64_t lda, int M, int K,
-                                                         const int32_t* __restrict__ gather, const int32_t* __restrict__ expo,
-                                                         int8_t* __restrict__ planes, int nkb) {
-    const int kb = blockIdx.x, mt = blockIdx.y, r = threadIdx.x & 127, half = threadIdx.x >> 7;
+__global__ void __launch_bounds__(256) tc_slice_a_kernel(const TcTask* __restrict__ tasks) {
+    const TcTask T = tasks[blockIdx.z];
+    const int nkb = (T.K + 63) >> 6, kb = blockIdx.x, mt = blockIdx.y, r = threadIdx.x & 127, half = threadIdx.x >> 7;
+    if (kb >= nkb || mt * 128 >= T.M) return;
     const int i = mt * 128 + r;
-    int8_t* base = planes + ((size_t)mt * nkb + kb) * (size_t)(S * 8192);
-    const int e = (i < M) ? expo[i] : 0;
+    int8_t* base = T.Ap + ((size_t)mt * nkb + kb) * (size_t)(S * 8192);
+    const int e = (i < T.M) ? tc_line_exp(T.ea[i]) : 0;
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {                                // two 16-byte k chunks per thread
         const int chunk = half * 2 + c;
@@ -161,7 +176,7 @@ __global__ void __launch_bounds__(256) tc_slice_a_kernel(const double* __restric
         for (int q = 0; q < 16; ++q) {
             const int k = kb * 64 + chunk * 16 + q;
             double x = 0.0;
-            if (i < M && k < K) x = A[(size_t)(gather ? gather[k] : k) * lda + i];
+            if (i < T.M && k < T.K) x = T.A[(size_t)(T.gather ? T.gather[k] : k) * T.lda + i];
             int8_t d[S];
             tc_digits<S>(x, e, d);
 #pragma unroll
@@ -175,21 +190,22 @@ __global__ void __launch_bounds__(256) tc_slice_a_kernel(const double* __restric
     }
 }
 
-// grid (k blocks, n tiles), block 256: one (64 k x 64 columns) block of B -> S planes of 4 KB.  Thread = (k chunk = tid >> 6,
-// column = tid & 63): 16 consecutive k of one column (contiguous in memory: B is column-major K x N)
+// grid (k blocks max, n tiles max, tasks), block 256: one (64 k x 64 columns) block of B -> S planes of 4 KB.  Thread = (k chunk =
+// tid >> 6, column = tid & 63): 16 consecutive k of one column (contiguous in memory: B is column-major K x N)
 template <int S>
-__global__ void __launch_bounds__(256) tc_slice_b_kernel(const double* __restrict__ B, int64_t ldb, int K, int N,
-                                                         const int32_t* __restrict__ expo, int8_t* __restrict__ planes, int nkb) {
-    const int kb = blockIdx.x, nt = blockIdx.y, chunk = threadIdx.x >> 6, c = threadIdx.x & 63;
+__global__ void __launch_bounds__(256) tc_slice_b_kernel(const TcTask* __restrict__ tasks) {
+    const TcTask T = tasks[blockIdx.z];
+    const int nkb = (T.K + 63) >> 6, kb = blockIdx.x, nt = blockIdx.y, chunk = threadIdx.x >> 6, c = threadIdx.x & 63;
+    if (kb >= nkb || nt * 64 >= T.N) return;
     const int j = nt * 64 + c;
-    int8_t* base = planes + ((size_t)nt * nkb + kb) * (size_t)(S * 4096);
-    const int e = (j < N) ? expo[j] : 0;
+    int8_t* base = T.Bp + ((size_t)nt * nkb + kb) * (size_t)(S * 4096);
+    const int e = (j < T.N) ? tc_line_exp(T.eb[j]) : 0;
     __align__(16) int8_t dig[S][16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
         const int k = kb * 64 + chunk * 16 + q;
         double x = 0.0;
-        if (j < N && k < K) x = B[(size_t)j * ldb + k];
+        if (j < T.N && k < T.K) x = T.B[(size_t)j * T.ldb + k];
         int8_t d[S];
         tc_digits<S>(x, e, d);
 #pragma unroll
@@ -202,6 +218,29 @@ __global__ void __launch_bounds__(256) tc_slice_b_kernel(const double* __restric
     }
 }
 
+// tile prefix sums of the task list (one CTA; tasks[ntasks].tile0 = total).  Called after the tasks' sizes are final.
+__global__ void __launch_bounds__(256) tc_tile_scan_kernel(TcTask* __restrict__ tasks, int ntasks) {
+    __shared__ int s[256];
+    const int tid = threadIdx.x, per = (ntasks + 255) / 256;
+    const int b = min(ntasks, tid * per), e = min(ntasks, b + per);
+    int acc = 0;
+    for (int t = b; t < e; ++t) acc += ((tasks[t].M + 127) >> 7) * ((tasks[t].N + 63) >> 6);
+    s[tid] = acc;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        const int x = (tid >= o) ? s[tid - o] : 0;
+        __syncthreads();
+        s[tid] += x;
+        __syncthreads();
+    }
+    int run = s[tid] - acc;
+    for (int t = b; t < e; ++t) {
+        tasks[t].tile0 = run;
+        run += ((tasks[t].M + 127) >> 7) * ((tasks[t].N + 63) >> 6);
+    }
+    if (tid == 255) tasks[ntasks].tile0 = s[255];
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // the GEMM
 // ---------------------------------------------------------------------------------------------------------------------
@@ -211,8 +250,19 @@ template <int S> struct TcSmem {
     static constexpr int TOTAL = TC_STAGES * STAGE + 1024;      // + barriers / tmem pointer (and alignment slack)
 };
 
+struct TcTile { int task, mt, nt, nkb; };
+__device__ __forceinline__ TcTile tc_find_tile(const TcTask* __restrict__ tasks, int ntasks, int tile) {
+    int lo = 0, hi = ntasks - 1;                                // last task with tile0 <= tile (empty tasks share their successor's tile0)
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tasks[mid].tile0 <= tile) lo = mid; else hi = mid - 1; }
+    TcTile r;
+    r.task = lo;
+    const int local = tile - tasks[lo].tile0, mtiles = (tasks[lo].M + 127) >> 7;
+    r.mt = local % mtiles; r.nt = local / mtiles; r.nkb = (tasks[lo].K + 63) >> 6;
+    return r;
+}
+
 template <int S>
-__global__ void __launch_bounds__(192, 1) tc_gemm_kernel(TcGemmParams P) {
+__global__ void __launch_bounds__(192, 1) tc_gemm_kernel(const TcTask* __restrict__ tasks, int ntasks) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     using SM = TcSmem<S>;
     uint8_t* stage0 = tc_smem;
@@ -223,7 +273,7 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_kernel(TcGemmParams P) {
     uint64_t* acc_empty = acc_full + 1;           // the epilogue has read them
     uint32_t* tmem_ptr = (uint32_t*)(acc_empty + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mtiles = (P.M + 127) >> 7, ntiles = (P.N + 63) >> 6, nkb = (P.K + 63) >> 6, total = mtiles * ntiles;
+    const int total = tasks[ntasks].tile0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -242,14 +292,16 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_kernel(TcGemmParams P) {
         if (lane == 0) {
             int it = 0;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const int mt = tile % mtiles, nt = tile / mtiles;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const TcTile tl = tc_find_tile(tasks, ntasks, tile);
+                const int8_t* Ap = tasks[tl.task].Ap + (size_t)tl.mt * tl.nkb * SM::A_BYTES;
+                const int8_t* Bp = tasks[tl.task].Bp + (size_t)tl.nt * tl.nkb * SM::B_BYTES;
+                for (int kb = 0; kb < tl.nkb; ++kb, ++it) {
                     const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
                     mbar_wait(empty + s, ph ^ 1);
                     uint8_t* sa = stage0 + (size_t)s * SM::STAGE;
                     mbar_expect_tx(full + s, SM::STAGE);
-                    bulk_g2s(sa, P.Ap + ((size_t)mt * nkb + kb) * SM::A_BYTES, SM::A_BYTES, full + s);
-                    bulk_g2s(sa + SM::A_BYTES, P.Bp + ((size_t)nt * nkb + kb) * SM::B_BYTES, SM::B_BYTES, full + s);
+                    bulk_g2s(sa, Ap + (size_t)kb * SM::A_BYTES, SM::A_BYTES, full + s);
+                    bulk_g2s(sa + SM::A_BYTES, Bp + (size_t)kb * SM::B_BYTES, SM::B_BYTES, full + s);
                 }
             }
         }
@@ -259,6 +311,7 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_kernel(TcGemmParams P) {
             constexpr uint32_t idesc = umma_idesc_i8(128, 64);
             int it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
+                const int nkb = tc_find_tile(tasks, ntasks, tile).nkb;
                 mbar_wait(acc_empty, (tcount & 1) ^ 1);
                 tc_fence_after();
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -288,11 +341,13 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_kernel(TcGemmParams P) {
         const int quad = warp & 3, row = quad * 32 + lane;
         int tcount = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
-            const int mt = tile % mtiles, nt = tile / mtiles;
-            const int i = mt * 128 + row;
+            const TcTile tl = tc_find_tile(tasks, ntasks, tile);
+            const TcTask T = tasks[tl.task];
+            const int i = tl.mt * 128 + row;
             mbar_wait(acc_full, tcount & 1);
             tc_fence_after();
-            const double rs = (i < P.M) ? ldexp(1.0, P.ea[i] - 7 - 7 * S) : 0.0;      // 2^(e_i - P) 128^(S-1) ... see below
+            // C_ij = 2^(e_i + f_j - 2P) 128^(2S-2) sum_g G_g 128^-g,  P = 7S:  2^(e_i + f_j - 14) per unit of the Horner sum
+            const double rs = (i < T.M) ? ldexp(1.0, tc_line_exp(T.ea[i]) - 7 - 7 * S) : 0.0;
             for (int c0 = 0; c0 < 64; c0 += 16) {
                 double acc[16];
 #pragma unroll
@@ -305,15 +360,14 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_kernel(TcGemmParams P) {
 #pragma unroll
                     for (int q = 0; q < 16; ++q) acc[q] = fma(acc[q], 0.0078125, (double)(int)v[q]);
                 }
-                // C_ij = 2^(e_i + f_j - 2P) 128^(2S-2) sum_g G_g 128^-g   with P = 7S:  2^(e_i + f_j - 14) per unit of acc
-                if (i < P.M) {
+                if (i < T.M) {
 #pragma unroll
                     for (int q = 0; q < 16; ++q) {
-                        const int j = nt * 64 + c0 + q;
-                        if (j < P.N) {
-                            const double val = acc[q] * rs * ldexp(1.0, P.eb[j] - 7 + 7 * S);
-                            const int jo = P.scatter ? P.scatter[j] : j;
-                            P.C[(size_t)jo * P.ldc + i] = val;
+                        const int j = tl.nt * 64 + c0 + q;
+                        if (j < T.N) {
+                            const double val = (tl.nkb > 0) ? acc[q] * rs * ldexp(1.0, tc_line_exp(T.eb[j]) - 7 + 7 * S) : 0.0;
+                            const int jo = T.scatter ? T.scatter[j] : j;
+                            T.C[(size_t)jo * T.ldc + i] = val;
                         }
                     }
                 }
@@ -334,45 +388,46 @@ size_t tc_gemm_plane_bytes_a(int M, int K, int S) { return (size_t)((M + 127) / 
 size_t tc_gemm_plane_bytes_b(int K, int N, int S) { return (size_t)((N + 63) / 64) * ((K + 63) / 64) * S * 4096; }
 
 template <int S>
-static cudaError_t tc_slice_run(const TcGemmArgs& a, cudaStream_t st) {
-    const int nkb = (a.K + 63) / 64, mt = (a.M + 127) / 128, nt = (a.N + 63) / 64;
-    tc_row_exp_kernel<<<(a.M + 255) / 256, 256, 0, st>>>(a.A, a.lda, a.M, a.K, a.gather, a.ea);
-    tc_line_exp_kernel<<<a.N, 256, 0, st>>>(a.B, a.ldb, a.N, a.K, 0, nullptr, a.eb);
-    tc_slice_a_kernel<S><<<dim3(nkb, mt), 256, 0, st>>>(a.A, a.lda, a.M, a.K, a.gather, a.ea, a.Ap, nkb);
-    tc_slice_b_kernel<S><<<dim3(nkb, nt), 256, 0, st>>>(a.B, a.ldb, a.K, a.N, a.eb, a.Bp, nkb);
+static cudaError_t tc_slice_run(const TcBatch& b, cudaStream_t st) {
+    const int nkb = (b.Kmax + 63) / 64, mt = (b.Mmax + 127) / 128, nt = (b.Nmax + 63) / 64;
+    tc_exp_init_kernel<<<dim3((b.Mmax + b.Nmax + 255) / 256, 1, b.ntasks), 256, 0, st>>>(b.tasks);
+    tc_row_exp_kernel<<<dim3(nkb, mt, b.ntasks), 256, 0, st>>>(b.tasks);
+    tc_col_exp_kernel<<<dim3(nkb, nt, b.ntasks), 256, 0, st>>>(b.tasks);
+    tc_slice_a_kernel<S><<<dim3(nkb, mt, b.ntasks), 256, 0, st>>>(b.tasks);
+    tc_slice_b_kernel<S><<<dim3(nkb, nt, b.ntasks), 256, 0, st>>>(b.tasks);
     return cudaGetLastError();
 }
 
 template <int S>
-static cudaError_t tc_mma_run(const TcGemmArgs& a, cudaStream_t st, int sms) {
-    const int mt = (a.M + 127) / 128, nt = (a.N + 63) / 64;
-    TcGemmParams P;
-    P.Ap = a.Ap; P.Bp = a.Bp; P.ea = a.ea; P.eb = a.eb; P.C = a.C; P.ldc = a.ldc; P.scatter = a.scatter; P.M = a.M; P.N = a.N; P.K = a.K;
+static cudaError_t tc_mma_run(const TcBatch& b, cudaStream_t st, int sms) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<S>::TOTAL);
     if (e != cudaSuccess) return e;
-    const int grid = std::min(sms, mt * nt);
-    tc_gemm_kernel<S><<<grid, 192, TcSmem<S>::TOTAL, st>>>(P);
+    tc_tile_scan_kernel<<<1, 256, 0, st>>>(b.tasks, b.ntasks);
+    const int64_t bound = (int64_t)b.ntasks * ((b.Mmax + 127) / 128) * ((b.Nmax + 63) / 64);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sms, bound));
+    tc_gemm_kernel<S><<<grid, 192, TcSmem<S>::TOTAL, st>>>(b.tasks, b.ntasks);
     return cudaGetLastError();
 }
 
-cudaError_t tc_gemm_slice_only(const TcGemmArgs& a, cudaStream_t st) {
-    switch (a.S) {
-        case 6: return tc_slice_run<6>(a, st);
-        case 7: return tc_slice_run<7>(a, st);
-        case 8: return tc_slice_run<8>(a, st);
+cudaError_t tc_gemm_slice(const TcBatch& b, cudaStream_t st) {
+    if (b.ntasks <= 0 || b.Mmax <= 0 || b.Nmax <= 0 || b.Kmax <= 0) return cudaSuccess;
+    switch (b.S) {
+        case 6: return tc_slice_run<6>(b, st);
+        case 7: return tc_slice_run<7>(b, st);
+        case 8: return tc_slice_run<8>(b, st);
         default: return cudaErrorInvalidValue;
     }
 }
-cudaError_t tc_gemm_mma_only(const TcGemmArgs& a, cudaStream_t st, int sms) {
-    switch (a.S) {
-        case 6: return tc_mma_run<6>(a, st, sms);
-        case 7: return tc_mma_run<7>(a, st, sms);
-        case 8: return tc_mma_run<8>(a, st, sms);
+cudaError_t tc_gemm_mma(const TcBatch& b, cudaStream_t st, int sms) {
+    if (b.ntasks <= 0 || b.Mmax <= 0 || b.Nmax <= 0 || b.Kmax <= 0) return cudaSuccess;
+    switch (b.S) {
+        case 6: return tc_mma_run<6>(b, st, sms);
+        case 7: return tc_mma_run<7>(b, st, sms);
+        case 8: return tc_mma_run<8>(b, st, sms);
         default: return cudaErrorInvalidValue;
     }
 }
-cudaError_t tc_gemm_fp64(const TcGemmArgs& a, cudaStream_t st, int sms) {
-    if (a.M <= 0 || a.N <= 0 || a.K <= 0) return cudaSuccess;
-    cudaError_t e = tc_gemm_slice_only(a, st);
-    return e != cudaSuccess ? e : tc_gemm_mma_only(a, st, sms);
+cudaError_t tc_gemm_batch(const TcBatch& b, cudaStream_t st, int sms) {
+    cudaError_t e = tc_gemm_slice(b, st);
+    return e != cudaSuccess ? e : tc_gemm_mma(b, st, sms);
 }

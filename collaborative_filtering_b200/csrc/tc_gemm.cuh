@@ -3,28 +3,27 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-struct TcGemmParams {            // device-side view
-    const int8_t* Ap; const int8_t* Bp;     // slice planes (tc_gemm.cu: "slicing")
-    const int32_t* ea; const int32_t* eb;   // row exponents of A, column exponents of B
-    double* C; int64_t ldc;                 // column-major M x N
-    const int32_t* scatter;                 // optional: column j of the product goes to column scatter[j] of C
-    int M, N, K;
+// One product C[:, scatter[j]] = A[:, gather[0..K)] * B[0..K, j], all column-major FP64.  The list lives in DEVICE memory: M, N, K
+// (and the pointers) may be written by a kernel earlier in the stream -- the divide-and-conquer fills them from its deflation
+// counts.  The array has ntasks + 1 entries; tile0 is filled by the engine (prefix sum of the tiles, total in the last entry).
+struct TcTask {
+    const double* A; const double* B; double* C;
+    const int32_t* gather;                  // optional [K]: column of A that is the k-th column of the product's left operand
+    const int32_t* scatter;                 // optional [N]: column of C that receives column j of the product
+    int64_t lda, ldb, ldc;
+    int8_t* Ap; int8_t* Bp;                 // slice planes, sized by tc_gemm_plane_bytes_a / _b of the task's UPPER bounds
+    int32_t* ea; int32_t* eb;               // row exponents of A [M], column exponents of B [N]
+    int M, N, K, tile0;
 };
 
-struct TcGemmArgs {              // C[:, scatter[j]] = A[:, gather[0..K)] * B[0..K, j], all column-major FP64
-    const double* A; int64_t lda;           // M x (>= max gather) ; element (i, k) = A[gather[k] * lda + i]
-    const double* B; int64_t ldb;           // K x N
-    double* C; int64_t ldc;
-    const int32_t* gather;                  // optional [K]
-    const int32_t* scatter;                 // optional [N]
-    int M, N, K, S;                         // S = slices per operand (6, 7 or 8: 42 / 49 / 56 bit fixed point)
-    int8_t* Ap; int8_t* Bp;                 // workspaces: tc_gemm_plane_bytes_a / _b
-    int32_t* ea; int32_t* eb;               // workspaces: M and N ints
+struct TcBatch {
+    TcTask* tasks; int ntasks;              // device pointer
+    int Mmax, Nmax, Kmax;                   // host-side upper bounds over the tasks (grid sizes)
+    int S;                                  // slices per operand entry: 6, 7 or 8 digits of 7 bits
 };
 
 size_t tc_gemm_plane_bytes_a(int M, int K, int S);
 size_t tc_gemm_plane_bytes_b(int K, int N, int S);
-// enqueues exponent scan, slicing and the GEMM on `st`; sms = CTAs of the persistent GEMM kernel
-cudaError_t tc_gemm_fp64(const TcGemmArgs& a, cudaStream_t st, int sms);
-cudaError_t tc_gemm_slice_only(const TcGemmArgs& a, cudaStream_t st);            // the two halves, for separate timing
-cudaError_t tc_gemm_mma_only(const TcGemmArgs& a, cudaStream_t st, int sms);
+cudaError_t tc_gemm_batch(const TcBatch& b, cudaStream_t st, int sms);   // exponent scan + slicing + GEMM, enqueued on `st`
+cudaError_t tc_gemm_slice(const TcBatch& b, cudaStream_t st);            // the two halves, for separate timing
+cudaError_t tc_gemm_mma(const TcBatch& b, cudaStream_t st, int sms);     // sms = CTAs of the persistent kernel

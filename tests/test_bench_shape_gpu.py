@@ -71,6 +71,31 @@ def test_user_above_9216(ctx, weights):
     assert s["ok"]
 
 
+@pytest.mark.skipif(not __import__("os").environ.get("GSI_TEST_NETFLIX_MAX"), reason="minutes of LAPACK on the host: set GSI_TEST_NETFLIX_MAX=1")
+def test_user_at_the_netflix_maximum():
+    """BASELINE.json configs[3]: the heaviest Netflix-shaped user rates 17,653 of 17,770 movies.  One such user (plus filler)
+    through gsi_precompute_host: sig_min bit-exact, k exact, |d lam| <= 1e-10, residual / orthonormality <= 1e-9."""
+    from collaborative_filtering_b200 import datasets as D
+    from collaborative_filtering_b200.api import Context
+    n_items = 17770
+    w = D.make_weights(n_items)
+    c = Context(0)
+    try:
+        c.set_workspace_limit(64 << 30)
+        c.set_weights(w)
+        rng = np.random.default_rng(13)
+        sizes = [17653, 400, 30]
+        offsets = np.zeros(len(sizes) + 1, dtype=np.int64)
+        np.cumsum(sizes, out=offsets[1:])
+        items = np.concatenate([np.sort(rng.choice(n_items, size=n, replace=False) + 1) for n in sizes]).astype(np.int32)
+        recs = c.precompute(offsets, items)
+        s = _check(recs, w, [0, 1, 2])
+        assert s["ok"] and s["sig_min_bit_exact"] and s["k_exact"], s
+        print("netflix-max user:", s)
+    finally:
+        c.close()
+
+
 def test_records_do_not_depend_on_the_batch(ctx, weights):
     """SURVEY.md section 7 test (h) on one device: the records of a user are bit-identical whether it is solved alone,
     in the whole batch, or in either half of a 2-way LPT shard (what a 2-GPU run computes per rank)."""
