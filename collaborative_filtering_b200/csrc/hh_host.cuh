@@ -292,6 +292,80 @@ static int hh_trd(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_tea
     return GSI_OK;
 }
 
+// ---- tensor-core merges: host plan ---------------------------------------------------------------------------------------
+struct HhTcBatch { int level, first, ntasks, Mmax, Nmax, Kmax; };
+struct HhTcPlan {
+    std::vector<HhTcBatch> batches;
+    const uint8_t* d_flags = nullptr; const DcTcTask* d_tasks = nullptr; TcTask* d_tc = nullptr;
+    int8_t* d_planes = nullptr; int32_t* d_expo = nullptr;
+    int S = 8;
+};
+// merged size from which a node's GEMMs go to the tcgen05 engine (GSI_TC_MIN; 0 = never).  Below ~2,000 the slicing passes and
+// the tile quantisation (128 x 64 tiles, one CTA per SM) cost more than the engine saves over the DMMA kernel.
+static int hh_tc_min() { const char* e = getenv("GSI_TC_MIN"); return e ? atoi(e) : 2048; }
+
+static int hh_tc_plan(gsi_ctx* ctx, const HhPlan& pl, HhTcPlan& TC) {
+    Workspace& ws = WS(ctx);
+    const int tc_min = hh_tc_min();
+    if (const char* e = getenv("GSI_TC_SLICES")) TC.S = std::min(8, std::max(6, atoi(e)));
+    if (tc_min <= 0 || pl.nodes.empty()) return GSI_OK;
+    const int64_t budget = std::min<int64_t>((int64_t)8 << 30, std::max<int64_t>(ctx->ws_limit / 8, (int64_t)256 << 20));
+    std::vector<uint8_t> flags(pl.nodes.size(), 0);
+    std::vector<DcTcTask> tasks;
+    int64_t planes_max = 0, expo_max = 0;
+    int ntasks_max = 0;
+    for (int l = 1; l <= pl.Lmax; ++l) {
+        HhTcBatch cur{l, (int)tasks.size(), 0, 0, 0, 0};
+        int64_t used = 0, eused = 0;
+        auto flush = [&]() {
+            if (cur.ntasks > 0) {
+                TC.batches.push_back(cur);
+                planes_max = std::max(planes_max, used); expo_max = std::max(expo_max, eused); ntasks_max = std::max(ntasks_max, cur.ntasks);
+            }
+            cur = HhTcBatch{l, (int)tasks.size(), 0, 0, 0, 0};
+            used = 0; eused = 0;
+        };
+        for (int nd = pl.lvl_begin[l]; nd < pl.lvl_begin[l + 1]; ++nd) {
+            const DcNode& N = pl.nodes[nd];
+            const int m = N.n1 + N.n2;
+            if (m < tc_min) continue;
+            int64_t need = 0;
+            for (int h = 0; h < 2; ++h)
+                need += (int64_t)tc_gemm_plane_bytes_a(h ? N.n2 : N.n1, m, TC.S) + (int64_t)tc_gemm_plane_bytes_b(m, m, TC.S);
+            if (need > budget) continue;                                    // stays on the DMMA kernel
+            if (used + need > budget) flush();
+            flags[nd] = 1;
+            for (int h = 0; h < 2; ++h) {
+                const int M = h ? N.n2 : N.n1;
+                DcTcTask t;
+                t.node = nd; t.bottom = h; t.ap_off = used; used += (int64_t)tc_gemm_plane_bytes_a(M, m, TC.S);
+                t.bp_off = used; used += (int64_t)tc_gemm_plane_bytes_b(m, m, TC.S);
+                t.e_off = eused; eused += M + m;
+                tasks.push_back(t);
+                ++cur.ntasks;
+                cur.Mmax = std::max(cur.Mmax, M); cur.Nmax = std::max(cur.Nmax, m); cur.Kmax = std::max(cur.Kmax, m);
+            }
+        }
+        flush();
+    }
+    if (tasks.empty()) return GSI_OK;
+    int rc;
+    MetaBuilder mb;
+    const size_t o_f = mb.add(flags), o_t = mb.add(tasks);
+    if ((rc = ws.tc_meta.ensure(ctx, mb.host.size())) != GSI_OK) return rc;
+    if ((rc = ws.tc_tasks.ensure(ctx, (size_t)(ntasks_max + 1) * sizeof(TcTask))) != GSI_OK) return rc;
+    if ((rc = ws.tc_planes.ensure(ctx, (size_t)planes_max)) != GSI_OK) return rc;
+    if ((rc = ws.tc_expo.ensure(ctx, (size_t)expo_max * 4)) != GSI_OK) return rc;
+    GSI_CUDA(ctx, cudaMemcpyAsync(ws.tc_meta.p, mb.host.data(), mb.host.size(), cudaMemcpyHostToDevice, ctx->stream));
+    GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));                       // mb.host is a local
+    TC.d_flags = (const uint8_t*)(ws.tc_meta.as<char>() + o_f);
+    TC.d_tasks = (const DcTcTask*)(ws.tc_meta.as<char>() + o_t);
+    TC.d_tc = ws.tc_tasks.as<TcTask>(); TC.d_planes = ws.tc_planes.as<int8_t>(); TC.d_expo = ws.tc_expo.as<int32_t>();
+    if (ctx->trace) fprintf(stderr, "[gsi trace] tcgen05 merges: %zu tasks in %zu batches, planes %.2f GB, %d slices, nodes >= %d\n", tasks.size(),
+                            TC.batches.size(), planes_max / 1073741824.0, TC.S, tc_min);
+    return GSI_OK;
+}
+
 static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_team, bool defer_bt_apply = false) {
     cudaStream_t st = ctx->stream;
     const int nj = pl.nj;
@@ -314,6 +388,11 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
     }
     const size_t gemm_smem = (size_t)DCG_STAGES * DCG_STAGE_DBL * sizeof(double);
     GSI_CUDA(ctx, cudaFuncSetAttribute(dc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
+    // ---- big merges on the tcgen05 engine (tc_gemm.cu): planned here from the node sizes (upper bounds), in sub-batches that fit
+    // the plane budget; everything is uploaded once, the level loop only launches
+    HhTcPlan TC;
+    if ((rc = hh_tc_plan(ctx, pl, TC)) != GSI_OK) return rc;
+    P.tc_node = TC.d_flags;
     for (int l = 1; l <= pl.Lmax; ++l) {
         P.node0 = pl.lvl_begin[l]; P.nnodes = pl.lvl_begin[l + 1] - pl.lvl_begin[l]; P.in_b = (l - 1) & 1;
         const int mmax = pl.lvl_mmax[l];
@@ -342,6 +421,15 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
         {
             GsiSpan sp(ctx, GSI_T_DC_GEMM, 2);
             { HhTrace tr(ctx, "  gemm"); dc_gemm_kernel<<<2 * ctx->sm_count, 256, gemm_smem, st>>>(P, D.tile_off); }
+            for (const HhTcBatch& tb : TC.batches) {
+                if (tb.level != l) continue;
+                HhTrace tr(ctx, "  gemm (tcgen05 batch)");
+                dc_tc_resolve_kernel<<<(tb.ntasks + 1 + 127) / 128, 128, 0, st>>>(P, TC.d_tasks + tb.first, tb.ntasks, TC.d_planes, TC.d_expo, TC.d_tc);
+                TcBatch B;
+                B.tasks = TC.d_tc; B.ntasks = tb.ntasks; B.Mmax = tb.Mmax; B.Nmax = tb.Nmax; B.Kmax = tb.Kmax; B.S = TC.S;
+                GSI_CUDA(ctx, tc_gemm_batch(B, st, ctx->sm_count));
+                gsi_count_launch(ctx, GSI_T_DC_GEMM, 9);
+            }
             { HhTrace tr(ctx, "  copy"); dc_copy_kernel<<<dim3(P.nnodes, (mmax + 7) / 8), 256, 0, st>>>(P); }
             sp.end();
         }

@@ -20,6 +20,7 @@
 #include "gsi_internal.cuh"
 #include "kern_trd.cuh"
 #include "ptx.cuh"
+#include "tc_gemm.cuh"
 
 #define DC_LEAF 32
 #define DC_EPS 1.1102230246251565e-16     // 2^-53 (LAPACK dlamch('E'))
@@ -44,7 +45,11 @@ struct DcParams {
     // cutoff
     const unsigned int* sigmax;   // [jobs] float bits of max_i ||row_i||
     int32_t* kuser;               // [jobs] kept eigenpairs (written by the final merge)
+    const uint8_t* tc_node;       // optional [all nodes]: 1 = the merge GEMMs of this node run on the tcgen05 engine (tc_gemm.cu)
 };
+
+// merge GEMM of a node half on the tensor-core engine: planned on the host (upper bounds), resolved on the device (deflation counts)
+struct DcTcTask { int node, bottom; int64_t ap_off, bp_off, e_off; };
 
 // ---------------------------------------------------------------------------------------------
 // leaves
@@ -505,7 +510,7 @@ __global__ void __launch_bounds__(1024) dc_plan_kernel(DcParams P, int32_t* __re
         const DcNode nd = P.nodes[P.node0 + (t >> 1)];
         const DcState st = P.state[P.node0 + (t >> 1)];
         const int M = (t & 1) ? nd.n2 : nd.n1, N = st.kneed;
-        acc += ((M + DCG_BM - 1) / DCG_BM) * ((N + DCG_BN - 1) / DCG_BN);
+        if (!(P.tc_node && P.tc_node[P.node0 + (t >> 1)])) acc += ((M + DCG_BM - 1) / DCG_BM) * ((N + DCG_BN - 1) / DCG_BN);
     }
     s[tid] = acc;
     __syncthreads();
@@ -522,9 +527,37 @@ __global__ void __launch_bounds__(1024) dc_plan_kernel(DcParams P, int32_t* __re
         const DcNode nd = P.nodes[P.node0 + (t >> 1)];
         const DcState st = P.state[P.node0 + (t >> 1)];
         const int M = (t & 1) ? nd.n2 : nd.n1, N = st.kneed;
-        run += ((M + DCG_BM - 1) / DCG_BM) * ((N + DCG_BN - 1) / DCG_BN);
+        if (!(P.tc_node && P.tc_node[P.node0 + (t >> 1)])) run += ((M + DCG_BM - 1) / DCG_BM) * ((N + DCG_BN - 1) / DCG_BN);
     }
     if (tid == 1023) tile_off[ntask] = s[1023];
+}
+
+// The same product as dc_gemm_kernel below, described for the tcgen05 engine: Qout[rows, pos_nd[j]] = Qin[rows, colsrc[kb .. ke)] *
+// S[kb .. ke, j], j < kneed.  One thread per task; entry `nt` is the engine's sentinel.
+__global__ void dc_tc_resolve_kernel(DcParams P, const DcTcTask* __restrict__ ht, int nt, int8_t* __restrict__ planes,
+                                     int32_t* __restrict__ expo, TcTask* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > nt) return;
+    TcTask T;
+    memset(&T, 0, sizeof T);
+    if (t < nt) {
+        const DcTcTask h = ht[t];
+        const DcNode nd = P.nodes[h.node];
+        const DcState st = P.state[h.node];
+        const HJob jb = P.jobs[nd.job];
+        const bool bottom = h.bottom != 0;
+        const int M = bottom ? nd.n2 : nd.n1;
+        const int kb = bottom ? st.k1 : 0, ke = bottom ? st.k : st.k1 + st.k2;
+        const int rowbeg = bottom ? nd.n1 : 0, ld = jb.np;
+        const size_t vb = (size_t)jb.r_off + nd.off;
+        const size_t blk = (size_t)jb.m_off + (size_t)nd.off * ld + nd.off;
+        T.A = (P.in_b ? P.Qb : P.Qa) + blk + rowbeg; T.lda = ld; T.gather = P.colsrc + vb + kb;
+        T.B = P.S + blk + kb; T.ldb = ld;
+        T.C = (P.in_b ? P.Qa : P.Qb) + blk + rowbeg; T.ldc = ld; T.scatter = P.pos_nd + vb;
+        T.M = M; T.N = st.kneed; T.K = max(ke - kb, 0);
+        T.Ap = planes + h.ap_off; T.Bp = planes + h.bp_off; T.ea = expo + h.e_off; T.eb = T.ea + M;
+    }
+    out[t] = T;
 }
 
 __global__ void __launch_bounds__(256, 2) dc_gemm_kernel(DcParams P, const int32_t* __restrict__ tile_off) {
