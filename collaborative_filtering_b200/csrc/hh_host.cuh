@@ -419,7 +419,9 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
             sp.end();
         }
         {
-            GsiSpan sp(ctx, GSI_T_DC_GEMM, 2);
+            int ntcb = 0;
+            for (const HhTcBatch& tb : TC.batches) ntcb += (tb.level == l);
+            GsiSpan sp(ctx, GSI_T_DC_GEMM, 2 + 8 * ntcb);          // per tcgen05 batch: resolve, 5 slicing kernels, tile scan, GEMM
             { HhTrace tr(ctx, "  gemm"); dc_gemm_kernel<<<2 * ctx->sm_count, 256, gemm_smem, st>>>(P, D.tile_off); }
             for (const HhTcBatch& tb : TC.batches) {
                 if (tb.level != l) continue;
@@ -428,7 +430,6 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
                 TcBatch B;
                 B.tasks = TC.d_tc; B.ntasks = tb.ntasks; B.Mmax = tb.Mmax; B.Nmax = tb.Nmax; B.Kmax = tb.Kmax; B.S = TC.S;
                 GSI_CUDA(ctx, tc_gemm_batch(B, st, ctx->sm_count));
-                gsi_count_launch(ctx, GSI_T_DC_GEMM, 9);
             }
             { HhTrace tr(ctx, "  copy"); dc_copy_kernel<<<dim3(P.nnodes, (mmax + 7) / 8), 256, 0, st>>>(P); }
             sp.end();
