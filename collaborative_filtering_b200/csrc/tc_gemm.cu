@@ -10,8 +10,11 @@
 //             a (128 x 64) A block or a (64 x 64) B block into shared memory.
 //   product   A_ik B_kj = 2^(e_i + f_j - 2P) sum_{t,u} d_t(ik) g_u(kj) 128^(2S-2-t-u).  The slice pairs with t + u = g share a
 //             weight, so they accumulate -- exactly, in INT32 -- into ONE tensor-memory accumulator per g: S accumulators of
-//             128 lanes x 64 columns fill the 512 columns of tensor memory, one pass over K, S (S + 1) / 2 MMAs per K step of 32
-//             (pairs with t + u >= S are below the rounding of X and are dropped).
+//             128 lanes x 64 columns fill the 512 columns of tensor memory, one pass over K, S (S + 1) / 2 slice products per K
+//             step of 32 (pairs with t + u >= S are below the rounding of X and are dropped).  The products of one A slice t
+//             with its partners u = 0 .. S-1-t land in CONSECUTIVE accumulators, so they are issued as one MMA of
+//             N = 64 (S - t) columns (cut at 256): 12 instructions per K step for S = 8 instead of 36, and a third of the
+//             shared-memory reads of the A block.
 //   epilogue  four warps read the S accumulators of their rows (tcgen05.ld), combine them by Horner in FP64
 //             (acc = acc / 128 + G_g, exact conversions), scale by the row and column factors and write C.
 //
@@ -83,7 +86,9 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(int M, int N) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // slicing.  Plane storage (bytes):  A: [m tile][k block][slice][k chunk (4)][row group (16)][8 rows][16 k]   8 KB per slice
-//                                   B: [n tile][k block][slice][k chunk (4)][col group ( 8)][8 cols][16 k]   4 KB per slice
+//                                   B: [n tile][k block][k chunk (4)][slice][col group ( 8)][8 cols][16 k]   4 KB per slice
+//   (B: the slices of one k chunk are adjacent, so that 8-column groups of consecutive slices are 128 bytes apart: one MMA descriptor
+//    spans several slices, see the issue loop)
 // ---------------------------------------------------------------------------------------------------------------------
 // exponent e with |x| 2^-e < 1/2 for every x of the line (max |x| = 0 -> e = 0)
 __device__ __forceinline__ int tc_exponent(double amax) {
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(256) tc_slice_b_kernel(const TcTask* __restric
     }
 #pragma unroll
     for (int t = 0; t < S; ++t) {
-        int8_t* dst = base + (size_t)t * 4096 + chunk * 1024 + (c >> 3) * 128 + (c & 7) * 16;
+        int8_t* dst = base + (size_t)chunk * (S * 1024) + t * 1024 + (c >> 3) * 128 + (c & 7) * 16;
         *(int4*)dst = *(const int4*)dig[t];
     }
 }
@@ -308,7 +313,6 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_kernel(const TcTask* __restric
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_i8(128, 64);
             int it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
                 const int nkb = tc_find_tile(tasks, ntasks, tile).nkb;
@@ -319,15 +323,20 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_kernel(const TcTask* __restric
                     mbar_wait(full + s, ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(stage0 + (size_t)s * SM::STAGE), sb = sa + SM::A_BYTES;
+                    // For a fixed A slice t the partners u = 0 .. S-1-t write the accumulators t .. S-1: CONSECUTIVE column blocks of
+                    // tensor memory, and the B planes of one k chunk are stored slice after slice -- so the S - t products are ONE
+                    // MMA of N = 64 (S - t) columns (cut at the instruction's limit of 256): the A block is read from shared memory
+                    // 12 times per K step instead of 36 (S = 8), which takes the operand reads off the shared-memory roofline.
 #pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {             // two MMAs of K = 32 per 64-byte k block
+                    for (int kk = 0; kk < 2; ++kk) {             // two K steps of 32 per 64-byte k block
 #pragma unroll
                         for (int t = 0; t < S; ++t) {
                             const uint64_t ad = umma_desc(sa + t * 8192 + kk * 4096, 2048, 128);
 #pragma unroll
-                            for (int u = 0; u + t < S; ++u) {
-                                const uint64_t bd = umma_desc(sb + u * 4096 + kk * 2048, 1024, 128);
-                                umma_i8(tmem + (uint32_t)(64 * (t + u)), ad, bd, idesc, (kb > 0 || kk > 0 || t > 0) ? 1u : 0u);
+                            for (int c0 = 0; c0 < 64 * (S - t); c0 += 256) {
+                                const int ncols = (64 * (S - t) - c0) < 256 ? (64 * (S - t) - c0) : 256;
+                                const uint64_t bd = umma_desc(sb + kk * (2 * S * 1024) + (c0 >> 3) * 128, S * 1024, 128);
+                                umma_i8(tmem + (uint32_t)(64 * t + c0), ad, bd, umma_idesc_i8(128, ncols), (kb > 0 || kk > 0 || t > 0) ? 1u : 0u);
                             }
                         }
                     }
