@@ -347,6 +347,7 @@ def predict_fold(local_rank, rank=0, world=1, shape="ml-1m", fold=0, oracle_pair
             # ---- RMSE delta: the oracle's predictor (numpy restatement of local_calc_precomp.cpp:217-380) on the SAME records
             # (stage-wise protocol) over a seeded sample of this rank's pairs from users with n <= nmax_oracle
             from oracle import gsi_oracle as O
+            _all_host_threads()
             graph = O.item_graph([(int(x), int(y), float(z)) for x, y, z in zip(a, b, w)])
             rng = np.random.default_rng(D.SEED + 7)
             deg_s = np.diff(s_off)
@@ -419,10 +420,21 @@ def bind_to_gpu_numa_node(local_rank):
     return None
 
 
+def _all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the post-timed checks (LAPACK on rank 0 only, outside every timed region)
+    would then run on one core -- 141 s instead of 22 s for the parity block at N = 2.  Give them the box's cores back."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=max(1, os.cpu_count() or 1))
+    except Exception:  # pragma: no cover
+        pass
+
+
 def parity_block(offsets, items, w_host, d_sig, d_k, d_lo, d_vo, d_lam, d_vec, n_random=20, n_largest=3):
     """after the timed region, the records of the last timed step -- the shard's largest users and a
     seeded random sample -- against the oracle (oracle/light_check.py).  The oracle is the checker here, nothing else."""
     from oracle.light_check import check_record, summarise
+    _all_host_threads()
     deg = np.diff(offsets)
     rng = np.random.default_rng(D.SEED + 5)
     largest = np.argsort(-deg, kind="stable")[:n_largest]
