@@ -23,6 +23,7 @@
 #include "kern_cheby.cuh"
 #include "kern_lc.cuh"
 #include "tc_gemm.cuh"
+#include "kern_bt_tc.cuh"
 
 static thread_local std::string g_tls_err;
 
@@ -104,7 +105,8 @@ struct PinBuf {
 struct Workspace {
     DevBuf k_off, k_items, k_rat, k_cnt, k_num, k_S, k_ecnt, k_eoff, k_ea, k_eb, k_ew, k_co, k_err, k_mcnt, k_has;
     DevBuf k_coff, k_cur, k_cuser, k_crat, k_useg;
-    DevBuf tc_meta, tc_tasks, tc_planes, tc_expo;      // tensor-core merges of the divide & conquer (hh_tc_plan)     // item-major transpose of the knn CSR (knn_row_kernel)
+    DevBuf tc_meta, tc_tasks, tc_planes, tc_expo;
+    DevBuf btt_gt, btt_x, btt_planes, btt_expo, btt_meta;   // tensor-core back-transform (hh_bt_tc)      // tensor-core merges of the divide & conquer (hh_tc_plan)     // item-major transpose of the knn CSR (knn_row_kernel)
     DevBuf c_off, c_col, c_w, c_wn, c_vec;          // Chebyshev filter: CSR, normalised weights, 5 vertex vectors
     int64_t knn_edges = 0;
     DevBuf pred_meta, pred_work, p_off, p_items, p_wlim, p_rat, p_k, p_lamoff, p_vecoff, p_lam, p_vec, p_err, p_kk, p_pred, p_status, p_cols, p_gsum, p_hsum, p_sumoff, p_exact, p_lim, p_mask;
@@ -179,7 +181,7 @@ extern "C" int gsi_destroy(gsi_ctx* c) {
                     &w.p_exact, &w.p_lim, &w.p_mask};
     for (auto b : d2) b->release();
     DevBuf* d3[] = {&w.k_off, &w.k_items, &w.k_rat, &w.k_cnt, &w.k_num, &w.k_S, &w.k_ecnt, &w.k_eoff, &w.k_ea, &w.k_eb, &w.k_ew,
-                    &w.k_co, &w.k_err, &w.k_mcnt, &w.k_has, &w.k_coff, &w.k_cur, &w.k_cuser, &w.k_crat, &w.k_useg, &w.tc_meta, &w.tc_tasks, &w.tc_planes, &w.tc_expo, &w.c_off, &w.c_col, &w.c_w, &w.c_wn, &w.c_vec};
+                    &w.k_co, &w.k_err, &w.k_mcnt, &w.k_has, &w.k_coff, &w.k_cur, &w.k_cuser, &w.k_crat, &w.k_useg, &w.tc_meta, &w.tc_tasks, &w.tc_planes, &w.tc_expo, &w.btt_gt, &w.btt_x, &w.btt_planes, &w.btt_expo, &w.btt_meta, &w.c_off, &w.c_col, &w.c_w, &w.c_wn, &w.c_vec};
     for (auto b : d3) b->release();
     DevBuf* d4[] = {&w.hhA, &w.hhQa, &w.hhQb, &w.hhS, &w.hhvec, &w.hhivec, &w.trd_acol, &w.trd_ypart, &w.trd_part, &w.trd_panels,
                     &w.sbr_panels, &w.sbr_small, &w.sbr_band, &w.sbr_v2, &w.sbr_prog, &w.sbr_list};

@@ -65,7 +65,7 @@ static void hh_build_plan(const Job* jobs, int nj, HhPlan& pl) {
 
 struct HhDev {           // device views of one chunk
     const HJob* jobs; const DcLeaf* leaves; const DcNode* nodes; const int2* bt_items;
-    DcState* state; int32_t* tile_off; unsigned int* sigmax; int32_t* kuser; int* ctl;
+    DcState* state; int32_t* tile_off; unsigned int* sigmax; int32_t* kuser; int* ctl; uint8_t* bt_skip;
     double *A, *Qa, *Qb, *S;
     double *d, *e, *tau, *lamA, *lamB, *dk, *zk, *zhat, *dctau, *lamk, *dval, *ds, *zs, *sgn, *deg, *scale, *rot;
     int32_t *orig, *gmap, *colsrc, *dsrc, *pos_nd, *pos_df, *src;
@@ -102,11 +102,12 @@ static int hh_alloc(gsi_ctx* ctx, const HhPlan& pl, const Job* jobs, HhDev& D) {
     const size_t o_tile = mb.reserve((2 * pl.nodes.size() + 2) * 4);
     const size_t o_sig = mb.reserve((size_t)nj * 4), o_ku = mb.reserve((size_t)nj * 4), o_ctl = mb.reserve(HH_CTL_INTS * 4);
     const size_t o_vd = mb.reserve((size_t)nj * 8), o_ldst = mb.reserve((size_t)nj * 8);
+    const size_t o_skip = mb.reserve((size_t)nj);
     char* base;
     if ((rc = upload_meta(ctx, mb, &base)) != GSI_OK) return rc;
     D.jobs = (const HJob*)(base + o_jobs); D.leaves = (const DcLeaf*)(base + o_leaves); D.nodes = (const DcNode*)(base + o_nodes);
     D.bt_items = (const int2*)(base + o_items); D.state = (DcState*)(base + o_state); D.tile_off = (int32_t*)(base + o_tile);
-    D.sigmax = (unsigned int*)(base + o_sig); D.kuser = (int32_t*)(base + o_ku); D.ctl = (int*)(base + o_ctl);
+    D.sigmax = (unsigned int*)(base + o_sig); D.kuser = (int32_t*)(base + o_ku); D.ctl = (int*)(base + o_ctl); D.bt_skip = (uint8_t*)(base + o_skip);
     D.user = (int64_t*)(base + o_user); D.vec_dst = (int64_t*)(base + o_vd); D.lam_dst = (int64_t*)(base + o_ldst);
     D.n_arr = (int32_t*)(base + o_n); D.ld_arr = (int32_t*)(base + o_ld); D.moff_arr = (int64_t*)(base + o_moff);
     D.ioff_arr = (int64_t*)(base + o_ioff); D.roff_arr = (int64_t*)(base + o_roff); D.voff_arr = (int64_t*)(base + o_voff);
@@ -366,6 +367,172 @@ static int hh_tc_plan(gsi_ctx* ctx, const HhPlan& pl, HhTcPlan& TC) {
     return GSI_OK;
 }
 
+// ---- back-transformation of the big users on the tensor-core engine (kern_bt_tc.cuh) ------------------------------------------
+// users with n >= this take it (GSI_BT_TC_MIN; 0 = never, the default).  Jobs are sorted by n descending: they are a prefix of the
+// chunk.  Measured on the ML-10M shape (profiles/r02n_bt_tc.md): with GSI_BT_TC_MIN=3072 the 49 biggest users' back-transform takes
+// 399 ms on the engine against ~460 ms on the DMMA kernel (bt class 935 -> 875 ms per step, step -1.0 %), but the host path loses
+// the overlap of their records' copy with the back-transform of the next group (e2e 12,146 -> 11,858 users/s).  Not a default yet:
+// the K = 512 update GEMM re-reads 768 KB of INT8 planes per 128 x 64 tile and sits on the L2 -> SM bandwidth, not on the MMA rate.
+static int hh_bt_tc_min() { const char* e = getenv("GSI_BT_TC_MIN"); return e ? atoi(e) : 0; }
+
+static int hh_bt_tc(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D) {
+    Workspace& ws = WS(ctx);
+    cudaStream_t st = ctx->stream;
+    const int tmin = hh_bt_tc_min();
+    int nu = 0;
+    if (tmin > 0) while (nu < pl.nj && pl.jobs[nu].n >= tmin) ++nu;
+    GSI_CUDA(ctx, cudaMemsetAsync(D.bt_skip, 0, (size_t)pl.nj, st));
+    if (nu == 0) return GSI_OK;
+    int S = 8;
+    if (const char* e = getenv("GSI_TC_SLICES")) S = std::min(8, std::max(6, atoi(e)));
+    const int64_t budget = std::min<int64_t>((int64_t)8 << 30, std::max<int64_t>(ctx->ws_limit / 8, (int64_t)256 << 20));
+    // ---- super-panels
+    std::vector<BttSp> sps;
+    std::vector<int> sp_first(nu + 1, 0);
+    int max_nsp = 0;
+    for (int u = 0; u < nu; ++u) {
+        const int nrefl = pl.jobs[u].n - 1;
+        sp_first[u] = (int)sps.size();
+        for (int j0 = 0; j0 < nrefl; j0 += BTT_NB) sps.push_back(BttSp{u, j0, std::min(BTT_NB, nrefl - j0), 0, (int64_t)sps.size() * BTT_NB * BTT_NB});
+        max_nsp = std::max(max_nsp, (int)sps.size() - sp_first[u]);
+    }
+    sp_first[nu] = (int)sps.size();
+    const int nsp = (int)sps.size();
+    int rc;
+    if ((rc = ws.btt_gt.ensure(ctx, (size_t)nsp * BTT_NB * BTT_NB * 8)) != GSI_OK) return rc;
+    std::vector<int64_t> x_off(nu + 1, 0);
+    for (int u = 0; u < nu; ++u) x_off[u + 1] = x_off[u] + (int64_t)BTT_NB * pl.jobs[u].np;
+    if ((rc = ws.btt_x.ensure(ctx, (size_t)x_off[nu] * 8)) != GSI_OK) return rc;
+    double* GT = ws.btt_gt.as<double>();
+    double* X = ws.btt_x.as<double>();
+    // ---- task list: batches of (tasks..., sentinel); planes / exponents are sub-allocated per batch from shared buffers
+    struct Batch { int first, ntasks, Mmax, Nmax, Kmax; };
+    std::vector<TcTask> tasks;
+    std::vector<int32_t> task_job;
+    std::vector<Batch> b_g, b_vt;
+    std::vector<std::vector<Batch>> b_x(max_nsp), b_u(max_nsp);
+    int64_t planes_max = 0, expo_max = 0;
+    int8_t* planes = nullptr;       // filled in after the buffers exist: offsets are kept in the pointer fields until then
+    struct Open { Batch b; int64_t used, eused; };
+    auto begin = [&]() { Open o; o.b = Batch{(int)tasks.size(), 0, 0, 0, 0}; o.used = 0; o.eused = 0; return o; };
+    auto close = [&](Open& o, std::vector<Batch>& dst) {
+        if (o.b.ntasks == 0) return;
+        TcTask z; memset(&z, 0, sizeof z);
+        tasks.push_back(z); task_job.push_back(-1);                       // sentinel
+        dst.push_back(o.b);
+        planes_max = std::max(planes_max, o.used); expo_max = std::max(expo_max, o.eused);
+        o = begin();
+    };
+    auto add = [&](Open& o, std::vector<Batch>& dst, TcTask t, int job_for_n, int Nbound) {
+        const int64_t need = (int64_t)tc_gemm_plane_bytes_a(t.M, t.K, S) + (int64_t)tc_gemm_plane_bytes_b(t.K, Nbound, S);
+        if (o.b.ntasks > 0 && o.used + need > budget) close(o, dst);
+        t.Ap = (int8_t*)(intptr_t)o.used; o.used += (int64_t)tc_gemm_plane_bytes_a(t.M, t.K, S);
+        t.Bp = (int8_t*)(intptr_t)o.used; o.used += (int64_t)tc_gemm_plane_bytes_b(t.K, Nbound, S);
+        t.ea = (int32_t*)(intptr_t)(o.eused * 4); t.eb = (int32_t*)(intptr_t)((o.eused + t.M) * 4); o.eused += t.M + Nbound;
+        t.N = Nbound;                                                      // replaced by kuser on the device where job_for_n >= 0
+        tasks.push_back(t); task_job.push_back(job_for_n);
+        ++o.b.ntasks;
+        o.b.Mmax = std::max(o.b.Mmax, t.M); o.b.Nmax = std::max(o.b.Nmax, Nbound); o.b.Kmax = std::max(o.b.Kmax, t.K);
+    };
+    auto vfull = [&](int u) { return ((pl.jobs[u].levels & 1) ? D.Qa : D.Qb) + pl.jobs[u].m_off; };
+    auto zbuf = [&](int u) { return ((pl.jobs[u].levels & 1) ? D.Qb : D.Qa) + pl.jobs[u].m_off; };
+    {   // G = V^T V and VT = V T of every super-panel
+        Open og = begin();
+        for (const BttSp& sp : sps) {
+            const HJob& jb = pl.jobs[sp.job];
+            TcTask t; memset(&t, 0, sizeof t);
+            const double* Vb = vfull(sp.job) + (size_t)sp.j0 * jb.np + sp.j0;
+            t.A = Vb; t.lda = jb.np; t.flags = TC_TRANS_A | TC_UNIT_A | TC_UNIT_B; t.B = Vb; t.ldb = jb.np; t.C = GT + sp.g_off; t.ldc = BTT_NB;
+            t.M = sp.nb; t.K = jb.n - sp.j0;
+            add(og, b_g, t, -1, sp.nb);
+        }
+        close(og, b_g);
+        Open ov = begin();
+        for (const BttSp& sp : sps) {
+            const HJob& jb = pl.jobs[sp.job];
+            TcTask t; memset(&t, 0, sizeof t);
+            t.A = vfull(sp.job) + (size_t)sp.j0 * jb.np + sp.j0; t.lda = jb.np; t.flags = TC_UNIT_A; t.B = GT + sp.g_off; t.ldb = BTT_NB;
+            t.C = D.S + jb.m_off + (size_t)sp.j0 * jb.np + sp.j0; t.ldc = jb.np;
+            t.M = jb.n - sp.j0; t.K = sp.nb;
+            add(ov, b_vt, t, -1, sp.nb);
+        }
+        close(ov, b_vt);
+    }
+    for (int s = 0; s < max_nsp; ++s) {   // step s: every user's s-th super-panel from the end
+        Open ox = begin();
+        for (int u = 0; u < nu; ++u) {
+            const int cnt = sp_first[u + 1] - sp_first[u];
+            if (s >= cnt) continue;
+            const BttSp& sp = sps[sp_first[u] + cnt - 1 - s];
+            const HJob& jb = pl.jobs[u];
+            TcTask t; memset(&t, 0, sizeof t);
+            t.A = vfull(u) + (size_t)sp.j0 * jb.np + sp.j0; t.lda = jb.np; t.flags = TC_TRANS_A | TC_UNIT_A | TC_UNIT_B;
+            t.B = zbuf(u) + sp.j0; t.ldb = jb.np; t.C = X + x_off[u]; t.ldc = BTT_NB;
+            t.M = sp.nb; t.K = jb.n - sp.j0;
+            add(ox, b_x[s], t, u, jb.n);
+        }
+        close(ox, b_x[s]);
+        Open ou = begin();
+        for (int u = 0; u < nu; ++u) {
+            const int cnt = sp_first[u + 1] - sp_first[u];
+            if (s >= cnt) continue;
+            const BttSp& sp = sps[sp_first[u] + cnt - 1 - s];
+            const HJob& jb = pl.jobs[u];
+            TcTask t; memset(&t, 0, sizeof t);
+            t.A = D.S + jb.m_off + (size_t)sp.j0 * jb.np + sp.j0; t.lda = jb.np;
+            t.B = X + x_off[u]; t.ldb = BTT_NB; t.C = zbuf(u) + sp.j0; t.ldc = jb.np; t.flags = TC_SUB_C;
+            t.M = jb.n - sp.j0; t.K = sp.nb;
+            add(ou, b_u[s], t, u, jb.n);
+        }
+        close(ou, b_u[s]);
+    }
+    if ((rc = ws.btt_planes.ensure(ctx, (size_t)planes_max)) != GSI_OK) return rc;
+    if ((rc = ws.btt_expo.ensure(ctx, (size_t)expo_max * 4)) != GSI_OK) return rc;
+    planes = ws.btt_planes.as<int8_t>();
+    int32_t* expo = ws.btt_expo.as<int32_t>();
+    for (size_t t = 0; t < tasks.size(); ++t) {
+        if (!tasks[t].A) continue;                                          // sentinel
+        tasks[t].Ap = planes + (intptr_t)tasks[t].Ap; tasks[t].Bp = planes + (intptr_t)tasks[t].Bp;
+        tasks[t].ea = (int32_t*)((char*)expo + (intptr_t)tasks[t].ea); tasks[t].eb = (int32_t*)((char*)expo + (intptr_t)tasks[t].eb);
+    }
+    MetaBuilder mb;
+    const size_t o_t = mb.add(tasks), o_j = mb.add(task_job), o_sp = mb.add(sps);
+    if ((rc = ws.btt_meta.ensure(ctx, mb.host.size())) != GSI_OK) return rc;
+    GSI_CUDA(ctx, cudaMemcpyAsync(ws.btt_meta.p, mb.host.data(), mb.host.size(), cudaMemcpyHostToDevice, st));
+    GSI_CUDA(ctx, cudaStreamSynchronize(st));                                 // mb.host is a local
+    TcTask* d_tasks = (TcTask*)(ws.btt_meta.as<char>() + o_t);
+    const int32_t* d_tjob = (const int32_t*)(ws.btt_meta.as<char>() + o_j);
+    const BttSp* d_sps = (const BttSp*)(ws.btt_meta.as<char>() + o_sp);
+    auto run = [&](const Batch& b) -> int {
+        TcBatch B;
+        B.tasks = d_tasks + b.first; B.ntasks = b.ntasks; B.Mmax = b.Mmax; B.Nmax = b.Nmax; B.Kmax = b.Kmax; B.S = S;
+        GSI_CUDA(ctx, tc_gemm_batch(B, st, ctx->sm_count));
+        return GSI_OK;
+    };
+    size_t nbatches = b_g.size() + b_vt.size();
+    for (int s = 0; s < max_nsp; ++s) nbatches += b_x[s].size() + b_u[s].size();
+    GsiSpan span(ctx, GSI_T_BT, 3 + 7 * (int64_t)nbatches);
+    HhTrace tr(ctx, "bt on the tcgen05 engine");
+    if (ctx->trace) fprintf(stderr, "[gsi trace] tcgen05 back-transform: %d users n >= %d, %d super-panels, %zu tasks in %zu batches, planes %.2f GB\n", nu,
+                            tmin, nsp, tasks.size(), nbatches, planes_max / 1073741824.0);
+    GSI_CUDA(ctx, cudaMemsetAsync(D.bt_skip, 1, (size_t)nu, st));
+    btt_set_n_kernel<<<((int)tasks.size() + 255) / 256, 256, 0, st>>>(d_tasks, d_tjob, (int)tasks.size(), D.kuser);
+    const int NTmax = pl.jobs[0].np >> 6;
+    btt_extract_kernel<<<dim3(NTmax * NTmax, nu), 256, 0, st>>>(D.jobs, nu, NTmax, D.A, D.Qa, D.Qb);
+    GSI_CUDA(ctx, cudaMemsetAsync(GT, 0, (size_t)nsp * BTT_NB * BTT_NB * 8, st));
+    for (const Batch& b : b_g) if ((rc = run(b)) != GSI_OK) return rc;
+    GSI_CUDA(ctx, cudaFuncSetAttribute(btt_formt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)btt_formt_smem_bytes()));
+    btt_formt_kernel<<<nsp, 256, btt_formt_smem_bytes(), st>>>(D.jobs, d_sps, D.tau, GT);
+    for (const Batch& b : b_vt) if ((rc = run(b)) != GSI_OK) return rc;
+    for (int s = 0; s < max_nsp; ++s) {
+        for (const Batch& b : b_x[s]) if ((rc = run(b)) != GSI_OK) return rc;
+        for (const Batch& b : b_u[s]) if ((rc = run(b)) != GSI_OK) return rc;
+    }
+    span.end();
+    GSI_CUDA(ctx, cudaGetLastError());
+    return GSI_OK;
+}
+
 static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_team, bool defer_bt_apply = false) {
     cudaStream_t st = ctx->stream;
     const int nj = pl.nj;
@@ -440,7 +607,8 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
     if (SB.nu > 0 && (rc = sbr_bt2(ctx, D, SB.st2)) != GSI_OK) return rc;
     BtParams B;
     B.jobs = D.jobs; B.njobs = nj; B.A = D.A; B.tau = D.tau; B.S = D.S; B.Qa = D.Qa; B.Qb = D.Qb; B.kuser = D.kuser;
-    B.items = D.bt_items; B.nitems = (int)pl.bt_items.size(); B.queue = D.ctl + 8;
+    B.items = D.bt_items; B.nitems = (int)pl.bt_items.size(); B.queue = D.ctl + 8; B.skip = D.bt_skip;
+    if ((rc = hh_bt_tc(ctx, pl, D)) != GSI_OK) return rc;            // the big users: aggregated panels on the tcgen05 engine
     {
         GsiSpan sp(ctx, GSI_T_BT, 2);
         GSI_CUDA(ctx, cudaFuncSetAttribute(bt_formt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_formt_smem_bytes()));
@@ -457,7 +625,7 @@ static int hh_solve(gsi_ctx* ctx, const HhPlan& pl, const HhDev& D, int forced_t
 static BtParams hh_bt_params(const HhPlan& pl, const HhDev& D) {
     BtParams B;
     B.jobs = D.jobs; B.njobs = pl.nj; B.A = D.A; B.tau = D.tau; B.S = D.S; B.Qa = D.Qa; B.Qb = D.Qb; B.kuser = D.kuser;
-    B.items = D.bt_items; B.nitems = (int)pl.bt_items.size(); B.queue = D.ctl + 8;
+    B.items = D.bt_items; B.nitems = (int)pl.bt_items.size(); B.queue = D.ctl + 8; B.skip = D.bt_skip;
     return B;
 }
 

@@ -30,12 +30,14 @@ struct BtParams {
     const int2* items;    // (job, column block), sorted by cost descending
     int nitems;
     int* queue;
+    const uint8_t* skip;  // optional [jobs]: 1 = this user's back-transform ran on the tensor-core engine (kern_bt_tc.cuh)
 };
 
 // grid (max panels, njobs), block 256, dynamic smem 3 * 64*65 doubles
 static inline size_t bt_formt_smem_bytes() { return (size_t)3 * 64 * 65 * sizeof(double); }
 __global__ void __launch_bounds__(256) bt_formt_kernel(BtParams P) {
     extern __shared__ __align__(16) double formt_smem[];
+    if (P.skip && P.skip[blockIdx.y]) return;
     const HJob jb = P.jobs[blockIdx.y];
     const int n = jb.n, np = jb.np, ld = jb.np;
     const int j0 = blockIdx.x * BT_NB;
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(256, 1) bt_apply_kernel(BtParams P) {
         const int it = item_s;
         if (it >= P.nitems) break;
         const int2 item = P.items[it];
+        if (P.skip && P.skip[item.x]) continue;
         const HJob jb = P.jobs[item.x];
         const int lim = P.kuser[item.x];
         const int c0 = item.y * BT_CB;

@@ -125,11 +125,11 @@ __global__ void __launch_bounds__(256) tc_exp_init_kernel(const TcTask* __restri
 __global__ void __launch_bounds__(256) tc_row_exp_kernel(const TcTask* __restrict__ tasks) {
     const TcTask T = tasks[blockIdx.z];
     const int kb = blockIdx.x, i = blockIdx.y * 128 + (threadIdx.x & 127), half = threadIdx.x >> 7;
-    if (kb * 64 >= T.K || i >= T.M) return;
+    if (kb * 64 >= T.K || i >= T.M || (T.flags & TC_UNIT_A)) return;
     int e = TC_EXP_NONE;
     for (int q = 0; q < 32; ++q) {
         const int k = kb * 64 + half * 32 + q;
-        if (k < T.K) e = max(e, tc_elem_exp(T.A[(size_t)(T.gather ? T.gather[k] : k) * T.lda + i]));
+        if (k < T.K) e = max(e, tc_elem_exp((T.flags & TC_TRANS_A) ? T.A[(size_t)i * T.lda + k] : T.A[(size_t)(T.gather ? T.gather[k] : k) * T.lda + i]));
     }
     if (e != TC_EXP_NONE) atomicMax(T.ea + i, e);
 }
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) tc_row_exp_kernel(const TcTask* __restric
 __global__ void __launch_bounds__(256) tc_col_exp_kernel(const TcTask* __restrict__ tasks) {
     const TcTask T = tasks[blockIdx.z];
     const int kb = blockIdx.x, j = blockIdx.y * 64 + (threadIdx.x & 63), chunk = threadIdx.x >> 6;
-    if (kb * 64 >= T.K || j >= T.N) return;
+    if (kb * 64 >= T.K || j >= T.N || (T.flags & TC_UNIT_B)) return;
     int e = TC_EXP_NONE;
     const double* col = T.B + (size_t)j * T.ldb;
     for (int q = 0; q < 16; ++q) {
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) tc_slice_a_kernel(const TcTask* __restric
     if (kb >= nkb || mt * 128 >= T.M) return;
     const int i = mt * 128 + r;
     int8_t* base = T.Ap + ((size_t)mt * nkb + kb) * (size_t)(S * 8192);
-    const int e = (i < T.M) ? tc_line_exp(T.ea[i]) : 0;
+    const int e = (T.flags & TC_UNIT_A) ? 1 : ((i < T.M) ? tc_line_exp(T.ea[i]) : 0);
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {                                // two 16-byte k chunks per thread
         const int chunk = half * 2 + c;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) tc_slice_a_kernel(const TcTask* __restric
         for (int q = 0; q < 16; ++q) {
             const int k = kb * 64 + chunk * 16 + q;
             double x = 0.0;
-            if (i < T.M && k < T.K) x = T.A[(size_t)(T.gather ? T.gather[k] : k) * T.lda + i];
+            if (i < T.M && k < T.K) x = (T.flags & TC_TRANS_A) ? T.A[(size_t)i * T.lda + k] : T.A[(size_t)(T.gather ? T.gather[k] : k) * T.lda + i];
             int8_t d[S];
             tc_digits<S>(x, e, d);
 #pragma unroll
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256) tc_slice_b_kernel(const TcTask* __restric
     if (kb >= nkb || nt * 64 >= T.N) return;
     const int j = nt * 64 + c;
     int8_t* base = T.Bp + ((size_t)nt * nkb + kb) * (size_t)(S * 4096);
-    const int e = (j < T.N) ? tc_line_exp(T.eb[j]) : 0;
+    const int e = (T.flags & TC_UNIT_B) ? 1 : ((j < T.N) ? tc_line_exp(T.eb[j]) : 0);
     __align__(16) int8_t dig[S][16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
@@ -356,7 +356,19 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_kernel(const TcTask* __restric
             mbar_wait(acc_full, tcount & 1);
             tc_fence_after();
             // C_ij = 2^(e_i + f_j - 2P) 128^(2S-2) sum_g G_g 128^-g,  P = 7S:  2^(e_i + f_j - 14) per unit of the Horner sum
-            const double rs = (i < T.M) ? ldexp(1.0, tc_line_exp(T.ea[i]) - 7 - 7 * S) : 0.0;
+            const double rs = (i < T.M) ? ldexp(1.0, ((T.flags & TC_UNIT_A) ? 1 : tc_line_exp(T.ea[i])) - 7 - 7 * S) : 0.0;
+            // C -= product: the 64 old values of this thread's row are requested before the accumulators are read, so that their
+            // latency hides behind the tensor-memory loads instead of serialising load / store pairs column by column
+            const bool sub = (T.flags & TC_SUB_C) != 0;
+            double cold[64];
+            if (sub) {
+#pragma unroll
+                for (int q = 0; q < 64; ++q) {
+                    const int j = tl.nt * 64 + q;
+                    cold[q] = (i < T.M && j < T.N) ? T.C[(size_t)(T.scatter ? T.scatter[j] : j) * T.ldc + i] : 0.0;
+                }
+            }
+#pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 16) {
                 double acc[16];
 #pragma unroll
@@ -374,9 +386,10 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_kernel(const TcTask* __restric
                     for (int q = 0; q < 16; ++q) {
                         const int j = tl.nt * 64 + c0 + q;
                         if (j < T.N) {
-                            const double val = (tl.nkb > 0) ? acc[q] * rs * ldexp(1.0, tc_line_exp(T.eb[j]) - 7 + 7 * S) : 0.0;
+                            const int eb = (T.flags & TC_UNIT_B) ? 1 : tc_line_exp(T.eb[j]);
+                            const double val = (tl.nkb > 0) ? acc[q] * rs * ldexp(1.0, eb - 7 + 7 * S) : 0.0;
                             const int jo = T.scatter ? T.scatter[j] : j;
-                            T.C[(size_t)jo * T.ldc + i] = val;
+                            T.C[(size_t)jo * T.ldc + i] = sub ? cold[c0 + q] - val : val;
                         }
                     }
                 }

@@ -14,7 +14,12 @@ struct TcTask {
     int8_t* Ap; int8_t* Bp;                 // slice planes, sized by tc_gemm_plane_bytes_a / _b of the task's UPPER bounds
     int32_t* ea; int32_t* eb;               // row exponents of A [M], column exponents of B [N]
     int M, N, K, tile0;
+    int flags, pad_;                        // TC_TRANS_A: element (i, k) of the left operand is A[i * lda + k] (gather unused); TC_SUB_C: C -= product
 };
+#define TC_TRANS_A 1
+#define TC_SUB_C 2
+#define TC_UNIT_A 4                         // every entry of the left / right operand is at most 1 in magnitude (orthonormal columns,
+#define TC_UNIT_B 8                         // Householder vectors with unit head): fixed exponent 1, no exponent scan
 
 struct TcBatch {
     TcTask* tasks; int ntasks;              // device pointer

@@ -66,3 +66,31 @@ def test_zero_rows_and_identity(ctx):
     b = np.eye(70)
     c, _, _ = ctx.debug_tc_gemm(a, b, slices=8)
     assert np.array_equal(c, a)
+
+
+@pytest.mark.parametrize("n,sbr", [(700, False), (1100, False), (1537, False), (1100, True)])
+def test_back_transform_on_the_engine(ctx, monkeypatch, n, sbr):
+    """Back-transformation with aggregated 512-reflector panels on the tcgen05 engine (kern_bt_tc.cuh: G = V^T V, T from G,
+    VT = V T, then X = V^T Z and Z -= VT X per super-panel) instead of the 64-reflector DMMA kernel: eigenpairs of a normalised
+    Laplacian through gsi_debug_eigh with the switch-over lowered (GSI_BT_TC_MIN), one-stage and two-stage reflector layouts,
+    sizes with a short last super-panel.  Same bars as the stage tests: eigenvalues 1e-12, residual / orthonormality 1e-11."""
+    from oracle import gsi_oracle as O
+    monkeypatch.setenv("GSI_BT_TC_MIN", "600")
+    if sbr:
+        monkeypatch.setenv("GSI_SBR_MIN", "600")
+    rng = np.random.default_rng(5 + n)
+    w = np.triu((rng.random((n, n)) < 0.8) * (0.5 + 0.5 * rng.random((n, n))), 1)
+    w = w + w.T
+    _, _, ll2 = O.normalized_laplacian(w)
+    a = np.tril(ll2) + np.tril(ll2, -1).T
+    lam_ref, _ = O.eig_lower(a)
+    thr = float(np.float32(np.median(lam_ref) + 0.013))
+    r = ctx.debug_eigh(a, thr=thr, team=0)
+    k_ref = max(2, int((lam_ref <= np.float32(thr)).sum()))
+    assert r["k"] == k_ref and np.abs(r["lam"] - lam_ref).max() < 1e-12
+    u = r["u"]
+    assert np.abs(a @ u - u * r["lam"][:k_ref]).max() < 1e-11
+    assert np.abs(u.T @ u - np.eye(k_ref)).max() < 1e-11
+    monkeypatch.setenv("GSI_BT_TC_MIN", "0")                         # the DMMA kernel on the same matrix: same vectors up to rounding
+    r2 = ctx.debug_eigh(a, thr=thr, team=0)
+    assert np.abs(np.abs(r2["u"]) - np.abs(u)).max() < 1e-9
