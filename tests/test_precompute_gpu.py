@@ -60,7 +60,7 @@ def test_weights_from_edges_equals_dense(ctx, golden_dir):
 
 def test_ml100k_shape_sample_vs_oracle(ctx):
     """Seeded ML-100K shaped users against the oracle: every size bucket of the
-    CTA-resident solver and the block-Jacobi path (n > 160)."""
+    CTA-resident solver and the Householder path (n > 160)."""
     from collaborative_filtering_b200 import datasets as D
     from tests.parity import check_records
     r = D.make_ratings("ml-100k")
@@ -131,8 +131,8 @@ def test_error_paths(ctx):
 
 
 def test_large_path_vs_oracle(ctx):
-    """Block-Jacobi path at sizes the oracle still finishes in seconds (n = 161 .. 700): mixed
-    sizes in one call, ids beyond the table and an isolated item."""
+    """Householder / divide & conquer path at sizes the oracle still finishes in seconds (n = 161 .. 700: shared-memory and
+    persistent tridiagonalisation kernels): mixed sizes in one call, ids beyond the table and an isolated item."""
     from tests.parity import check_records
     rng = np.random.default_rng(31413)
     n_items = 900
@@ -151,6 +151,32 @@ def test_large_path_vs_oracle(ctx):
     ctx.set_weights(w)
     recs = ctx.precompute(offsets, items)
     check_records(recs, w, tag="large")
+
+
+def test_block_jacobi_route_vs_oracle():
+    """The first large path (kern_bj.cuh, one-sided block Jacobi) is still reachable behind GSI_LARGE=bj (comparison runs) and
+    for n > 9,216 when the two-stage path is switched off (GSI_SBR_MIN=0): it must stay correct.  Same records as the
+    Householder path to the parity bars (k exact, eigenvalues 1e-10, residual / orthonormality 1e-9, sig_min bit-exact)."""
+    from tests.parity import check_records
+    rng = np.random.default_rng(77)
+    n_items = 500
+    w = np.round(1.0 - 0.5 * rng.random((n_items + 1, n_items + 1)), 6)
+    w = np.where(rng.random(w.shape) < 0.8, w, 0.0)
+    w = np.triu(w, 1)
+    w = w + w.T
+    w[0] = 0
+    w[:, 0] = 0
+    sizes = [161, 200, 257, 300, 64, 12]
+    lists = [np.sort(rng.choice(np.arange(1, n_items + 1), n, replace=False)).astype(np.int32) for n in sizes]
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    items = np.concatenate(lists)
+    c = _fresh_context({"GSI_LARGE": "bj"})
+    try:
+        c.set_weights(w)
+        recs = c.precompute(offsets, items)
+        check_records(recs, w, tag="bj")
+    finally:
+        c.close()
 
 
 def _fresh_context(env):
