@@ -135,10 +135,21 @@ extern "C" int gsi_create(gsi_ctx** out, int device, void* stream) {
                         cudaGetErrorString(e));
     if (device < 0 || device >= ndev) return gsi_fail(nullptr, GSI_ERR_INVALID, "gsi_create: device %d of %d", device, ndev);
     gsi_ctx_full* ctx = new gsi_ctx_full();
+    // a failure below must not leak the half-built context (and its message has to outlive it: thread-local, gsi_last_error(NULL))
+#define CREATE_CUDA(call)                                                                                              \
+    do {                                                                                                               \
+        cudaError_t e_ = (call);                                                                                       \
+        if (e_ != cudaSuccess) {                                                                                       \
+            const int rc_ = gsi_fail(nullptr, GSI_ERR_CUDA, "gsi_create: %s: %s", #call, cudaGetErrorString(e_));     \
+            if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);                                        \
+            delete ctx;                                                                                                \
+            return rc_;                                                                                                \
+        }                                                                                                              \
+    } while (0)
     ctx->device = device;
-    GSI_CUDA(ctx, cudaSetDevice(device));
+    CREATE_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
-    GSI_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+    CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) {
         int rc = gsi_fail(nullptr, GSI_ERR_CUDA, "gsi_create: device %d is sm_%d%d; libgsi is built for sm_100a only", device, prop.major, prop.minor);
         delete ctx;
@@ -146,12 +157,12 @@ extern "C" int gsi_create(gsi_ctx** out, int device, void* stream) {
     }
     ctx->sm_count = prop.multiProcessorCount;
     if (stream) ctx->stream = (cudaStream_t)stream;
-    else { GSI_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
-    GSI_CUDA(ctx, set_smem_attr<1>());
-    GSI_CUDA(ctx, set_smem_attr<2>());
-    GSI_CUDA(ctx, set_smem_attr<3>());
-    GSI_CUDA(ctx, set_smem_attr<4>());
-    GSI_CUDA(ctx, set_smem_attr<5>());
+    else { CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    CREATE_CUDA(set_smem_attr<1>());
+    CREATE_CUDA(set_smem_attr<2>());
+    CREATE_CUDA(set_smem_attr<3>());
+    CREATE_CUDA(set_smem_attr<4>());
+    CREATE_CUDA(set_smem_attr<5>());
     const char* bm = getenv("GSI_BJ_M");
     ctx->bj_m = (bm && atoi(bm) == 32) ? 32 : 64;
     const char* lp = getenv("GSI_LARGE");          // "bj": one-sided block Jacobi (kept for comparison); default Householder + D&C
@@ -159,7 +170,8 @@ extern "C" int gsi_create(gsi_ctx** out, int device, void* stream) {
     if (const char* sm = getenv("GSI_SMALL_MAX")) ctx->small_max = std::min(GSI_S_MAX_N, std::max(32, atoi(sm)));
     const char* tr = getenv("GSI_TRACE");
     ctx->trace = tr && atoi(tr) != 0;
-    GSI_CUDA(ctx, cudaFuncSetAttribute(bj_inner_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 65 * 8));
+    CREATE_CUDA(cudaFuncSetAttribute(bj_inner_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 65 * 8));
+#undef CREATE_CUDA
     *out = ctx;
     return GSI_OK;
 }
@@ -244,17 +256,19 @@ extern "C" int gsi_set_weights_edges(gsi_ctx* ctx, const int32_t* m1, const int3
     ctx->own_w = true; ctx->w_rows = rows;
     GSI_CUDA(ctx, cudaMemsetAsync(ctx->d_w, 0, (size_t)rows * rows * sizeof(double), ctx->stream));
     if (ne > 0) {
-        int32_t *da, *db; double* dw;
-        GSI_CUDA(ctx, cudaMalloc((void**)&da, ne * 4));
-        GSI_CUDA(ctx, cudaMalloc((void**)&db, ne * 4));
-        GSI_CUDA(ctx, cudaMalloc((void**)&dw, ne * 8));
-        GSI_CUDA(ctx, cudaMemcpyAsync(da, m1, ne * 4, cudaMemcpyHostToDevice, ctx->stream));
-        GSI_CUDA(ctx, cudaMemcpyAsync(db, m2, ne * 4, cudaMemcpyHostToDevice, ctx->stream));
-        GSI_CUDA(ctx, cudaMemcpyAsync(dw, w, ne * 8, cudaMemcpyHostToDevice, ctx->stream));
-        scatter_edges_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(da, db, dw, ne, ctx->d_w, rows);
+        struct Tmp {                                                // freed on every exit path
+            int32_t *da = nullptr, *db = nullptr; double* dw = nullptr;
+            ~Tmp() { cudaFree(da); cudaFree(db); cudaFree(dw); }
+        } t;
+        GSI_CUDA(ctx, cudaMalloc((void**)&t.da, ne * 4));
+        GSI_CUDA(ctx, cudaMalloc((void**)&t.db, ne * 4));
+        GSI_CUDA(ctx, cudaMalloc((void**)&t.dw, ne * 8));
+        GSI_CUDA(ctx, cudaMemcpyAsync(t.da, m1, ne * 4, cudaMemcpyHostToDevice, ctx->stream));
+        GSI_CUDA(ctx, cudaMemcpyAsync(t.db, m2, ne * 4, cudaMemcpyHostToDevice, ctx->stream));
+        GSI_CUDA(ctx, cudaMemcpyAsync(t.dw, w, ne * 8, cudaMemcpyHostToDevice, ctx->stream));
+        scatter_edges_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(t.da, t.db, t.dw, ne, ctx->d_w, rows);
         GSI_CUDA(ctx, cudaGetLastError());
         GSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(da); cudaFree(db); cudaFree(dw);
     }
     if (rows_out) *rows_out = rows;
     return GSI_OK;
