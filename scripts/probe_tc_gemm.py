@@ -16,7 +16,7 @@ quick = "--quick" in sys.argv
 ctx = Context(0)
 out = {"fp64_fma_tflops": ctx.measure_fp64_tflops(False), "fp64_dmma_tflops": ctx.measure_fp64_tflops(True), "shapes": []}
 rng = np.random.default_rng(1)
-shapes = [(2048, 2048, 2048)] if quick else [(1024, 1024, 1024), (2048, 2048, 2048), (4096, 4096, 4096), (3712, 4416, 3008), (7424, 4416, 3712), (4096, 4096, 512), (4096, 4096, 128)]
+shapes = [(4096, 4096, 4096)] if quick else [(1024, 1024, 1024), (2048, 2048, 2048), (4096, 4096, 4096), (3712, 4416, 3008), (7424, 4416, 3712), (4096, 4096, 512), (4096, 4096, 128)]
 for (m, n, k) in shapes:
     a = rng.standard_normal((m, k)) / np.sqrt(k)
     b = rng.standard_normal((k, n)) / np.sqrt(k)
