@@ -181,7 +181,7 @@ int gsi_predict_device(gsi_ctx* ctx, int64_t n_users, const int64_t* h_offsets, 
  * How the cutoff is computed: lambda_min of P[unrated, unrated], P = L L^T per movie, by Lanczos through the movie's P
  * (no per-pair matrix); a pair whose Ritz value has not settled after 96 steps, and every pair when the environment
  * variable GSI_LC_EXACT=1 is set, is solved exactly instead (gathered matrix -> Householder tridiagonalisation ->
- * Sturm-count bracket).  Local graphs of more than 9,216 nodes are rejected with GSI_ERR_INVALID.  Neighbour order is
+ * Sturm-count bracket).  Local graphs of more than 9,216 nodes take the two-stage tridiagonalisation (46,000 nodes is the limit).  Neighbour order is
  * ascending movie id (the reference: hash order); where the two directions of an edge carry different weights the
  * reference's result depends on that order, with the bit-symmetric weights knn2 emits it does not. */
 int gsi_local_calc_host(gsi_ctx* ctx, int64_t n_users, const int64_t* offsets, const int32_t* items,
