@@ -9,6 +9,22 @@
 #include "../../include/gsi.h"
 
 #define GSI_WARP 32
+// In-kernel bounds checks for builds where compute-sanitizer is not available (it is closed on the pool this was developed on):
+// `make debug` compiles libgsi_debug.so with -DGSI_DEBUG_BOUNDS, a failed check prints the site and traps (the launch then fails
+// with an error the C ABI reports).  Off in the product build: the macro expands to nothing.
+#ifdef GSI_DEBUG_BOUNDS
+#include <stdio.h>
+#define GSI_BOUNDS(cond)                                                                                          \
+    do {                                                                                                          \
+        if (!(cond)) {                                                                                            \
+            printf("gsi bounds check failed: %s  (%s:%d, block %d,%d,%d thread %d)\n", #cond, __FILE__, __LINE__, \
+                   (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)threadIdx.x);                          \
+            __trap();                                                                                             \
+        }                                                                                                         \
+    } while (0)
+#else
+#define GSI_BOUNDS(cond) ((void)0)
+#endif
 // One-sided Jacobi thresholds (fp64).  A pair is rotated when gamma^2 > ROT2 * alpha * beta; a
 // sweep whose largest pre-rotation ratio^2 is <= STOP2 is the last one (quadratic convergence:
 // a 3e-8 ratio before the sweep leaves ~1e-15 after it).

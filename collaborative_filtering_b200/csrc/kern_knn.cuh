@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(256) knn_row_kernel(const int64_t* __restrict_
             if (b == a || b >= c1) continue;
             const int cb = __float2int_rn(ratings[o + j] * 2.f);
             const int c = b - c0;
+            GSI_BOUNDS(c >= 0 && c < KNN_CT);
             atomicAdd(s_cnt + c, 1);
             atomicAdd(s_num + c, ca * cb);
             atomicAdd(s_ab + c, ca * ca);

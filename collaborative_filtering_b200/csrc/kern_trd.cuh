@@ -53,6 +53,9 @@ struct HJob {
 
 // element (r, c) of a tile-major np x np matrix with NT = np / 64 tiles per dimension
 __host__ __device__ __forceinline__ size_t hh_tidx(int r, int c, int NT) {
+#ifdef __CUDA_ARCH__
+    GSI_BOUNDS(r >= 0 && c >= 0 && (r >> 6) < NT && (c >> 6) < NT);
+#endif
     return (((size_t)(c >> 6) * NT + (r >> 6)) << 12) + ((c & 63) << 6) + (r & 63);
 }
 

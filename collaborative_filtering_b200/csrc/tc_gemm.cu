@@ -30,6 +30,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include "gsi_internal.cuh"
 #include "ptx.cuh"
 #include "tc_gemm.cuh"
 
@@ -298,6 +299,7 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_kernel(const TcTask* __restric
             int it = 0;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
                 const TcTile tl = tc_find_tile(tasks, ntasks, tile);
+                GSI_BOUNDS(tl.task >= 0 && tl.task < ntasks && tl.mt * 128 < tasks[tl.task].M && tl.nt * 64 < tasks[tl.task].N);
                 const int8_t* Ap = tasks[tl.task].Ap + (size_t)tl.mt * tl.nkb * SM::A_BYTES;
                 const int8_t* Bp = tasks[tl.task].Bp + (size_t)tl.nt * tl.nkb * SM::B_BYTES;
                 for (int kb = 0; kb < tl.nkb; ++kb, ++it) {
